@@ -1,0 +1,164 @@
+/* pcdgpu.h -- C ABI of libpcdgpu.so: the B200 (sm_100a) prover backend for the Groth16 proving
+ * step of arkworks-rs/pcd on the MNT4-298 / MNT6-298 cycle.
+ *
+ * This is the drop-in boundary: a Rust shim implementing ark-snark's `SNARK`
+ * trait binds exactly these entry points (INTEGRATION.md shows the `extern "C"` block).  The
+ * reference reaches the replaced code through
+ *     IC::MainSNARK::prove / IC::HelpSNARK::prove   /root/reference/src/ec_cycle_pcd/mod.rs:171,179
+ *     tiny default-circuit proves                   /root/reference/src/ec_cycle_pcd/data_structures.rs:139-143,343-350
+ * and the arithmetic itself lives in the un-vendored arkworks crates named per function below.
+ *
+ * Conventions
+ *   - every function returns 0 (PCDGPU_OK) or a negative PCDGPU_E_* code; nothing throws or aborts
+ *     across the boundary; pcdgpu_strerror() names a code, pcdgpu_last_error() gives detail.
+ *   - the caller owns every host buffer; device objects are opaque handles with explicit free.
+ *   - one context = one GPU + one stream set; a context must not be used from two host threads at
+ *     once.  There is NO CPU fallback: without a usable sm_100 device ctx_create fails.
+ *   - encodings are arkworks' in-memory ones so the shim copies, never converts:
+ *       field element  : 40 bytes, five little-endian u64 limbs of a*R mod p, R = 2^320
+ *                        (ark-ff Fp320 / BigInteger320)
+ *       MSM scalar     : 40 bytes, five little-endian u64 limbs of the plain integer
+ *                        (`into_repr()`); *_mont variants take Montgomery-form elements instead
+ *       affine point   : x || y (G1: 80 B; MNT4 G2 over Fq2: 160 B = x.c0 x.c1 y.c0 y.c1;
+ *                        MNT6 G2 over Fq3: 240 B); the point at infinity is x = y = 0
+ *       xyzz point     : X || Y || ZZ || ZZZ (x = X/ZZ, y = Y/ZZZ; infinity: ZZ = 0) -- only used
+ *                        for partial sums exchanged between GPUs
+ *   - functions with the _dev suffix take DEVICE pointers on the context's GPU and are
+ *     asynchronous on the context's stream (pcdgpu_sync() waits); the others take HOST pointers
+ *     and return when the result is in the host buffer.
+ */
+#ifndef PCDGPU_H
+#define PCDGPU_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+typedef struct pcdgpu_ctx pcdgpu_ctx;
+typedef struct pcdgpu_bases pcdgpu_bases; /* device-resident MSM base vector             */
+typedef struct pcdgpu_r1cs pcdgpu_r1cs;   /* device-resident CSR matrices A, B, C        */
+typedef struct pcdgpu_pk pcdgpu_pk;       /* device-resident Groth16 proving key         */
+
+enum {
+  PCDGPU_OK = 0,
+  PCDGPU_E_ARG = -1,       /* bad argument (null pointer, unknown id, size out of range)  */
+  PCDGPU_E_NODEVICE = -2,  /* no usable CUDA device (there is no CPU fallback)            */
+  PCDGPU_E_CUDA = -3,      /* a CUDA call failed; see pcdgpu_last_error()                 */
+  PCDGPU_E_DOMAIN = -4,    /* evaluation domain larger than the field's 2-adicity allows  */
+  PCDGPU_E_NOMEM = -5
+};
+
+/* scalar fields (ark-mnt4-298 Fr / ark-mnt6-298 Fr) */
+enum { PCDGPU_FIELD_R4 = 0, PCDGPU_FIELD_Q4 = 1 };
+/* pairings: MNT4-298 has Fr = r4, G1 over q4, G2 over Fq2; MNT6-298 has Fr = q4, G1 over r4, G2 over Fq3 */
+enum { PCDGPU_MNT4_298 = 0, PCDGPU_MNT6_298 = 1 };
+/* groups */
+enum { PCDGPU_MNT4_G1 = 0, PCDGPU_MNT4_G2 = 1, PCDGPU_MNT6_G1 = 2, PCDGPU_MNT6_G2 = 3 };
+
+const char* pcdgpu_strerror(int code);
+const char* pcdgpu_last_error(const pcdgpu_ctx* ctx);
+/* bytes of an affine point of `curve` (80 / 160 / 80 / 240) */
+size_t pcdgpu_affine_bytes(int curve);
+
+/* ---- context ------------------------------------------------------------------------------- */
+int pcdgpu_ctx_create(int device, pcdgpu_ctx** out);
+void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx);
+int pcdgpu_sync(pcdgpu_ctx* ctx);
+/* use a caller-owned CUDA stream (e.g. torch's current stream) instead of the context's own;
+ * stream = the cudaStream_t value; 0 restores the context's stream */
+int pcdgpu_set_stream(pcdgpu_ctx* ctx, void* stream);
+/* MSM window override (0 = automatic); exposed for benchmarking */
+int pcdgpu_set_msm_window(pcdgpu_ctx* ctx, int c);
+
+/* ---- radix-2 (coset) NTT --------------------------------------------------------------------
+ * Replaces ark-poly EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place on
+ * Radix2EvaluationDomain (natural order in and out; omega_n = TWO_ADIC_ROOT^(2^(s-log_n)); coset
+ * shift by GENERATOR = 10 (r4) / 17 (q4); ifft includes the 1/n scale).  data: 2^log_n elements,
+ * transformed in place.  log_n <= 34 (r4) / 17 (q4), else PCDGPU_E_DOMAIN. */
+int pcdgpu_ntt(pcdgpu_ctx* ctx, int field, void* data, uint32_t log_n, int inverse, int coset);
+int pcdgpu_ntt_dev(pcdgpu_ctx* ctx, int field, void* d_data, uint32_t log_n, int inverse, int coset);
+
+/* ---- variable-base MSM ----------------------------------------------------------------------
+ * Replaces ark-ec VariableBaseMSM::multi_scalar_mul(bases, scalars): sum_i scalars[i] * bases[i]
+ * over min(n_bases, n_scalars) pairs.  out_affine: one affine point (arkworks returns a
+ * projective point whose representation is algorithm dependent; callers compare / serialize
+ * after into_affine(), which is what is returned here). */
+int pcdgpu_msm(pcdgpu_ctx* ctx, int curve, const void* bases, const void* scalars, size_t n, void* out_affine);
+/* device pointers; scalars_mont != 0: scalars are Montgomery-form field elements (converted on
+ * the fly).  d_out_xyzz: one xyzz point in device memory (not normalised). */
+int pcdgpu_msm_dev(pcdgpu_ctx* ctx, int curve, const void* d_bases, const void* d_scalars, int scalars_mont,
+                   size_t n, void* d_out_xyzz);
+/* Resident base vectors (proving-key queries, KZG powers): uploaded once, reused by every MSM.
+ * precompute != 0 additionally stores 2^(c*j) * P for every window j so that all windows share
+ * one bucket set (no window-combination doubling chain; costs ~ceil(299/c) x the memory). */
+int pcdgpu_bases_upload(pcdgpu_ctx* ctx, int curve, const void* bases, size_t n, int precompute, pcdgpu_bases** out);
+void pcdgpu_bases_free(pcdgpu_bases* b);
+int pcdgpu_msm_bases(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* scalars, size_t n,
+                     void* out_affine);
+int pcdgpu_msm_bases_dev(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* d_scalars,
+                         int scalars_mont, size_t n, void* d_out_xyzz);
+/* sum of n xyzz partial sums (host buffers), normalised to affine: the gather step of a
+ * point-range sharded MSM */
+int pcdgpu_xyzz_sum(pcdgpu_ctx* ctx, int curve, const void* xyzz, size_t n, void* out_affine);
+/* copy an xyzz point from device to host (partials for the gather) */
+int pcdgpu_xyzz_download(pcdgpu_ctx* ctx, int curve, const void* d_xyzz, void* out_xyzz);
+
+/* ---- fixed-base batch multiplication --------------------------------------------------------
+ * out[i] = scalars[i] * base (affine).  Replaces ark-ec FixedBaseMSM::multi_scalar_mul as used by
+ * the Groth16 generator; here it builds proving keys and synthetic point sets. */
+int pcdgpu_fixed_base_mul(pcdgpu_ctx* ctx, int curve, const void* base, const void* scalars, size_t n, void* out);
+int pcdgpu_fixed_base_mul_dev(pcdgpu_ctx* ctx, int curve, const void* base_host, const void* d_scalars, size_t n,
+                              void* d_out);
+
+/* ---- R1CS -> QAP witness map ----------------------------------------------------------------
+ * Replaces ark-relations ConstraintSystem::to_matrices consumers + ark-groth16
+ * R1CStoQAP::witness_map.  Matrices are CSR: row_ptr[m + 1] (u32), col[nnz] (u32, instance
+ * variables first, column 0 is the constant 1), val[nnz] (field elements). */
+int pcdgpu_r1cs_upload(pcdgpu_ctx* ctx, int pairing, size_t num_constraints, size_t num_inputs, size_t num_witness,
+                       const uint32_t* a_ptr, const uint32_t* a_col, const void* a_val, const uint32_t* b_ptr,
+                       const uint32_t* b_col, const void* b_val, const uint32_t* c_ptr, const uint32_t* c_col,
+                       const void* c_val, pcdgpu_r1cs** out);
+void pcdgpu_r1cs_free(pcdgpu_r1cs* r);
+/* domain size n = next_pow2(num_constraints + num_inputs) of an uploaded system */
+size_t pcdgpu_r1cs_domain_size(const pcdgpu_r1cs* r);
+/* z: num_inputs + num_witness elements (instance || witness, z[0] = 1); h: n elements */
+int pcdgpu_witness_map(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* z, void* h);
+
+/* ---- Groth16 --------------------------------------------------------------------------------
+ * Replaces ark-groth16 create_proof_with_reduction (Groth16::prove).  The key is uploaded once
+ * (ProvingKey {vk.alpha_g1, beta_g1, delta_g1, vk.beta_g2, vk.delta_g2, a_query, b_g1_query,
+ * b_g2_query, h_query, l_query}); r and s are inputs so that the RNG and its draw order stay on the
+ * Rust side.  out_proof: A (G1 affine) || B (G2 affine) || C (G1 affine) = 320 B (MNT4) / 400 B
+ * (MNT6); pcdgpu_serialize_proof() gives ark-serialize's compressed bytes (152 / 190). */
+int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_inputs, size_t h_len,
+                     const void* alpha_g1, const void* beta_g1, const void* delta_g1, const void* beta_g2,
+                     const void* delta_g2, const void* a_query, const void* b_g1_query, const void* b_g2_query,
+                     const void* h_query, const void* l_query, int precompute, pcdgpu_pk** out);
+void pcdgpu_pk_free(pcdgpu_pk* pk);
+int pcdgpu_groth16_prove(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* z, const void* r,
+                         const void* s, void* out_proof);
+/* same with z already in device memory (Montgomery elements) */
+int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
+                             const void* r, const void* s, void* out_proof);
+/* Partial proof for a point-range shard [lo, hi) of every query (multi-GPU): the
+ * witness map runs on every rank; out_partials = 5 xyzz sums (h, l, a, b_g1 in G1; b_g2 in G2).
+ * The pk passed here holds only this rank's slice of each query. */
+int pcdgpu_groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* alpha_g1, const void* beta_g1,
+                          const void* delta_g1, const void* beta_g2, const void* delta_g2, const void* a_query0,
+                          const void* b_g1_query0, const void* b_g2_query0, const void* sums_affine, const void* r,
+                          const void* s, void* out_proof);
+int pcdgpu_serialize_proof(int pairing, const void* proof_affine, uint8_t* out, size_t* out_len);
+
+/* ---- measurement helpers ----------------------------------------------------------------------
+ * Integer-pipe microbenchmark: every thread runs `iters` rounds of 8 independent
+ * mad.wide-style chains; returns achieved 32x32->64 multiply-adds per second (the IMAD roof of
+ * SURVEY.md 8d) and, with modmul != 0, Montgomery products per second of fp.cuh's operator*. */
+int pcdgpu_bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* out_ops_per_s, double* out_ms);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* PCDGPU_H */
