@@ -143,14 +143,9 @@ int pcdgpu_groth16_prove(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs
 /* same with z already in device memory (Montgomery elements) */
 int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
                              const void* r, const void* s, void* out_proof);
-/* Partial proof for a point-range shard [lo, hi) of every query (multi-GPU): the
- * witness map runs on every rank; out_partials = 5 xyzz sums (h, l, a, b_g1 in G1; b_g2 in G2).
- * The pk passed here holds only this rank's slice of each query. */
-int pcdgpu_groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* alpha_g1, const void* beta_g1,
-                          const void* delta_g1, const void* beta_g2, const void* delta_g2, const void* a_query0,
-                          const void* b_g1_query0, const void* b_g2_query0, const void* sums_affine, const void* r,
-                          const void* s, void* out_proof);
-int pcdgpu_serialize_proof(int pairing, const void* proof_affine, uint8_t* out, size_t* out_len);
+/* ark-serialize CanonicalSerialize of the proof (compressed points: x with flag bits 7 = "y is the
+ * larger root", 6 = infinity on the last byte): 152 B (MNT4) / 190 B (MNT6).  out: >= 190 bytes. */
+int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affine, uint8_t* out, size_t* out_len);
 
 /* ---- measurement helpers ----------------------------------------------------------------------
  * Integer-pipe microbenchmark: every thread runs `iters` rounds of 8 independent

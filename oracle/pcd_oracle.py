@@ -951,22 +951,34 @@ class Groth16PK:
 
 
 def _lagrange_at(d: Domain, tau: int) -> List[int]:
-    """L_i(tau) for the domain (ark-poly evaluate_all_lagrange_coefficients)."""
+    """L_i(tau) for the domain (ark-poly evaluate_all_lagrange_coefficients):
+    L_i(tau) = Z(tau) * w^i / (n * (tau - w^i)), with one batched inversion."""
     p, n = d.p, d.size
     zt = (pow(tau, n, p) - 1) % p
     assert zt != 0
     ninv = pow(n, -1, p)
-    out = []
+    ws, dens = [], []
     w = 1
     for i in range(n):
-        # L_i(tau) = Z(tau) * w^i / (n * (tau - w^i))
-        out.append(zt * w % p * ninv % p * pow((tau - w) % p, -1, p) % p)
+        ws.append(w)
+        dens.append((tau - w) % p)
         w = w * d.omega % p
+    pref = [1] * (n + 1)
+    for i in range(n):
+        pref[i + 1] = pref[i] * dens[i] % p
+    inv_all = pow(pref[n], -1, p)
+    out = [0] * n
+    c = zt * ninv % p
+    for i in range(n - 1, -1, -1):
+        out[i] = c * ws[i] % p * (inv_all * pref[i] % p) % p
+        inv_all = inv_all * dens[i] % p
     return out
 
 
-def groth16_setup(pairing: Pairing, r1cs: R1CS, seed: int = 7) -> Groth16PK:
-    """``generate_random_parameters`` restated with the trapdoor kept (test infrastructure)."""
+def groth16_setup_scalars(pairing: Pairing, r1cs: R1CS, seed: int = 7) -> dict:
+    """The discrete logs of every proving-key element for a known trapdoor (test infrastructure):
+    At/Bt/Ct = the QAP polynomials of each variable evaluated at tau, h_sc[i] = tau^i Z(tau)/delta,
+    l_sc[j] = (beta At + alpha Bt + Ct)/delta for the witness variables."""
     fp = pairing.fr
     assert fp is r1cs.fp
     p = fp.p
@@ -991,29 +1003,34 @@ def groth16_setup(pairing: Pairing, r1cs: R1CS, seed: int = 7) -> Groth16PK:
         At[j] = (At[j] + L[m + j]) % p
     zt = (pow(tau, n, p) - 1) % p
     dinv = pow(delta, -1, p)
+    h_sc = []
+    cur = zt * dinv % p
+    for i in range(n - 1):
+        h_sc.append(cur)
+        cur = cur * tau % p
+    l_sc = [(beta * At[j] + alpha * Bt[j] + Ct[j]) % p * dinv % p for j in range(r1cs.num_inputs, nv)]
+    return dict(alpha=alpha, beta=beta, gamma=gamma, delta=delta, tau=tau, At=At, Bt=Bt, Ct=Ct,
+                h_sc=h_sc, l_sc=l_sc)
+
+
+def groth16_setup(pairing: Pairing, r1cs: R1CS, seed: int = 7) -> Groth16PK:
+    """``generate_random_parameters`` restated with the trapdoor kept (test infrastructure)."""
+    t = groth16_setup_scalars(pairing, r1cs, seed)
     G1, G2 = pairing.g1, pairing.g2
     g1, g2 = generator(G1), generator(G2)
-    a_query = [G1.mul(g1, x) for x in At]
-    b_g1_query = [G1.mul(g1, x) for x in Bt]
-    b_g2_query = [G2.mul(g2, x) for x in Bt]
-    h_sc = [pow(tau, i, p) * zt % p * dinv % p for i in range(n - 1)]
-    h_query = [G1.mul(g1, x) for x in h_sc]
-    l_sc = [(beta * At[j] + alpha * Bt[j] + Ct[j]) % p * dinv % p for j in range(r1cs.num_inputs, nv)]
-    l_query = [G1.mul(g1, x) for x in l_sc]
     return Groth16PK(
         pairing,
-        G1.mul(g1, alpha),
-        G1.mul(g1, beta),
-        G1.mul(g1, delta),
-        G2.mul(g2, beta),
-        G2.mul(g2, delta),
-        a_query,
-        b_g1_query,
-        b_g2_query,
-        h_query,
-        l_query,
-        dict(alpha=alpha, beta=beta, gamma=gamma, delta=delta, tau=tau, At=At, Bt=Bt, Ct=Ct,
-             h_sc=h_sc, l_sc=l_sc),
+        G1.mul(g1, t["alpha"]),
+        G1.mul(g1, t["beta"]),
+        G1.mul(g1, t["delta"]),
+        G2.mul(g2, t["beta"]),
+        G2.mul(g2, t["delta"]),
+        [G1.mul(g1, x) for x in t["At"]],
+        [G1.mul(g1, x) for x in t["Bt"]],
+        [G2.mul(g2, x) for x in t["Bt"]],
+        [G1.mul(g1, x) for x in t["h_sc"]],
+        [G1.mul(g1, x) for x in t["l_sc"]],
+        t,
     )
 
 

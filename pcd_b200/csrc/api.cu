@@ -1,0 +1,568 @@
+// api.cu -- the extern "C" surface of libpcdgpu.so (include/pcdgpu.h).  Host-pointer entry points
+// stage through device scratch; _dev entry points are asynchronous on the context's stream.
+#include "groth16.cuh"
+#include "msm_ops.cuh"
+#include "ntt.cuh"
+
+// ---- small helpers -----------------------------------------------------------------------------
+const MsmOps* msm_ops(int curve) {
+  switch (curve) {
+    case PCDGPU_MNT4_G1: return &MSM_OPS_MNT4_G1;
+    case PCDGPU_MNT4_G2: return &MSM_OPS_MNT4_G2;
+    case PCDGPU_MNT6_G1: return &MSM_OPS_MNT6_G1;
+    case PCDGPU_MNT6_G2: return &MSM_OPS_MNT6_G2;
+  }
+  return nullptr;
+}
+static int g1_of(int pairing) { return pairing == PCDGPU_MNT4_298 ? PCDGPU_MNT4_G1 : PCDGPU_MNT6_G1; }
+static int g2_of(int pairing) { return pairing == PCDGPU_MNT4_298 ? PCDGPU_MNT4_G2 : PCDGPU_MNT6_G2; }
+
+static const int MSM_BITS = 298;
+int msm_num_windows_c(int c) { return (MSM_BITS + 1 + c - 1) / c; }
+int msm_auto_window_c(size_t n, int shared) {
+  int lg = ilog2_ceil(n ? n : 1);
+  int c;
+  if (shared) {
+    c = lg;  // one bucket set for all windows: ~2 * nwin entries per bucket
+    if (c < 6) c = 6;
+    if (c > 21) c = 21;
+  } else {
+    c = lg - 4;  // ~32 entries per bucket and window
+    if (c < 4) c = 4;
+    if (c > 16) c = 16;
+  }
+  return c;
+}
+
+static MsmPlanC plan_plain(pcdgpu_ctx* ctx, size_t n) {
+  int c = ctx->msm_window > 0 ? ctx->msm_window : msm_auto_window_c(n, 0);
+  return MsmPlanC{c, msm_num_windows_c(c), 0, 0, 0};
+}
+
+#define CHECK_ARG(ctx, cond, msg)         \
+  do {                                    \
+    if (!(cond)) {                        \
+      if (ctx) (ctx)->set_error("%s", msg); \
+      return PCDGPU_E_ARG;                \
+    }                                     \
+  } while (0)
+
+extern "C" {
+
+const char* pcdgpu_strerror(int code) {
+  switch (code) {
+    case PCDGPU_OK: return "ok";
+    case PCDGPU_E_ARG: return "bad argument";
+    case PCDGPU_E_NODEVICE: return "no usable CUDA device (libpcdgpu has no CPU fallback)";
+    case PCDGPU_E_CUDA: return "CUDA call failed";
+    case PCDGPU_E_DOMAIN: return "evaluation domain exceeds the field's 2-adicity";
+    case PCDGPU_E_NOMEM: return "out of device memory";
+  }
+  return "unknown error";
+}
+const char* pcdgpu_last_error(const pcdgpu_ctx* ctx) { return ctx ? ctx->err : ""; }
+size_t pcdgpu_affine_bytes(int curve) {
+  const MsmOps* o = msm_ops(curve);
+  return o ? o->affine_bytes : 0;
+}
+
+int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
+  if (!out) return PCDGPU_E_ARG;
+  *out = nullptr;
+  int count = 0;
+  if (cudaGetDeviceCount(&count) != cudaSuccess || count <= 0 || device < 0 || device >= count) return PCDGPU_E_NODEVICE;
+  cudaDeviceProp prop;
+  if (cudaGetDeviceProperties(&prop, device) != cudaSuccess) return PCDGPU_E_NODEVICE;
+  if (prop.major != 10) return PCDGPU_E_NODEVICE;  // the only code in the library is sm_100a SASS
+  if (cudaSetDevice(device) != cudaSuccess) return PCDGPU_E_NODEVICE;
+  pcdgpu_ctx* ctx = new pcdgpu_ctx();
+  ctx->device = device;
+  ctx->sm_count = prop.multiProcessorCount;
+  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+    delete ctx;
+    return PCDGPU_E_CUDA;
+  }
+  ctx->stream = ctx->own_stream;
+  ctx->pinned_bytes = 1 << 16;
+  if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
+    cudaStreamDestroy(ctx->own_stream);
+    delete ctx;
+    return PCDGPU_E_NOMEM;
+  }
+  *out = ctx;
+  return PCDGPU_OK;
+}
+
+void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx) {
+  if (!ctx) return;
+  cudaSetDevice(ctx->device);
+  cudaStreamSynchronize(ctx->stream);
+  for (int i = 0; i < pcdgpu_ctx::NSLOT; i++)
+    if (ctx->slot[i]) cudaFree(ctx->slot[i]);
+  for (auto& kv : ctx->ntt_tables) cudaFree(kv.second.twiddles);
+  if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  cudaStreamDestroy(ctx->own_stream);
+  delete ctx;
+}
+
+int pcdgpu_sync(pcdgpu_ctx* ctx) {
+  if (!ctx) return PCDGPU_E_ARG;
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+int pcdgpu_set_stream(pcdgpu_ctx* ctx, void* stream) {
+  if (!ctx) return PCDGPU_E_ARG;
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+  return 0;
+}
+int pcdgpu_set_msm_window(pcdgpu_ctx* ctx, int c) {
+  if (!ctx || c < 0 || c > 21 || c == 1) return PCDGPU_E_ARG;
+  ctx->msm_window = c;
+  return 0;
+}
+
+// ---- NTT ---------------------------------------------------------------------------------------
+int pcdgpu_ntt_dev(pcdgpu_ctx* ctx, int field, void* d_data, uint32_t log_n, int inverse, int coset) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, d_data, "null data pointer");
+  CHECK_ARG(ctx, field == PCDGPU_FIELD_R4 || field == PCDGPU_FIELD_Q4, "unknown field id");
+  CHECK_ARG(ctx, log_n < 40, "log_n out of range");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return ntt_run(ctx, field, d_data, (int)log_n, inverse != 0, coset != 0);
+}
+
+int pcdgpu_ntt(pcdgpu_ctx* ctx, int field, void* data, uint32_t log_n, int inverse, int coset) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, data, "null data pointer");
+  CHECK_ARG(ctx, field == PCDGPU_FIELD_R4 || field == PCDGPU_FIELD_Q4, "unknown field id");
+  CHECK_ARG(ctx, log_n < 40, "log_n out of range");
+  int two_adicity = field == PCDGPU_FIELD_R4 ? 34 : 17;
+  if ((int)log_n > two_adicity) {
+    ctx->set_error("radix-2 domain 2^%u exceeds the field's 2-adicity %d", log_n, two_adicity);
+    return PCDGPU_E_DOMAIN;
+  }
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t bytes = ((size_t)40) << log_n;
+  void* d;
+  PCD_TRY(ctx->scratch(SLOT_IO, bytes, &d));
+  PCD_CUDA(ctx, cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(ntt_run(ctx, field, d, (int)log_n, inverse != 0, coset != 0));
+  PCD_CUDA(ctx, cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- MSM ---------------------------------------------------------------------------------------
+int pcdgpu_msm_dev(pcdgpu_ctx* ctx, int curve, const void* d_bases, const void* d_scalars, int scalars_mont, size_t n,
+                   void* d_out_xyzz) {
+  if (!ctx) return PCDGPU_E_ARG;
+  const MsmOps* ops = msm_ops(curve);
+  CHECK_ARG(ctx, ops, "unknown curve id");
+  CHECK_ARG(ctx, d_out_xyzz && (n == 0 || (d_bases && d_scalars)), "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return ops->run(ctx, d_bases, d_scalars, scalars_mont, n, plan_plain(ctx, n), d_out_xyzz);
+}
+
+static int finish_to_host(pcdgpu_ctx* ctx, const MsmOps* ops, void* d_xyzz, void* out_affine) {
+  void* d_aff = (char*)d_xyzz + ops->xyzz_bytes;
+  PCD_TRY(ops->to_affine(ctx, d_xyzz, 1, d_aff));
+  PCD_CUDA(ctx, cudaMemcpyAsync(out_affine, d_aff, ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int pcdgpu_msm(pcdgpu_ctx* ctx, int curve, const void* bases, const void* scalars, size_t n, void* out_affine) {
+  if (!ctx) return PCDGPU_E_ARG;
+  const MsmOps* ops = msm_ops(curve);
+  CHECK_ARG(ctx, ops, "unknown curve id");
+  CHECK_ARG(ctx, out_affine && (n == 0 || (bases && scalars)), "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  void *db, *ds, *dres;
+  PCD_TRY(ctx->scratch(SLOT_IO, n * ops->affine_bytes + 16, &db));
+  PCD_TRY(ctx->scratch(SLOT_IO2, n * 40 + 16, &ds));
+  PCD_TRY(ctx->scratch(SLOT_MISC, 4096, &dres));
+  PCD_CUDA(ctx, cudaMemcpyAsync(db, bases, n * ops->affine_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_CUDA(ctx, cudaMemcpyAsync(ds, scalars, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(ops->run(ctx, db, ds, 0, n, plan_plain(ctx, n), dres));
+  return finish_to_host(ctx, ops, dres, out_affine);
+}
+
+int pcdgpu_bases_upload(pcdgpu_ctx* ctx, int curve, const void* bases, size_t n, int precompute, pcdgpu_bases** out) {
+  if (!ctx) return PCDGPU_E_ARG;
+  const MsmOps* ops = msm_ops(curve);
+  CHECK_ARG(ctx, ops, "unknown curve id");
+  CHECK_ARG(ctx, out && (n == 0 || bases), "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  pcdgpu_bases* b = new pcdgpu_bases();
+  b->ctx = ctx;
+  b->curve = curve;
+  b->n = n;
+  b->c = 0;
+  b->nwin = 0;
+  b->points = nullptr;
+  b->table = nullptr;
+  size_t rows = 1;
+  if (precompute && n > 0) {
+    b->c = ctx->msm_window > 0 ? ctx->msm_window : msm_auto_window_c(n, 1);
+    b->nwin = msm_num_windows_c(b->c);
+    rows = b->nwin;
+  }
+  cudaError_t e = cudaMalloc(&b->points, rows * (n ? n : 1) * ops->affine_bytes);
+  if (e != cudaSuccess) {
+    ctx->set_error("cudaMalloc for %zu x %zu base points: %s", rows, n, cudaGetErrorString(e));
+    delete b;
+    return PCDGPU_E_NOMEM;
+  }
+  if (n) {
+    e = cudaMemcpyAsync(b->points, bases, n * ops->affine_bytes, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && b->nwin) {
+      b->table = b->points;  // row 0 of the table is the points themselves
+      int rc = ops->precompute(ctx, b->points, n, b->c, b->nwin, b->table);
+      if (rc) {
+        cudaFree(b->points);
+        delete b;
+        return rc;
+      }
+    }
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->set_error("uploading base points: %s", cudaGetErrorString(e));
+      cudaFree(b->points);
+      delete b;
+      return PCDGPU_E_CUDA;
+    }
+  }
+  *out = b;
+  return 0;
+}
+
+void pcdgpu_bases_free(pcdgpu_bases* b) {
+  if (!b) return;
+  cudaSetDevice(b->ctx->device);
+  cudaStreamSynchronize(b->ctx->stream);
+  if (b->points) cudaFree(b->points);
+  delete b;
+}
+
+int pcdgpu_msm_bases_dev(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* d_scalars, int scalars_mont,
+                         size_t n, void* d_out_xyzz) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, b && d_out_xyzz && (n == 0 || d_scalars), "null pointer");
+  CHECK_ARG(ctx, offset <= b->n, "offset beyond the base vector");
+  const MsmOps* ops = msm_ops(b->curve);
+  if (n > b->n - offset) n = b->n - offset;  // truncate to the shorter input, as arkworks does
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  if (b->table) {
+    MsmPlanC plan{b->c, b->nwin, 1, b->n, offset};
+    return ops->run(ctx, b->table, d_scalars, scalars_mont, n, plan, d_out_xyzz);
+  }
+  return ops->run(ctx, (const char*)b->points + offset * ops->affine_bytes, d_scalars, scalars_mont, n,
+                  plan_plain(ctx, n), d_out_xyzz);
+}
+
+int pcdgpu_msm_bases(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* scalars, size_t n,
+                     void* out_affine) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, b && out_affine && (n == 0 || scalars), "null pointer");
+  const MsmOps* ops = msm_ops(b->curve);
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  void *ds, *dres;
+  PCD_TRY(ctx->scratch(SLOT_IO2, n * 40 + 16, &ds));
+  PCD_TRY(ctx->scratch(SLOT_MISC, 4096, &dres));
+  PCD_CUDA(ctx, cudaMemcpyAsync(ds, scalars, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(pcdgpu_msm_bases_dev(ctx, b, offset, ds, 0, n, dres));
+  return finish_to_host(ctx, ops, dres, out_affine);
+}
+
+int pcdgpu_xyzz_sum(pcdgpu_ctx* ctx, int curve, const void* xyzz, size_t n, void* out_affine) {
+  if (!ctx) return PCDGPU_E_ARG;
+  const MsmOps* ops = msm_ops(curve);
+  CHECK_ARG(ctx, ops, "unknown curve id");
+  CHECK_ARG(ctx, out_affine && (n == 0 || xyzz), "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* d;
+  PCD_TRY(ctx->scratch(SLOT_IO, (n + 1) * ops->xyzz_bytes, &d));
+  void* d_aff = (char*)d + n * ops->xyzz_bytes;
+  PCD_CUDA(ctx, cudaMemcpyAsync(d, xyzz, n * ops->xyzz_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(ops->xyzz_sum(ctx, d, n, d_aff));
+  PCD_CUDA(ctx, cudaMemcpyAsync(out_affine, d_aff, ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int pcdgpu_xyzz_download(pcdgpu_ctx* ctx, int curve, const void* d_xyzz, void* out_xyzz) {
+  if (!ctx) return PCDGPU_E_ARG;
+  const MsmOps* ops = msm_ops(curve);
+  CHECK_ARG(ctx, ops && d_xyzz && out_xyzz, "bad argument");
+  PCD_CUDA(ctx, cudaMemcpyAsync(out_xyzz, d_xyzz, ops->xyzz_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- fixed-base multiplication -------------------------------------------------------------------
+int pcdgpu_fixed_base_mul_dev(pcdgpu_ctx* ctx, int curve, const void* base_host, const void* d_scalars, size_t n,
+                              void* d_out) {
+  if (!ctx) return PCDGPU_E_ARG;
+  const MsmOps* ops = msm_ops(curve);
+  CHECK_ARG(ctx, ops, "unknown curve id");
+  CHECK_ARG(ctx, base_host && (n == 0 || (d_scalars && d_out)), "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  void* t;
+  PCD_TRY(ctx->scratch(SLOT_MSM_SEG, (75 * 15 + 1) * ops->affine_bytes, &t));
+  void* d_base = (char*)t + 75 * 15 * ops->affine_bytes;
+  memcpy(ctx->pinned, base_host, ops->affine_bytes);
+  PCD_CUDA(ctx, cudaMemcpyAsync(d_base, ctx->pinned, ops->affine_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(ops->fixed_table(ctx, d_base, t));
+  PCD_TRY(ops->fixed_mul(ctx, t, d_scalars, n, d_out));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));  // the pinned staging buffer is reusable afterwards
+  return 0;
+}
+
+int pcdgpu_fixed_base_mul(pcdgpu_ctx* ctx, int curve, const void* base, const void* scalars, size_t n, void* out) {
+  if (!ctx) return PCDGPU_E_ARG;
+  const MsmOps* ops = msm_ops(curve);
+  CHECK_ARG(ctx, ops, "unknown curve id");
+  CHECK_ARG(ctx, base && (n == 0 || (scalars && out)), "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  void *ds, *dout;
+  PCD_TRY(ctx->scratch(SLOT_IO2, n * 40 + 16, &ds));
+  PCD_TRY(ctx->scratch(SLOT_IO, n * ops->affine_bytes + 16, &dout));
+  PCD_CUDA(ctx, cudaMemcpyAsync(ds, scalars, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(pcdgpu_fixed_base_mul_dev(ctx, curve, base, ds, n, dout));
+  PCD_CUDA(ctx, cudaMemcpyAsync(out, dout, n * ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- R1CS / witness map ----------------------------------------------------------------------------
+int pcdgpu_r1cs_upload(pcdgpu_ctx* ctx, int pairing, size_t m, size_t num_inputs, size_t num_witness,
+                       const uint32_t* a_ptr, const uint32_t* a_col, const void* a_val, const uint32_t* b_ptr,
+                       const uint32_t* b_col, const void* b_val, const uint32_t* c_ptr, const uint32_t* c_col,
+                       const void* c_val, pcdgpu_r1cs** out) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pairing == PCDGPU_MNT4_298 || pairing == PCDGPU_MNT6_298, "unknown pairing id");
+  CHECK_ARG(ctx, out && a_ptr && b_ptr && c_ptr, "null pointer");
+  CHECK_ARG(ctx, num_inputs >= 1, "num_inputs counts the constant 1 and must be >= 1");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const uint32_t* ptrs[3] = {a_ptr, b_ptr, c_ptr};
+  const uint32_t* cols[3] = {a_col, b_col, c_col};
+  const void* vals[3] = {a_val, b_val, c_val};
+  size_t nnz[3], total = 0, off[9];
+  for (int i = 0; i < 3; i++) {
+    nnz[i] = ptrs[i][m];
+    CHECK_ARG(ctx, nnz[i] == 0 || (cols[i] && vals[i]), "null column / value array");
+    for (size_t k = 0; k < nnz[i]; k++) CHECK_ARG(ctx, cols[i][k] < num_inputs + num_witness, "column index out of range");
+    off[3 * i] = total;
+    total += ((m + 1) * 4 + 15) & ~(size_t)15;
+    off[3 * i + 1] = total;
+    total += (nnz[i] * 4 + 15) & ~(size_t)15;
+    off[3 * i + 2] = total;
+    total += (nnz[i] * 40 + 15) & ~(size_t)15;
+  }
+  pcdgpu_r1cs* r = new pcdgpu_r1cs();
+  r->ctx = ctx;
+  r->pairing = pairing;
+  r->m = m;
+  r->num_inputs = num_inputs;
+  r->num_witness = num_witness;
+  r->log_n = ilog2_ceil(m + num_inputs);
+  r->n = (size_t)1 << r->log_n;
+  cudaError_t e = cudaMalloc(&r->storage, total ? total : 16);
+  if (e != cudaSuccess) {
+    ctx->set_error("cudaMalloc(%zu) for R1CS matrices: %s", total, cudaGetErrorString(e));
+    delete r;
+    return PCDGPU_E_NOMEM;
+  }
+  char* base = (char*)r->storage;
+  CsrDev* M[3] = {&r->A, &r->B, &r->C};
+  for (int i = 0; i < 3 && e == cudaSuccess; i++) {
+    M[i]->row_ptr = (const u32*)(base + off[3 * i]);
+    M[i]->col = (const u32*)(base + off[3 * i + 1]);
+    M[i]->val = (const u32*)(base + off[3 * i + 2]);
+    e = cudaMemcpyAsync(base + off[3 * i], ptrs[i], (m + 1) * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz[i])
+      e = cudaMemcpyAsync(base + off[3 * i + 1], cols[i], nnz[i] * 4, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess && nnz[i])
+      e = cudaMemcpyAsync(base + off[3 * i + 2], vals[i], nnz[i] * 40, cudaMemcpyHostToDevice, ctx->stream);
+  }
+  if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+  if (e != cudaSuccess) {
+    ctx->set_error("uploading R1CS matrices: %s", cudaGetErrorString(e));
+    cudaFree(r->storage);
+    delete r;
+    return PCDGPU_E_CUDA;
+  }
+  *out = r;
+  return 0;
+}
+
+void pcdgpu_r1cs_free(pcdgpu_r1cs* r) {
+  if (!r) return;
+  cudaSetDevice(r->ctx->device);
+  cudaStreamSynchronize(r->ctx->stream);
+  cudaFree(r->storage);
+  delete r;
+}
+
+size_t pcdgpu_r1cs_domain_size(const pcdgpu_r1cs* r) { return r ? r->n : 0; }
+
+int pcdgpu_witness_map(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* z, void* h) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, r && z && h, "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t nv = r->num_inputs + r->num_witness;
+  void* dz;
+  PCD_TRY(ctx->scratch(SLOT_Z, nv * 40, &dz));
+  PCD_CUDA(ctx, cudaMemcpyAsync(dz, z, nv * 40, cudaMemcpyHostToDevice, ctx->stream));
+  void* dh;
+  PCD_TRY(witness_map_dev(ctx, r, dz, &dh));
+  PCD_CUDA(ctx, cudaMemcpyAsync(h, dh, r->n * 40, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+// ---- Groth16 ------------------------------------------------------------------------------------------
+int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_inputs, size_t h_len,
+                     const void* alpha_g1, const void* beta_g1, const void* delta_g1, const void* beta_g2,
+                     const void* delta_g2, const void* a_query, const void* b_g1_query, const void* b_g2_query,
+                     const void* h_query, const void* l_query, int precompute, pcdgpu_pk** out) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pairing == PCDGPU_MNT4_298 || pairing == PCDGPU_MNT6_298, "unknown pairing id");
+  CHECK_ARG(ctx, out && alpha_g1 && beta_g1 && delta_g1 && beta_g2 && delta_g2 && a_query && b_g1_query && b_g2_query,
+            "null pointer");
+  CHECK_ARG(ctx, num_inputs >= 1 && num_vars >= num_inputs, "bad variable counts");
+  CHECK_ARG(ctx, (h_len == 0 || h_query) && (num_vars == num_inputs || l_query), "null query");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int g1 = g1_of(pairing), g2 = g2_of(pairing);
+  size_t s1 = msm_ops(g1)->affine_bytes, s2 = msm_ops(g2)->affine_bytes;
+  pcdgpu_pk* pk = new pcdgpu_pk();
+  memset(pk, 0, sizeof(*pk));
+  pk->ctx = ctx;
+  pk->pairing = pairing;
+  pk->num_vars = num_vars;
+  pk->num_inputs = num_inputs;
+  pk->h_len = h_len;
+  int rc = 0;
+  // element 0 of a/b queries belongs to the constant 1 and is added outside the MSMs (prover.rs)
+  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, (const char*)a_query + s1, num_vars - 1, precompute, &pk->a_query);
+  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, (const char*)b_g1_query + s1, num_vars - 1, precompute, &pk->b_g1_query);
+  rc = rc ? rc : pcdgpu_bases_upload(ctx, g2, (const char*)b_g2_query + s2, num_vars - 1, precompute, &pk->b_g2_query);
+  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, h_query, h_len, precompute, &pk->h_query);
+  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, l_query, num_vars - num_inputs, precompute, &pk->l_query);
+  if (!rc && cudaMalloc(&pk->consts_g1, 5 * s1 + 3 * s2) != cudaSuccess) rc = PCDGPU_E_NOMEM;
+  if (!rc) {
+    pk->consts_g2 = (char*)pk->consts_g1 + 5 * s1;
+    const void* c1[5] = {alpha_g1, beta_g1, delta_g1, a_query, b_g1_query};
+    const void* c2[3] = {beta_g2, delta_g2, b_g2_query};
+    char* stage = (char*)ctx->pinned;
+    for (int i = 0; i < 5; i++) memcpy(stage + i * s1, c1[i], s1);
+    for (int i = 0; i < 3; i++) memcpy(stage + 5 * s1 + i * s2, c2[i], s2);
+    cudaError_t e = cudaMemcpyAsync(pk->consts_g1, stage, 5 * s1 + 3 * s2, cudaMemcpyHostToDevice, ctx->stream);
+    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
+    if (e != cudaSuccess) {
+      ctx->set_error("uploading key constants: %s", cudaGetErrorString(e));
+      rc = PCDGPU_E_CUDA;
+    }
+  }
+  if (rc) {
+    pcdgpu_pk_free(pk);
+    return rc;
+  }
+  *out = pk;
+  return 0;
+}
+
+void pcdgpu_pk_free(pcdgpu_pk* pk) {
+  if (!pk) return;
+  pcdgpu_bases_free(pk->a_query);
+  pcdgpu_bases_free(pk->b_g1_query);
+  pcdgpu_bases_free(pk->b_g2_query);
+  pcdgpu_bases_free(pk->h_query);
+  pcdgpu_bases_free(pk->l_query);
+  if (pk->consts_g1) cudaFree(pk->consts_g1);
+  delete pk;
+}
+
+int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
+                             const void* r, const void* s, void* out_proof) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pk && r1cs && d_z && r && s && out_proof, "null pointer");
+  CHECK_ARG(ctx, pk->pairing == r1cs->pairing, "key and constraint system are over different pairings");
+  CHECK_ARG(ctx, pk->num_vars == r1cs->num_inputs + r1cs->num_witness && pk->num_inputs == r1cs->num_inputs,
+            "key and constraint system disagree on the variable counts");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
+  const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
+  size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
+  // misc layout: rs (80 B) | t1: 3 G1 xyzz | sums1: 4 G1 xyzz | t2: 1 G2 xyzz | sum2: 1 G2 xyzz | proof
+  void* misc;
+  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
+  char* mb = (char*)misc;
+  u32* d_rs = (u32*)mb;
+  void* t1 = mb + 128;
+  void* sums1 = (char*)t1 + 3 * x1;
+  void* t2 = (char*)sums1 + 4 * x1;
+  void* sum2 = (char*)t2 + x2;
+  void* d_proof = (char*)sum2 + x2;
+  size_t proof_bytes = 2 * o1->affine_bytes + o2->affine_bytes;
+  memcpy(ctx->pinned, r, 40);
+  memcpy((char*)ctx->pinned + 40, s, 40);
+  PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(groth16_assemble(ctx, ctx->stream, pk->pairing, 1, pk->consts_g1, pk->consts_g2, d_rs, t1, t2, sums1, sum2,
+                           d_proof));
+  void* d_h;
+  PCD_TRY(witness_map_dev(ctx, r1cs, d_z, &d_h));
+  const char* z = (const char*)d_z;
+  size_t nv = pk->num_vars, ni = pk->num_inputs;
+  // h: n coefficients vs n - 1 query points: truncated to the shorter
+  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->h_query, 0, d_h, 1, r1cs->n, (char*)sums1 + 0 * x1));
+  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->l_query, 0, z + 40 * ni, 1, nv - ni, (char*)sums1 + 1 * x1));
+  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->a_query, 0, z + 40, 1, nv - 1, (char*)sums1 + 2 * x1));
+  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->b_g1_query, 0, z + 40, 1, nv - 1, (char*)sums1 + 3 * x1));
+  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->b_g2_query, 0, z + 40, 1, nv - 1, sum2));
+  PCD_TRY(groth16_assemble(ctx, ctx->stream, pk->pairing, 2, pk->consts_g1, pk->consts_g2, d_rs, t1, t2, sums1, sum2,
+                           d_proof));
+  PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
+int pcdgpu_groth16_prove(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* z, const void* r,
+                         const void* s, void* out_proof) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pk && r1cs && z && r && s && out_proof, "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t nv = r1cs->num_inputs + r1cs->num_witness;
+  void* dz;
+  PCD_TRY(ctx->scratch(SLOT_Z, nv * 40, &dz));
+  PCD_CUDA(ctx, cudaMemcpyAsync(dz, z, nv * 40, cudaMemcpyHostToDevice, ctx->stream));
+  return pcdgpu_groth16_prove_dev(ctx, pk, r1cs, dz, r, s, out_proof);
+}
+
+int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affine, uint8_t* out, size_t* out_len) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pairing == PCDGPU_MNT4_298 || pairing == PCDGPU_MNT6_298, "unknown pairing id");
+  CHECK_ARG(ctx, proof_affine && out && out_len, "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t in_bytes = 2 * msm_ops(g1_of(pairing))->affine_bytes + msm_ops(g2_of(pairing))->affine_bytes;
+  size_t out_bytes = pairing == PCDGPU_MNT4_298 ? 152 : 190;
+  void* d;
+  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &d));
+  unsigned char* d_out = (unsigned char*)d + 1024;
+  PCD_CUDA(ctx, cudaMemcpyAsync(d, proof_affine, in_bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(groth16_serialize(ctx, pairing, d, d_out));
+  PCD_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  *out_len = out_bytes;
+  return 0;
+}
+
+int pcdgpu_bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* out_ops_per_s, double* out_ms) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, out_ops_per_s && out_ms && iters > 0, "bad argument");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return bench_imad(ctx, modmul, iters, out_ops_per_s, out_ms);
+}
+
+}  // extern "C"

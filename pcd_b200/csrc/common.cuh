@@ -1,0 +1,104 @@
+// common.cuh -- context, error handling and the device scratch pool of libpcdgpu.so.
+#pragma once
+#include <cuda_runtime.h>
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <map>
+#include <string>
+#include <vector>
+
+#include "../../include/pcdgpu.h"
+#include "ec.cuh"
+
+#define PCD_CUDA(ctx, call)                                                                      \
+  do {                                                                                           \
+    cudaError_t e__ = (call);                                                                    \
+    if (e__ != cudaSuccess) {                                                                    \
+      (ctx)->set_error("%s:%d %s -> %s", __FILE__, __LINE__, #call, cudaGetErrorString(e__));   \
+      return PCDGPU_E_CUDA;                                                                      \
+    }                                                                                            \
+  } while (0)
+
+#define PCD_TRY(expr)           \
+  do {                          \
+    int rc__ = (expr);          \
+    if (rc__ != 0) return rc__; \
+  } while (0)
+
+// Per (field, log_n) NTT tables, built on first use and kept for the life of the context.
+struct NttTables {
+  void* twiddles = nullptr;   // omega^k, k < n/2
+  void* coset_pow = nullptr;  // g^i, i < n
+  void* coset_inv = nullptr;  // g^-i / n, i < n
+};
+
+struct pcdgpu_ctx {
+  int device = 0;
+  int sm_count = 148;
+  cudaStream_t own_stream = nullptr;
+  cudaStream_t stream = nullptr;
+  int msm_window = 0;
+  char err[512] = {0};
+  // grow-only scratch slots (slot ids are fixed per use so concurrent phases never alias)
+  static const int NSLOT = 16;
+  void* slot[NSLOT] = {nullptr};
+  size_t slot_bytes[NSLOT] = {0};
+  std::map<int, NttTables> ntt_tables;  // key = field * 64 + log_n
+  void* pinned = nullptr;               // small pinned staging buffer
+  size_t pinned_bytes = 0;
+
+  void set_error(const char* fmt, ...) {
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(err, sizeof(err), fmt, ap);
+    va_end(ap);
+  }
+  // scratch: returns a device buffer of at least `bytes` for slot `id`
+  int scratch(int id, size_t bytes, void** out) {
+    if (bytes > slot_bytes[id]) {
+      if (slot[id]) {
+        cudaStreamSynchronize(stream);
+        cudaFree(slot[id]);
+        slot[id] = nullptr;
+        slot_bytes[id] = 0;
+      }
+      size_t want = bytes + bytes / 8 + 256;
+      cudaError_t e = cudaMalloc(&slot[id], want);
+      if (e != cudaSuccess) {
+        set_error("cudaMalloc(%zu) for scratch slot %d: %s", want, id, cudaGetErrorString(e));
+        return PCDGPU_E_NOMEM;
+      }
+      slot_bytes[id] = want;
+    }
+    *out = slot[id];
+    return 0;
+  }
+};
+
+enum {
+  SLOT_NTT = 0,      // ping-pong buffer of a multi-pass NTT
+  SLOT_IO = 1,       // host-pointer entry points: staged input / output
+  SLOT_IO2 = 2,
+  SLOT_MSM_DIG = 3,  // MSM digits
+  SLOT_MSM_ENT = 4,  // MSM sorted entries
+  SLOT_MSM_CNT = 5,  // MSM bucket counts / offsets / cursors
+  SLOT_MSM_BKT = 6,  // MSM bucket sums
+  SLOT_MSM_SEG = 7,  // MSM reduction partials + result
+  SLOT_WM_A = 8,     // witness map vectors
+  SLOT_WM_B = 9,
+  SLOT_WM_C = 10,
+  SLOT_Z = 11,       // assignment on device
+  SLOT_MISC = 12,
+  SLOT_CUB = 13
+};
+
+template <class T>
+static inline T* dptr(void* p) { return reinterpret_cast<T*>(p); }
+
+static inline int ilog2_ceil(size_t n) {
+  int l = 0;
+  while (((size_t)1 << l) < n) l++;
+  return l;
+}

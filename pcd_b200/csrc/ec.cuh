@@ -20,18 +20,22 @@ struct AffinePoint {
 // Curve tags: coordinate field + multiplication by the curve coefficient a.
 struct CurveMnt4G1 {  // y^2 = x^3 + 2x + b over F_q4, order r4
   typedef FpQ4 F; typedef ParamsR4 ScalarParams; typedef GenMnt4G1 Gen; static constexpr int ID = 0;
+  static constexpr bool OUTLINE = false;
   PCD_HD static F mul_a(const F& v) { return v.dbl(); }
 };
 struct CurveMnt4G2 {  // twist over Fq2: a' = (34, 0)
   typedef Fq2 F; typedef ParamsR4 ScalarParams; typedef GenMnt4G2 Gen; static constexpr int ID = 1;
+  static constexpr bool OUTLINE = true;  // group operations are real function calls (code size, compile time)
   PCD_HD static F mul_a(const F& v) { return v.template mul_small<34>(); }
 };
 struct CurveMnt6G1 {  // y^2 = x^3 + 11x + b over F_r4, order q4
   typedef FpR4 F; typedef ParamsQ4 ScalarParams; typedef GenMnt6G1 Gen; static constexpr int ID = 2;
+  static constexpr bool OUTLINE = false;
   PCD_HD static F mul_a(const F& v) { return v.template mul_small<11>(); }
 };
 struct CurveMnt6G2 {  // twist over Fq3: a' = (0, 0, 11) = 11 u^2;  u^3 = 5
   typedef Fq3 F; typedef ParamsQ4 ScalarParams; typedef GenMnt6G2 Gen; static constexpr int ID = 3;
+  static constexpr bool OUTLINE = true;
   PCD_HD static F mul_a(const F& v) {
     F r;
     r.c0 = v.c1.template mul_small<55>();
@@ -71,8 +75,25 @@ struct XYZZ {
     p.zzz = W;
     return p;
   }
-  // dbl-2008-s-1
+  // Out-of-line entry points: for the G2 curves (C::OUTLINE) every group operation is a call, so a
+  // kernel holds one copy of each formula instead of one per use.
+  PCD_NOINLINE static void dbl_out(XYZZ* dst, const XYZZ* src) { *dst = src->dbl_impl(); }
+  PCD_NOINLINE static void madd_out(XYZZ* self, const AffinePoint<F>* a) { self->madd_impl(*a); }
+  PCD_NOINLINE static void add_out(XYZZ* self, const XYZZ* o) { self->add_impl(*o); }
   PCD_HD XYZZ dbl() const {
+    if constexpr (C::OUTLINE) { XYZZ r; dbl_out(&r, this); return r; }
+    else return dbl_impl();
+  }
+  PCD_HD void madd(const AffinePoint<F>& a) {
+    if constexpr (C::OUTLINE) madd_out(this, &a);
+    else madd_impl(a);
+  }
+  PCD_HD void add(const XYZZ& o) {
+    if constexpr (C::OUTLINE) add_out(this, &o);
+    else add_impl(o);
+  }
+  // dbl-2008-s-1
+  PCD_HD XYZZ dbl_impl() const {
     if (is_inf() || y.is_zero()) return inf();
     F U = y.dbl();
     F V = U.sqr();
@@ -88,7 +109,7 @@ struct XYZZ {
     return p;
   }
   // this += affine (madd-2008-s), all exceptional cases handled
-  PCD_HD void madd(const AffinePoint<F>& a) {
+  PCD_HD void madd_impl(const AffinePoint<F>& a) {
     if (a.is_inf()) return;
     if (is_inf()) { *this = from_affine(a); return; }
     F P = a.x * zz - x;
@@ -108,7 +129,7 @@ struct XYZZ {
     zzz = zzz * PPP;
   }
   // this += o (add-2008-s)
-  PCD_HD void add(const XYZZ& o) {
+  PCD_HD void add_impl(const XYZZ& o) {
     if (o.is_inf()) return;
     if (is_inf()) { *this = o; return; }
     F U1 = x * o.zz;
@@ -131,7 +152,13 @@ struct XYZZ {
     zz = zz * o.zz * PP;
     zzz = zzz * o.zzz * PPP;
   }
+  PCD_NOINLINE static void to_affine_out(AffinePoint<F>* dst, const XYZZ* src) { *dst = src->to_affine_impl(); }
   PCD_HD AffinePoint<F> to_affine() const {
+    AffinePoint<F> r;
+    to_affine_out(&r, this);
+    return r;
+  }
+  PCD_HD AffinePoint<F> to_affine_impl() const {
     if (is_inf()) return AffinePoint<F>::inf();
     F i = zzz.inverse();
     F t = zz * i;  // = 1/Z
@@ -141,7 +168,13 @@ struct XYZZ {
     return a;
   }
   // [k]P, k = nlimbs 32-bit little-endian limbs (plain integer), MSB-first double-and-add
+  PCD_NOINLINE static void mul_out(XYZZ* dst, const XYZZ* p, const u32* k, int nlimbs) { *dst = mul_impl(*p, k, nlimbs); }
   PCD_HD static XYZZ mul(const XYZZ& p, const u32* k, int nlimbs) {
+    XYZZ r;
+    mul_out(&r, &p, k, nlimbs);
+    return r;
+  }
+  PCD_HD static XYZZ mul_impl(const XYZZ& p, const u32* k, int nlimbs) {
     XYZZ acc = inf();
     bool started = false;
     for (int i = nlimbs - 1; i >= 0; i--) {

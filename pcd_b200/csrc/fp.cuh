@@ -172,6 +172,9 @@ struct Fp {
     return r;
   }
   PCD_HD Fp sqr() const { return (*this) * (*this); }
+  // Out-of-line product for the extension-field code (Fq2/Fq3 points would otherwise inline
+  // 40-80 copies of the 260-instruction product per group addition).
+  PCD_NOINLINE static Fp mul_ni(Fp a, Fp b) { return a * b; }
 
   // multiply by a small compile-time constant with additions only
   template <u32 K>

@@ -21,17 +21,17 @@ struct Fp2T {
   PCD_HD Fp2T dbl() const { Fp2T r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); return r; }
   // Karatsuba: 3 base products
   PCD_HD friend Fp2T operator*(const Fp2T& a, const Fp2T& b) {
-    B v0 = a.c0 * b.c0;
-    B v1 = a.c1 * b.c1;
+    B v0 = B::mul_ni(a.c0, b.c0);
+    B v1 = B::mul_ni(a.c1, b.c1);
     Fp2T r;
-    r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - v0 - v1;
+    r.c1 = B::mul_ni(a.c0 + a.c1, b.c0 + b.c1) - v0 - v1;
     r.c0 = v0 + v1.template mul_small<NR>();
     return r;
   }
   // complex squaring: 2 base products
   PCD_HD Fp2T sqr() const {
-    B ab = c0 * c1;
-    B t = (c0 + c1) * (c0 + c1.template mul_small<NR>());
+    B ab = B::mul_ni(c0, c1);
+    B t = B::mul_ni(c0 + c1, c0 + c1.template mul_small<NR>());
     Fp2T r;
     r.c0 = t - ab - ab.template mul_small<NR>();
     r.c1 = ab.dbl();
@@ -40,9 +40,9 @@ struct Fp2T {
   template <u32 K>
   PCD_HD Fp2T mul_small() const { Fp2T r; r.c0 = c0.template mul_small<K>(); r.c1 = c1.template mul_small<K>(); return r; }
   PCD_HD Fp2T inverse() const {
-    B n = c0.sqr() - c1.sqr().template mul_small<NR>();
+    B n = B::mul_ni(c0, c0) - B::mul_ni(c1, c1).template mul_small<NR>();
     B ni = n.inverse();
-    Fp2T r; r.c0 = c0 * ni; r.c1 = (c1 * ni).neg();
+    Fp2T r; r.c0 = B::mul_ni(c0, ni); r.c1 = B::mul_ni(c1, ni).neg();
     return r;
   }
   // ark-ec "is y the larger of {y,-y}": compare the highest coefficient first
@@ -68,20 +68,21 @@ struct Fp3T {
   PCD_HD Fp3T dbl() const { Fp3T r; r.c0 = c0.dbl(); r.c1 = c1.dbl(); r.c2 = c2.dbl(); return r; }
   // Karatsuba: 6 base products
   PCD_HD friend Fp3T operator*(const Fp3T& a, const Fp3T& b) {
-    B v0 = a.c0 * b.c0, v1 = a.c1 * b.c1, v2 = a.c2 * b.c2;
+    B v0 = B::mul_ni(a.c0, b.c0), v1 = B::mul_ni(a.c1, b.c1), v2 = B::mul_ni(a.c2, b.c2);
     Fp3T r;
-    r.c0 = v0 + ((a.c1 + a.c2) * (b.c1 + b.c2) - v1 - v2).template mul_small<NR>();
-    r.c1 = (a.c0 + a.c1) * (b.c0 + b.c1) - v0 - v1 + v2.template mul_small<NR>();
-    r.c2 = (a.c0 + a.c2) * (b.c0 + b.c2) - v0 - v2 + v1;
+    r.c0 = v0 + (B::mul_ni(a.c1 + a.c2, b.c1 + b.c2) - v1 - v2).template mul_small<NR>();
+    r.c1 = B::mul_ni(a.c0 + a.c1, b.c0 + b.c1) - v0 - v1 + v2.template mul_small<NR>();
+    r.c2 = B::mul_ni(a.c0 + a.c2, b.c0 + b.c2) - v0 - v2 + v1;
     return r;
   }
   // Chung-Hasan SQR2: 5 base products
   PCD_HD Fp3T sqr() const {
-    B s0 = c0.sqr();
-    B s1 = (c0 * c1).dbl();
-    B s2 = (c0 - c1 + c2).sqr();
-    B s3 = (c1 * c2).dbl();
-    B s4 = c2.sqr();
+    B s0 = B::mul_ni(c0, c0);
+    B s1 = B::mul_ni(c0, c1).dbl();
+    B t2 = c0 - c1 + c2;
+    B s2 = B::mul_ni(t2, t2);
+    B s3 = B::mul_ni(c1, c2).dbl();
+    B s4 = B::mul_ni(c2, c2);
     Fp3T r;
     r.c0 = s0 + s3.template mul_small<NR>();
     r.c1 = s1 + s4.template mul_small<NR>();
@@ -91,12 +92,12 @@ struct Fp3T {
   template <u32 K>
   PCD_HD Fp3T mul_small() const { Fp3T r; r.c0 = c0.template mul_small<K>(); r.c1 = c1.template mul_small<K>(); r.c2 = c2.template mul_small<K>(); return r; }
   PCD_HD Fp3T inverse() const {
-    B t0 = c0.sqr() - (c1 * c2).template mul_small<NR>();
-    B t1 = c2.sqr().template mul_small<NR>() - c0 * c1;
-    B t2 = c1.sqr() - c0 * c2;
-    B n = c0 * t0 + (c2 * t1 + c1 * t2).template mul_small<NR>();
+    B t0 = B::mul_ni(c0, c0) - B::mul_ni(c1, c2).template mul_small<NR>();
+    B t1 = B::mul_ni(c2, c2).template mul_small<NR>() - B::mul_ni(c0, c1);
+    B t2 = B::mul_ni(c1, c1) - B::mul_ni(c0, c2);
+    B n = B::mul_ni(c0, t0) + (B::mul_ni(c2, t1) + B::mul_ni(c1, t2)).template mul_small<NR>();
     B ni = n.inverse();
-    Fp3T r; r.c0 = t0 * ni; r.c1 = t1 * ni; r.c2 = t2 * ni;
+    Fp3T r; r.c0 = B::mul_ni(t0, ni); r.c1 = B::mul_ni(t1, ni); r.c2 = B::mul_ni(t2, ni);
     return r;
   }
   PCD_HD bool lexicographically_largest() const {

@@ -1,0 +1,314 @@
+// groth16.cu -- R1CS -> QAP witness map and the assembly of a Groth16 proof on the GPU.
+//
+// Replaces ark-groth16 R1CStoQAP::witness_map (r1cs_to_qap.rs) and create_proof_with_reduction
+// (prover.rs) -- SURVEY.md B.1 / B.2 -- reached from IC::MainSNARK::prove / IC::HelpSNARK::prove
+// (/root/reference/src/ec_cycle_pcd/mod.rs:171,179).  Field results are canonical, so h and the
+// affine proof points are bit-identical to any correct CPU evaluation of the same formulas.
+#include "groth16.cuh"
+
+#include "msm_ops.cuh"
+#include "ntt.cuh"
+
+template <class F>
+__device__ __forceinline__ F ld10(const u32* g, size_t idx) {
+  const uint2* p = reinterpret_cast<const uint2*>(g + idx * 10);
+  F r;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    uint2 v = __ldg(p + i);
+    r.l[2 * i] = v.x;
+    r.l[2 * i + 1] = v.y;
+  }
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void st10(u32* g, size_t idx, const F& a) {
+  uint2* p = reinterpret_cast<uint2*>(g + idx * 10);
+#pragma unroll
+  for (int i = 0; i < 5; i++) p[i] = make_uint2(a.l[2 * i], a.l[2 * i + 1]);
+}
+
+// ---- CSR sparse matrix x assignment (ark-groth16 evaluate_constraint) ---------------------------
+// blockIdx.y selects the matrix.  out[i] = <M_i, z> for i < m; a[m + j] = z[j] for the instance
+// variables (the rows that make the QAP's A polynomials linearly independent); 0 elsewhere.
+template <class F>
+__global__ void __launch_bounds__(128) spmv_kernel(CsrDev A, CsrDev B, CsrDev C, const u32* __restrict__ z, size_t m,
+                                                   size_t num_inputs, size_t n, u32* a, u32* b, u32* c) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  int mat = blockIdx.y;
+  const CsrDev& M = mat == 0 ? A : (mat == 1 ? B : C);
+  u32* out = mat == 0 ? a : (mat == 1 ? b : c);
+  F acc = F::zero();
+  if (i < m) {
+    const F one = F::one();
+    u32 lo = M.row_ptr[i], hi = M.row_ptr[i + 1];
+    for (u32 k = lo; k < hi; k++) {
+      F co = ld10<F>(M.val, k);
+      F v = ld10<F>(z, M.col[k]);
+      acc = acc + (co == one ? v : co * v);
+    }
+  } else if (mat == 0 && i < m + num_inputs) {
+    acc = ld10<F>(z, i - m);
+  }
+  st10<F>(out, i, acc);
+}
+
+// h[i] = (a[i] * b[i] - c[i]) / Z(g w^i),  Z constant on the coset: g^n - 1
+template <class F>
+__global__ void __launch_bounds__(256) qap_combine_kernel(u32* a, const u32* __restrict__ b, const u32* __restrict__ c,
+                                                          const u32* __restrict__ zinv, size_t n) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  F zi = ld10<F>(zinv, 0);
+  F r = (ld10<F>(a, i) * ld10<F>(b, i) - ld10<F>(c, i)) * zi;
+  st10<F>(a, i, r);
+}
+
+template <class F>
+static int witness_map_t(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h) {
+  int field = r->pairing == PCDGPU_MNT4_298 ? PCDGPU_FIELD_R4 : PCDGPU_FIELD_Q4;
+  size_t n = r->n;
+  int log_n = r->log_n;
+  if (log_n > F::Params::TWO_ADICITY) {
+    ctx->set_error("witness map needs a 2^%d domain; the field's 2-adicity is %d", log_n, F::Params::TWO_ADICITY);
+    return PCDGPU_E_DOMAIN;
+  }
+  void *a, *b, *c;
+  PCD_TRY(ctx->scratch(SLOT_WM_A, n * 40, &a));
+  PCD_TRY(ctx->scratch(SLOT_WM_B, n * 40, &b));
+  PCD_TRY(ctx->scratch(SLOT_WM_C, n * 40, &c));
+  dim3 grid((unsigned)((n + 127) / 128), 3);
+  spmv_kernel<F><<<grid, 128, 0, ctx->stream>>>(r->A, r->B, r->C, (const u32*)d_z, r->m, r->num_inputs, n, (u32*)a,
+                                                (u32*)b, (u32*)c);
+  PCD_CUDA(ctx, cudaGetLastError());
+  void* v[3] = {a, b, c};
+  for (int i = 0; i < 3; i++) {
+    PCD_TRY(ntt_run(ctx, field, v[i], log_n, 1, 0));
+    PCD_TRY(ntt_run(ctx, field, v[i], log_n, 0, 1));
+  }
+  NttTablesDev t;
+  PCD_TRY(ntt_tables(ctx, field, log_n, &t));
+  qap_combine_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((u32*)a, (const u32*)b, (const u32*)c,
+                                                                              t.zinv, n);
+  PCD_CUDA(ctx, cudaGetLastError());
+  PCD_TRY(ntt_run(ctx, field, a, log_n, 1, 1));
+  *d_h = a;
+  return 0;
+}
+
+int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h) {
+  if (r->pairing == PCDGPU_MNT4_298) return witness_map_t<FpR4>(ctx, r, d_z, d_h);
+  return witness_map_t<FpQ4>(ctx, r, d_z, d_h);
+}
+
+// ---- proof assembly ------------------------------------------------------------------------------
+// consts (affine, device): [0] alpha_g1 [1] beta_g1 [2] delta_g1 [3] a_query[0] [4] b_g1_query[0] as G1,
+// then beta_g2, delta_g2, b_g2_query[0] as G2.  sums (xyzz, device): h, l, a, b_g1 (G1), b_g2 (G2).
+// Scalars r, s: plain integers (10 x u32).
+//
+// Phase 1 (independent of the MSMs, runs beside the witness map): four scalar multiplications
+//   t0 = r delta1, t1 = s delta1, t2 = (r s mod p) delta1, t3 = s delta2    -- one thread each.
+template <class G1, class G2>
+__global__ void groth16_phase1_kernel(const void* __restrict__ c1, const void* __restrict__ c2, const u32* __restrict__ rs,
+                                      void* __restrict__ t1out, void* __restrict__ t2out) {
+  typedef Fp<typename G1::ScalarParams> Fr;
+  if (threadIdx.x & 31) return;
+  int w = threadIdx.x >> 5;
+  Fr r, s;
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    r.l[i] = rs[i];
+    s.l[i] = rs[10 + i];
+  }
+  if (w < 3) {
+    XYZZ<G1> d = XYZZ<G1>::from_affine(ld_aff<G1>(c1, 2));
+    Fr k = w == 0 ? r : s;
+    if (w == 2) k = (r.to_mont() * s.to_mont()).from_mont();
+    XYZZ<G1> o = XYZZ<G1>::mul(d, k.l, 10);
+    st_xyzz<G1>(t1out, w, o);
+  } else {
+    XYZZ<G2> d = XYZZ<G2>::from_affine(ld_aff<G2>(c2, 1));
+    XYZZ<G2> o = XYZZ<G2>::mul(d, s.l, 10);
+    st_xyzz<G2>(t2out, 0, o);
+  }
+}
+
+// Phase 2: warp 0: g_a, g1_b, g_c (Straus double-scalar multiplication s g_a + r g1_b);
+//          warp 1: g2_b.  Output affine A || B || C.
+template <class G1, class G2>
+__global__ void groth16_phase2_kernel(const void* __restrict__ c1, const void* __restrict__ c2, const u32* __restrict__ rs,
+                                      const void* __restrict__ t1, const void* __restrict__ t2,
+                                      const void* __restrict__ sums1, const void* __restrict__ sum2,
+                                      void* __restrict__ out) {
+  if (threadIdx.x & 31) return;
+  int w = threadIdx.x >> 5;
+  char* o = reinterpret_cast<char*>(out);
+  typedef typename G1::F F1;
+  typedef typename G2::F F2;
+  if (w == 0) {
+    // g_a = r delta + a_query[0] + a_acc + alpha
+    XYZZ<G1> ga = ld_xyzz<G1>(t1, 0);
+    ga.madd(ld_aff<G1>(c1, 3));
+    ga.add(ld_xyzz<G1>(sums1, 2));
+    ga.madd(ld_aff<G1>(c1, 0));
+    // g1_b = s delta + b_g1_query[0] + b_acc + beta
+    XYZZ<G1> gb = ld_xyzz<G1>(t1, 1);
+    gb.madd(ld_aff<G1>(c1, 4));
+    gb.add(ld_xyzz<G1>(sums1, 3));
+    gb.madd(ld_aff<G1>(c1, 1));
+    // s g_a + r g1_b, jointly (Straus): one doubling chain, table {ga, gb, ga + gb}
+    XYZZ<G1> gab = ga;
+    gab.add(gb);
+    XYZZ<G1> acc = XYZZ<G1>::inf();
+    bool started = false;
+    for (int i = 9; i >= 0; i--) {
+      u32 rw = rs[i], sw = rs[10 + i];
+      for (int b = 31; b >= 0; b--) {
+        if (started) acc = acc.dbl();
+        u32 sel = ((sw >> b) & 1) | (((rw >> b) & 1) << 1);
+        if (sel) {
+          acc.add(sel == 1 ? ga : (sel == 2 ? gb : gab));
+          started = true;
+        }
+      }
+    }
+    // g_c = s g_a + r g1_b - (r s) delta + l_acc + h_acc
+    acc.add(ld_xyzz<G1>(t1, 2).neg());
+    acc.add(ld_xyzz<G1>(sums1, 1));
+    acc.add(ld_xyzz<G1>(sums1, 0));
+    AffinePoint<F1> A = ga.to_affine(), Cc = acc.to_affine();
+    st_aff<G1>(o, 0, A);
+    st_aff<G1>(o + sizeof(AffinePoint<F1>) + sizeof(AffinePoint<F2>), 0, Cc);
+  } else if (w == 1) {
+    // g2_b = s delta2 + b_g2_query[0] + b2_acc + beta2
+    XYZZ<G2> gb = ld_xyzz<G2>(t2, 0);
+    gb.madd(ld_aff<G2>(c2, 2));
+    gb.add(ld_xyzz<G2>(sum2, 0));
+    gb.madd(ld_aff<G2>(c2, 0));
+    st_aff<G2>(o + sizeof(AffinePoint<F1>), 0, gb.to_affine());
+  }
+}
+
+template <class G1, class G2>
+static int groth16_assemble_t(pcdgpu_ctx* ctx, cudaStream_t st, int phase, const void* c1, const void* c2,
+                              const u32* d_rs, void* t1, void* t2, const void* sums1, const void* sum2, void* d_out) {
+  if (phase == 1) groth16_phase1_kernel<G1, G2><<<1, 128, 0, st>>>(c1, c2, d_rs, t1, t2);
+  else groth16_phase2_kernel<G1, G2><<<1, 64, 0, st>>>(c1, c2, d_rs, t1, t2, sums1, sum2, d_out);
+  PCD_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+int groth16_assemble(pcdgpu_ctx* ctx, cudaStream_t st, int pairing, int phase, const void* c1, const void* c2,
+                     const u32* d_rs, void* t1, void* t2, const void* sums1, const void* sum2, void* d_out) {
+  if (pairing == PCDGPU_MNT4_298)
+    return groth16_assemble_t<CurveMnt4G1, CurveMnt4G2>(ctx, st, phase, c1, c2, d_rs, t1, t2, sums1, sum2, d_out);
+  return groth16_assemble_t<CurveMnt6G1, CurveMnt6G2>(ctx, st, phase, c1, c2, d_rs, t1, t2, sums1, sum2, d_out);
+}
+
+// ---- ark-serialize compressed proof bytes -------------------------------------------------------
+template <class F>
+__device__ void ser_fp(const F& a, unsigned char* out, unsigned char flags) {
+  F v = a.from_mont();
+  for (int i = 0; i < 38; i++) out[i] = (unsigned char)(v.l[i >> 2] >> ((i & 3) * 8));
+  out[37] |= flags;
+}
+template <class P>
+__device__ unsigned char* ser_x(const Fp<P>& x, unsigned char* out, unsigned char flags) {
+  ser_fp(x, out, flags);
+  return out + 38;
+}
+template <class B, u32 NR>
+__device__ unsigned char* ser_x(const Fp2T<B, NR>& x, unsigned char* out, unsigned char flags) {
+  ser_fp(x.c0, out, 0);
+  ser_fp(x.c1, out + 38, flags);
+  return out + 76;
+}
+template <class B, u32 NR>
+__device__ unsigned char* ser_x(const Fp3T<B, NR>& x, unsigned char* out, unsigned char flags) {
+  ser_fp(x.c0, out, 0);
+  ser_fp(x.c1, out + 38, 0);
+  ser_fp(x.c2, out + 76, flags);
+  return out + 114;
+}
+template <class F>
+__device__ unsigned char* ser_point(const AffinePoint<F>& p, unsigned char* out) {
+  if (p.is_inf()) return ser_x(F::zero(), out, 0x40);
+  return ser_x(p.x, out, p.y.lexicographically_largest() ? 0x80 : 0);
+}
+template <class G1, class G2>
+__global__ void groth16_serialize_kernel(const void* __restrict__ proof, unsigned char* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  typedef typename G1::F F1;
+  typedef typename G2::F F2;
+  const char* p = reinterpret_cast<const char*>(proof);
+  unsigned char* o = out;
+  o = ser_point<F1>(ld_aff<G1>(p, 0), o);
+  o = ser_point<F2>(ld_aff<G2>(p + sizeof(AffinePoint<F1>), 0), o);
+  o = ser_point<F1>(ld_aff<G1>(p + sizeof(AffinePoint<F1>) + sizeof(AffinePoint<F2>), 0), o);
+}
+int groth16_serialize(pcdgpu_ctx* ctx, int pairing, const void* d_proof, unsigned char* d_out) {
+  if (pairing == PCDGPU_MNT4_298) groth16_serialize_kernel<CurveMnt4G1, CurveMnt4G2><<<1, 32, 0, ctx->stream>>>(d_proof, d_out);
+  else groth16_serialize_kernel<CurveMnt6G1, CurveMnt6G2><<<1, 32, 0, ctx->stream>>>(d_proof, d_out);
+  PCD_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// ---- integer-pipe microbenchmarks -----------------------------------------------------------------
+// 8 independent 32x32+64 multiply-add chains per thread (IMAD.WIDE.U32): the IMAD roof of SURVEY.md 8d.
+__global__ void __launch_bounds__(256) bench_imad_kernel(unsigned long long* out, int iters, u32 seed) {
+  unsigned long long acc[8];
+  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; j++) acc[j] = j + threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) {
+        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a + j), "r"(b));
+      }
+    }
+  }
+  unsigned long long s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= acc[j];
+  if (s == 0x1234567ull) out[0] = s;
+}
+// dependent Montgomery products (the prover's inner loop): 2 independent chains per thread
+template <class F>
+__global__ void __launch_bounds__(256) bench_modmul_kernel(u32* out, int iters, u32 seed) {
+  F x = F::one(), y = F::r2();
+  x.l[0] ^= (seed + threadIdx.x) & 0xffff;
+  y.l[0] ^= (seed + blockIdx.x) & 0xffff;
+  for (int i = 0; i < iters; i++) {
+    x = x * y;
+    y = y * x;
+  }
+  if (x.l[0] == 0x12345u && y.l[3] == 7u) out[0] = x.l[1];
+}
+
+int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double* ms_out) {
+  void* d;
+  PCD_TRY(ctx->scratch(SLOT_MISC, 4096, &d));
+  cudaEvent_t e0, e1;
+  PCD_CUDA(ctx, cudaEventCreate(&e0));
+  PCD_CUDA(ctx, cudaEventCreate(&e1));
+  int blocks = ctx->sm_count * 8;
+  double per_thread = modmul ? 2.0 * iters : 64.0 * iters;
+  for (int rep = 0; rep < 2; rep++) {  // first round warms up
+    PCD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
+    if (modmul == 1) bench_modmul_kernel<FpR4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 2) bench_modmul_kernel<FpQ4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else bench_imad_kernel<<<blocks, 256, 0, ctx->stream>>>((unsigned long long*)d, iters, 7u);
+    PCD_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
+    PCD_CUDA(ctx, cudaEventSynchronize(e1));
+  }
+  float ms = 0;
+  PCD_CUDA(ctx, cudaEventElapsedTime(&ms, e0, e1));
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  *ms_out = ms;
+  *ops_per_s = per_thread * 256.0 * blocks / (ms * 1e-3);
+  return 0;
+}

@@ -1,0 +1,46 @@
+// groth16.cuh -- device-resident objects behind the opaque ABI handles, and the internal
+// interface of groth16.cu.
+#pragma once
+#include "common.cuh"
+#include "vecio.cuh"
+
+struct CsrDev {
+  const u32* row_ptr;  // m + 1
+  const u32* col;      // nnz
+  const u32* val;      // nnz x 10 words, Montgomery
+};
+
+struct pcdgpu_r1cs {
+  pcdgpu_ctx* ctx;
+  int pairing;
+  size_t m, num_inputs, num_witness, n;
+  int log_n;
+  CsrDev A, B, C;
+  void* storage;  // one allocation holding all nine arrays
+};
+
+struct pcdgpu_bases {
+  pcdgpu_ctx* ctx;
+  int curve;
+  size_t n;       // points
+  void* points;   // n affine points (device)
+  int c, nwin;    // precomputed table parameters (c = 0: none)
+  void* table;    // nwin x n affine points: table[j * n + i] = 2^(c j) * points[i]
+};
+
+struct pcdgpu_pk {
+  pcdgpu_ctx* ctx;
+  int pairing;
+  size_t num_vars, num_inputs, h_len;
+  pcdgpu_bases *a_query, *b_g1_query, *b_g2_query, *h_query, *l_query;
+  void* consts_g1;  // alpha_g1, beta_g1, delta_g1, a_query[0], b_g1_query[0]
+  void* consts_g2;  // beta_g2, delta_g2, b_g2_query[0]
+};
+
+// a, b, c <- matrices x z; h = coset_ifft((coset_fft(ifft a) * coset_fft(ifft b) - coset_fft(ifft c)) / Z).
+// *d_h points into the context's scratch (n elements, Montgomery form).
+int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h);
+int groth16_assemble(pcdgpu_ctx* ctx, cudaStream_t st, int pairing, int phase, const void* c1, const void* c2,
+                     const u32* d_rs, void* t1, void* t2, const void* sums1, const void* sum2, void* d_out);
+int groth16_serialize(pcdgpu_ctx* ctx, int pairing, const void* d_proof, unsigned char* d_out);
+int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double* ms_out);

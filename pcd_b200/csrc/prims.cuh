@@ -17,7 +17,9 @@ typedef uint64_t u64;
 #if defined(__CUDACC__)
 #define PCD_HD __host__ __device__ __forceinline__
 #define PCD_D __device__ __forceinline__
+#define PCD_NOINLINE __host__ __device__ __noinline__
 #else
+#define PCD_NOINLINE
 #define PCD_HD inline
 #define PCD_D inline
 #endif

@@ -1,0 +1,184 @@
+"""Host-side mirror of the reference's SNARK interface for the Groth16 proving path.
+
+In the reference, `ECCyclePCD::prove` calls `IC::MainSNARK::prove(&pk.main_pk, main_circuit, rng)` and
+`IC::HelpSNARK::prove(&pk.help_pk, help_circuit, rng)` (/root/reference/src/ec_cycle_pcd/mod.rs:171,179)
+with `MainSNARK = Groth16<MNT4_298>` / `HelpSNARK = Groth16<MNT6_298>`
+(/root/reference/tests/mnt4_groth16.rs:23-30).  Constraint synthesis stays on the CPU side of the
+boundary; what crosses it is ark-relations' `ConstraintMatrices` (CSR rows of (coeff, col)), the
+full assignment z = instance || witness, the `ProvingKey` and the two field elements r, s drawn by
+the caller's RNG (r first, then s: ark-groth16 prover.rs `create_random_proof`).  Names and argument
+meaning follow ark-groth16 / ark-snark; everything numeric happens in libpcdgpu.so.
+"""
+from __future__ import annotations
+
+import ctypes
+from dataclasses import dataclass
+from typing import Callable, Optional, Tuple
+
+import numpy as np
+
+from . import lib as L
+
+CSR = Tuple[np.ndarray, np.ndarray, np.ndarray]  # (row_ptr u32[m+1], col u32[nnz], val u64[nnz,5] Montgomery)
+
+
+@dataclass
+class ConstraintMatrices:
+    """ark-relations `ConstraintMatrices`: instance variables first (column 0 is the constant 1)."""
+
+    pairing: int
+    num_instance_variables: int
+    num_witness_variables: int
+    a: CSR
+    b: CSR
+    c: CSR
+
+    @property
+    def num_constraints(self) -> int:
+        return len(self.a[0]) - 1
+
+
+@dataclass
+class ProvingKey:
+    """ark-groth16 `ProvingKey<E>` (vk.alpha_g1, vk.beta_g2, vk.delta_g2 flattened in)."""
+
+    pairing: int
+    alpha_g1: np.ndarray
+    beta_g1: np.ndarray
+    delta_g1: np.ndarray
+    beta_g2: np.ndarray
+    delta_g2: np.ndarray
+    a_query: np.ndarray
+    b_g1_query: np.ndarray
+    b_g2_query: np.ndarray
+    h_query: np.ndarray
+    l_query: np.ndarray
+
+
+@dataclass
+class Proof:
+    """ark-groth16 `Proof<E>`: a in G1, b in G2, c in G1 (affine limbs, Montgomery coordinates)."""
+
+    pairing: int
+    a: np.ndarray
+    b: np.ndarray
+    c: np.ndarray
+
+    def affine_limbs(self) -> np.ndarray:
+        return np.concatenate([self.a, self.b, self.c])
+
+
+class ProverIndex:
+    """Device-resident proving key + constraint matrices (uploaded once per circuit shape)."""
+
+    def __init__(self, ctx: L.Context, pk: ProvingKey, cm: ConstraintMatrices, precompute: bool = False):
+        if pk.pairing != cm.pairing:
+            raise ValueError("proving key and constraint matrices are over different pairings")
+        self.ctx, self.pairing = ctx, pk.pairing
+        self.num_inputs = cm.num_instance_variables
+        self.num_witness = cm.num_witness_variables
+        self.num_vars = self.num_inputs + self.num_witness
+        g1, g2 = L.G1_OF[pk.pairing], L.G2_OF[pk.pairing]
+        lib = ctx.lib
+        keep = []
+
+        def arr(a, dt, width=None):
+            a = np.ascontiguousarray(a, dtype=dt)
+            if width:
+                a = a.reshape(-1, width)
+            keep.append(a)
+            return ctypes.c_void_p(a.ctypes.data)
+
+        m = cm.num_constraints
+        args = []
+        for (ptr, col, val) in (cm.a, cm.b, cm.c):
+            args += [arr(ptr, np.uint32), arr(col, np.uint32), arr(val, np.uint64)]
+        h = ctypes.c_void_p()
+        ctx._check(lib.pcdgpu_r1cs_upload(ctx.h, pk.pairing, m, self.num_inputs, self.num_witness, *args,
+                                          ctypes.byref(h)))
+        self.r1cs = h
+        self.domain_size = lib.pcdgpu_r1cs_domain_size(h)
+        a_q = np.ascontiguousarray(pk.a_query, dtype=np.uint64).reshape(-1, L.AFFINE_LIMBS[g1])
+        if a_q.shape[0] != self.num_vars:
+            raise ValueError("a_query has %d points for %d variables" % (a_q.shape[0], self.num_vars))
+        h_q = np.ascontiguousarray(pk.h_query, dtype=np.uint64).reshape(-1, L.AFFINE_LIMBS[g1])
+        pkh = ctypes.c_void_p()
+        ctx._check(lib.pcdgpu_pk_upload(
+            ctx.h, pk.pairing, self.num_vars, self.num_inputs, h_q.shape[0],
+            arr(pk.alpha_g1, np.uint64), arr(pk.beta_g1, np.uint64), arr(pk.delta_g1, np.uint64),
+            arr(pk.beta_g2, np.uint64), arr(pk.delta_g2, np.uint64), arr(a_q, np.uint64),
+            arr(pk.b_g1_query, np.uint64), arr(pk.b_g2_query, np.uint64), arr(h_q, np.uint64),
+            arr(pk.l_query, np.uint64), int(precompute), ctypes.byref(pkh)))
+        self.pk = pkh
+
+    def close(self):
+        if getattr(self, "pk", None) and self.ctx.h:
+            self.ctx.lib.pcdgpu_pk_free(self.pk)
+            self.ctx.lib.pcdgpu_r1cs_free(self.r1cs)
+        self.pk = None
+        self.r1cs = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class Groth16:
+    """`Groth16<E>` as the reference binds it (SNARK + CircuitSpecificSetupSNARK); only `prove` and
+    its building blocks run on the GPU.  Setup / verify stay with the CPU implementation on the
+    Rust side of the boundary."""
+
+    def __init__(self, ctx: L.Context, pairing: int):
+        self.ctx, self.pairing = ctx, pairing
+
+    def index(self, pk: ProvingKey, cm: ConstraintMatrices, precompute: bool = False) -> ProverIndex:
+        return ProverIndex(self.ctx, pk, cm, precompute)
+
+    def witness_map(self, index: ProverIndex, z: np.ndarray) -> np.ndarray:
+        """R1CStoQAP::witness_map: the n coefficients of h."""
+        z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
+        if z.shape[0] != index.num_vars:
+            raise ValueError("assignment has %d elements for %d variables" % (z.shape[0], index.num_vars))
+        h = np.zeros((index.domain_size, 5), dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.pcdgpu_witness_map(self.ctx.h, index.r1cs, ctypes.c_void_p(z.ctypes.data),
+                                                        ctypes.c_void_p(h.ctypes.data)))
+        return h
+
+    def create_proof_with_reduction(self, index: ProverIndex, z: np.ndarray, r: np.ndarray, s: np.ndarray) -> Proof:
+        """ark-groth16 `create_proof_with_reduction(circuit, pk, r, s)`; r, s plain-integer limbs."""
+        z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
+        if z.shape[0] != index.num_vars:
+            raise ValueError("assignment has %d elements for %d variables" % (z.shape[0], index.num_vars))
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
+        out = np.zeros(2 * g1 + g2, dtype=np.uint64)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self.ctx._check(self.ctx.lib.pcdgpu_groth16_prove(self.ctx.h, index.pk, index.r1cs, vp(z), vp(r), vp(s),
+                                                          vp(out)))
+        return Proof(self.pairing, out[:g1].copy(), out[g1:g1 + g2].copy(), out[g1 + g2:].copy())
+
+    def create_proof_dev(self, index: ProverIndex, d_z: int, r: np.ndarray, s: np.ndarray) -> Proof:
+        """same with the assignment already resident on the GPU (device pointer)."""
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
+        out = np.zeros(2 * g1 + g2, dtype=np.uint64)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self.ctx._check(self.ctx.lib.pcdgpu_groth16_prove_dev(self.ctx.h, index.pk, index.r1cs, ctypes.c_void_p(d_z),
+                                                              vp(r), vp(s), vp(out)))
+        return Proof(self.pairing, out[:g1].copy(), out[g1:g1 + g2].copy(), out[g1 + g2:].copy())
+
+    def prove(self, index: ProverIndex, z: np.ndarray, rng: Callable[[int], np.ndarray]) -> Proof:
+        """`SNARK::prove(pk, circuit, rng)`: draws r, then s (`create_random_proof`), then proves.
+        rng(field_id) returns one uniformly random scalar as five plain-integer u64 limbs."""
+        f = L.SCALAR_FIELD_OF[self.pairing]
+        r = rng(f)
+        s = rng(f)
+        return self.create_proof_with_reduction(index, z, r, s)
+
+    def serialize(self, proof: Proof) -> bytes:
+        """ark-serialize canonical (compressed) bytes: 152 B (MNT4-298) / 190 B (MNT6-298)."""
+        return self.ctx.serialize_proof(self.pairing, proof.affine_limbs())
