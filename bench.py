@@ -1,0 +1,410 @@
+#!/usr/bin/env python3
+"""bench.py -- the Groth16 proving step of arkworks-rs/pcd (IC::MainSNARK::prove of ECCyclePCD::prove,
+/root/reference/src/ec_cycle_pcd/mod.rs:171) on B200, through libpcdgpu.so.
+
+One "step" = one Groth16 proof on MNT4-298 for a synthetic satisfiable R1CS whose evaluation domain
+is 2^LOG_N (default 2^20: 2^20 - 2 constraints, 2^20 variables): the CSR witness map with its seven
+NTTs, four G1 MSMs and one G2 MSM over the resident proving key, and the proof assembly.  With N > 1
+every GPU proves its own independent instance (independent PCD nodes: no data-path collective,
+weak scaling).  The JSON line also carries the two kernel figures BASELINE.json names: G1 MSM at
+2^20 points (Mpts/s) and the largest radix-2 NTT measured (GB/s), each with its roofline fraction.
+
+  python bench.py [--gpus N] [--steps K] [--warmup W] [--log-n 20] [--impl reference]
+
+`--impl reference`: the CPU arm.  The reference (Rust, un-vendored arkworks crates) cannot be built
+here, so this times oracle/c (the C++ restatement of the same algorithms in the shape arkworks runs
+them: 5x64 CIOS, arkworks' Pippenger with one task per window, per-stage parallel FFT) on all host
+threads, on a bounded sample of the same workload.
+"""
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+MODMUL_IMADS = 210            # 10-limb Montgomery product
+MADD_MODMULS = {1: 10, 2: 28, 3: 58}  # XYZZ mixed add 8M + 2S in Fq / Fq2 (M=3,S=2) / Fq3 (M=6,S=5)
+METRIC = "groth16_proofs_per_sec"
+
+
+def load_peaks():
+    path = os.path.join(ROOT, "MEASURED_PEAKS.json")
+    if os.path.exists(path):
+        with open(path) as f:
+            return json.load(f).get("hbm_gbs", 6650.0), "measured"
+    return 6650.0, "fallback"
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons sampled every 200 ms while the timed region runs."""
+
+    FIELDS = ("index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
+              "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+
+    def __init__(self, gpu_index):
+        self.gpu_index = gpu_index
+        self.proc = None
+        self.lines = []
+
+    def start(self):
+        try:
+            self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.gpu_index), "--query-gpu=" + self.FIELDS,
+                                          "--format=csv,noheader,nounits", "-lms", "200"], stdout=subprocess.PIPE,
+                                         stderr=subprocess.DEVNULL, text=True)
+            self.thread = threading.Thread(target=self._read, daemon=True)
+            self.thread.start()
+        except Exception:
+            self.proc = None
+
+    def _read(self):
+        for line in self.proc.stdout:
+            self.lines.append(line.strip())
+
+    def stop(self):
+        if not self.proc:
+            return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
+        self.proc.terminate()
+        try:
+            self.proc.wait(timeout=2)
+        except Exception:
+            self.proc.kill()
+        sm, mx, reasons = [], [], set()
+        names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
+        for ln in self.lines:
+            parts = [x.strip() for x in ln.split(",")]
+            if len(parts) < 9:
+                continue
+            try:
+                sm.append(float(parts[1]))
+                mx.append(float(parts[2]))
+            except ValueError:
+                continue
+            for nm, v in zip(names, parts[5:9]):
+                if v.lower().startswith("active"):
+                    reasons.add(nm)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(sm)}
+
+
+# ---------------------------------------------------------------------------------------------------
+# CPU arm (oracle/c): bounded sample of the same workload
+# ---------------------------------------------------------------------------------------------------
+def cpu_sample_setup(log_n_sample, seed=5):
+    """Instance of the same synthetic family at 2^log_n_sample for the CPU arm.  The key's points are
+    4096 random group elements tiled over the queries: Pippenger's running time does not depend on
+    which points it adds, and building 5 * 2^17 distinct points on the CPU would dominate the run."""
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    sys.path.insert(0, os.path.join(ROOT, "tests"))
+    import c_oracle as co
+    from pcd_b200 import synthetic
+
+    class NoGpu:  # the generator only needs fixed_base_mul for the key; give it the oracle's
+        def fixed_base_mul(self, curve, g, k):
+            k = np.ascontiguousarray(k, dtype=np.uint64).reshape(-1, 5)
+            if k.shape[0] <= 4096:
+                return co.fixed_base_mul(curve, g, k)
+            base = co.fixed_base_mul(curve, g, k[:4096])
+            reps = (k.shape[0] + 4095) // 4096
+            return np.tile(base, (reps, 1))[:k.shape[0]].copy()
+
+    inst = synthetic.make_groth16_instance(NoGpu(), 0, log_n_sample, seed=seed)
+    return co, inst
+
+
+def cpu_prove_once(co, inst, threads, r, s):
+    t0 = time.perf_counter()
+    co.groth16_prove(0, inst["pk"], inst["A"], inst["B"], inst["C"], inst["m"], inst["num_inputs"],
+                     inst["num_witness"], inst["z"], r, s, threads=threads)
+    return time.perf_counter() - t0
+
+
+def run_reference(args, rank, world):
+    if rank != 0:
+        return
+    log_n = args.log_n
+    sample_log = min(log_n, args.cpu_sample_log_n)
+    co, inst = cpu_sample_setup(sample_log)
+    threads = co.hw_threads()
+    rng = np.random.Generator(np.random.Philox(99))
+    draw = lambda: np.concatenate([rng.integers(0, 2 ** 64, 4, dtype=np.uint64), np.zeros(1, np.uint64)])
+    for _ in range(args.warmup):
+        cpu_prove_once(co, inst, threads, draw(), draw())
+    t = 0.0
+    for _ in range(args.steps):
+        t += cpu_prove_once(co, inst, threads, draw(), draw())
+    frac = 2.0 ** (sample_log - log_n)
+    value = frac * args.steps / t
+    sample = ("one Groth16 proof (MNT4-298) at 2^%d constraints per step = 2^%d of the 2^%d workload; value scaled "
+              "linearly by that fraction" % (sample_log, sample_log - log_n, log_n))
+    line = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * t / args.steps / frac,
+        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u64 (5x64-bit limbs)",
+        "data": "synthetic",
+        "config": {"workload": "groth16_mnt4_298_domain_2^%d" % log_n, "cpu_impl": "oracle/c (C++ restatement of "
+                   "arkworks' prover; the Rust reference cannot be built here)"},
+        "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
+        "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+    }
+    print(json.dumps(line), flush=True)
+
+
+# ---------------------------------------------------------------------------------------------------
+# GPU arm
+# ---------------------------------------------------------------------------------------------------
+def run_gpu(args, rank, local_rank, world):
+    import torch
+    import torch.distributed as dist
+
+    import pcd_b200
+    from pcd_b200 import synthetic
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    ctx = pcd_b200.Context(local_rank)
+    stream = torch.cuda.Stream(device=dev)  # a real (non-default) stream shared by torch's events and the library
+    torch.cuda.set_stream(stream)
+    ctx.set_stream(stream.cuda_stream)
+    log = (lambda m: print("[bench rank %d] %s" % (rank, m), file=sys.stderr, flush=True)) if rank == 0 else None
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    def max_over_ranks(x):
+        if world == 1:
+            return x
+        t = torch.tensor([x], dtype=torch.float64, device=dev)
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        return float(t.item())
+
+    imad_peak, _ = ctx.bench_imad(0, 4000)   # independent IMAD.WIDE.U32 chains: the integer roof
+    imad_chain, _ = ctx.bench_imad(3, 4000)  # the same multiply-adds as carry chains (.X form)
+
+    # ---- workload -----------------------------------------------------------------------------------
+    log_n = args.log_n
+    inst = synthetic.make_groth16_instance(ctx, pcd_b200.MNT4_298, log_n, seed=20261017 + 1000 * rank, verbose=log)
+    g = pcd_b200.Groth16(ctx, pcd_b200.MNT4_298)
+    pk = pcd_b200.ProvingKey(pairing=0, **inst["pk"])
+    cm = pcd_b200.ConstraintMatrices(0, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"])
+    idx = g.index(pk, cm, precompute=not args.no_precompute)
+    ctx.sync()
+    if log:
+        log("key resident on the GPU (precompute=%s)" % (not args.no_precompute))
+    nvars = inst["num_inputs"] + inst["num_witness"]
+    z_host = torch.from_numpy(inst["z"].view(np.int64)).pin_memory()
+    z_dev = z_host.to(dev)
+    p = inst["p"]
+    rng = np.random.Generator(np.random.Philox(7 + rank))
+
+    def draw():
+        v = int.from_bytes(rng.bytes(40), "little") % p
+        return v, np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(5)], dtype=np.uint64)
+
+    # correctness gate, outside the timed region: the proof must equal [known discrete logs] * G
+    r_i, r_l = draw()
+    s_i, s_l = draw()
+    proof = g.create_proof_dev(idx, z_dev.data_ptr(), r_l, s_l)
+    expect = synthetic.expected_proof(ctx, inst, r_i, s_i)
+    if not np.array_equal(proof.affine_limbs(), expect):
+        raise SystemExit("bench: GPU proof does not match its known discrete logarithms -- refusing to time it")
+    if log:
+        log("proof at 2^%d verified against the trapdoor" % log_n)
+
+    rs = [(draw()[1], draw()[1]) for _ in range(args.warmup + 2 * args.steps)]
+    for i in range(args.warmup):
+        g.create_proof_dev(idx, z_dev.data_ptr(), *rs[i])
+
+    # ---- timed region 1: inputs resident in HBM -------------------------------------------------------
+    sampler = ClockSampler(local_rank)
+    sampler.start()
+    ctx.lib.pcdgpu_profile_enable(ctx.h, 1)
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    barrier()
+    e0.record(stream)
+    for i in range(args.steps):
+        g.create_proof_dev(idx, z_dev.data_ptr(), *rs[args.warmup + i])
+    e1.record(stream)
+    barrier()
+    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    import ctypes
+    NC = 8
+    ms = (ctypes.c_double * NC)()
+    units = (ctypes.c_double * NC)()
+    spans = (ctypes.c_uint64 * NC)()
+    launches = ctypes.c_uint64()
+    ctx._check(ctx.lib.pcdgpu_profile_read(ctx.h, ms, units, spans, ctypes.byref(launches)))
+    ctx.lib.pcdgpu_profile_enable(ctx.h, 0)
+    prof = {"ms": list(ms), "units": list(units), "spans": list(spans)}
+
+    # ---- timed region 2: end to end through the C ABI with host buffers ---------------------------------
+    barrier()
+    e0.record(stream)
+    t_wall = time.perf_counter()
+    for i in range(args.steps):
+        r_l, s_l = rs[args.warmup + args.steps + i]
+        out = np.zeros(40, dtype=np.uint64)
+        ctx._check(ctx.lib.pcdgpu_groth16_prove(ctx.h, idx.pk, idx.r1cs, z_host.data_ptr(), r_l.ctypes.data,
+                                                s_l.ctypes.data, out.ctypes.data))
+    e1.record(stream)
+    barrier()
+    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall)))
+    clocks = sampler.stop()
+
+    # ---- kernel figures: G1 MSM at 2^20 points and the largest NTT --------------------------------------
+    extra = {}
+    if rank == 0:
+        extra = kernel_figures(args, ctx, dev, stream, imad_peak)
+    cpu_baseline = None
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        sample_log = min(log_n, args.cpu_sample_log_n)
+        co, cinst = cpu_sample_setup(sample_log)
+        threads = co.hw_threads()
+        cpu_prove_once(co, cinst, threads, rs[0][0], rs[0][1])
+        reps, t = 0, 0.0
+        while t < 10.0 and reps < 8:
+            t += cpu_prove_once(co, cinst, threads, rs[reps][0], rs[reps][1])
+            reps += 1
+        frac = 2.0 ** (sample_log - log_n)
+        cpu_baseline = {"value": frac * reps / t, "unit": "proofs/s", "cores": threads, "kind": "port",
+                        "sample": "%d Groth16 proofs at 2^%d constraints (2^%d of the workload, scaled linearly), "
+                                  "oracle/c on all host threads" % (reps, sample_log, sample_log - log_n)}
+    if rank != 0:
+        return
+    # ---- roofline of the dominant kernel class ----------------------------------------------------------
+    names = ["msm_digits_sort", "msm_accumulate_g1", "msm_accumulate_g2", "msm_reduce", "msm_horner", "ntt",
+             "spmv_qap", "assemble"]
+    total_ms = sum(prof["ms"]) or 1.0
+    shares = {names[i]: round(prof["ms"][i] / total_ms, 4) for i in range(NC)}
+    dom = max((1, 2), key=lambda i: prof["ms"][i])
+    deg = 1 if dom == 1 else 2
+    imads = prof["units"][dom] * MADD_MODMULS[deg] * MODMUL_IMADS
+    achieved = imads / (prof["ms"][dom] * 1e-3) / 1e12 if prof["ms"][dom] > 0 else 0.0
+    hbm_peak, hbm_src = load_peaks()
+    roofline = {
+        "kernel": names[dom], "bound": "imad", "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+        "frac": achieved / (imad_peak / 1e12), "traffic": None,
+        "peak_source": "measured live: independent IMAD.WIDE.U32 chains (carry-chain form: %.2f TIMAD/s)" % (imad_chain / 1e12),
+        "launch_ms_avg": prof["ms"][dom] / max(prof["spans"][dom], 1),
+        "work": "bucket entries x %d Montgomery products (XYZZ mixed add 8M+2S) x %d IMAD" % (MADD_MODMULS[deg], MODMUL_IMADS),
+    }
+    value = world * args.steps / (ms_dev * 1e-3)
+    e2e_value = world * args.steps / (ms_e2e * 1e-3)
+    line = {
+        "metric": METRIC, "value": value, "unit": "proofs/s", "n_gpus": world, "steps": args.steps,
+        "warmup": args.warmup, "ms_per_step": ms_dev / args.steps, "higher_is_better": True, "scaling": "weak",
+        "vs_baseline": None, "dtype": "u32 (10x32-bit limbs, Montgomery, integer only)", "data": "synthetic",
+        "config": {"workload": "groth16_mnt4_298_domain_2^%d" % log_n, "constraints": inst["m"], "variables": nvars,
+                   "msm_lengths": {"h": (1 << log_n) - 1, "l": inst["num_witness"], "a": nvars - 1, "b_g1": nvars - 1,
+                                   "b_g2": nvars - 1},
+                   "per_gpu": "independent instance per GPU (PCD nodes), no collective",
+                   "precomputed_window_tables": not args.no_precompute,
+                   "l2": "per-step inputs (proving-key tables, several GB) exceed the 126 MB L2"},
+        "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": nvars * 40 + 80,
+                "d2h_bytes_per_step": 320, "ms_per_step": ms_e2e / args.steps},
+        "gpu_launches": int(launches.value),
+        "clocks": clocks,
+        "roofline": roofline,
+        "kernel_time_shares": shares,
+        "imad_peak_measured": {"independent_TIMAD_s": imad_peak / 1e12, "carry_chain_TIMAD_s": imad_chain / 1e12},
+        "hbm_peak_GBps": {"value": hbm_peak, "source": hbm_src},
+    }
+    line.update(extra)
+    if cpu_baseline:
+        line["cpu_baseline"] = cpu_baseline
+    print(json.dumps(line), flush=True)
+
+
+def kernel_figures(args, ctx, dev, stream, imad_peak):
+    """G1 MSM Mpts/s at 2^20 (uniform scalars; resident bases with and without the window tables) and
+    the largest radix-2 NTT (coset FFT over r4), each timed with CUDA events on the launching stream."""
+    import torch
+
+    import pcd_b200
+    from pcd_b200 import synthetic
+    out = {}
+    hbm_peak, _ = load_peaks()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+
+    def timed(fn, reps):
+        for _ in range(3):
+            fn()
+        torch.cuda.synchronize()
+        e0.record(stream)
+        for _ in range(reps):
+            fn()
+        e1.record(stream)
+        torch.cuda.synchronize()
+        return e0.elapsed_time(e1) / reps
+
+    n = 1 << args.msm_log_n
+    pts = synthetic.random_points_dev(ctx, pcd_b200.MNT4_G1, n, seed=3)
+    sc = torch.from_numpy(synthetic.random_limbs(n, 0, 9).view(np.int64)).to(dev)
+    res = torch.zeros(64, dtype=torch.int64, device=dev)
+    ms_plain = timed(lambda: ctx.msm_dev(0, pts.data_ptr(), sc.data_ptr(), n, res.data_ptr()), 5)
+    bases = pcd_b200.Bases(ctx, 0, pts.cpu().numpy().view(np.uint64), precompute=True)
+    ms_pre = timed(lambda: bases.msm_dev(sc.data_ptr(), n, res.data_ptr()), 5)
+    bases.close()
+    del pts
+    out["g1_msm"] = {"points": n, "scalars": "uniform 298-bit", "mpts_per_s": n / ms_pre / 1e3, "ms": ms_pre,
+                     "mode": "resident bases with precomputed window tables",
+                     "variable_base_mpts_per_s": n / ms_plain / 1e3, "variable_base_ms": ms_plain}
+    log_n = args.ntt_log_n
+    x = torch.from_numpy(synthetic.random_limbs(1 << min(log_n, 20), 0, 5).view(np.int64)).to(dev)
+    if log_n > 20:
+        x = x.repeat(1 << (log_n - 20), 1)
+    ms_ntt = timed(lambda: ctx.ntt_dev(0, x.data_ptr(), log_n, False, True), 5)
+    gbs = 2 * 40 * (1 << log_n) / (ms_ntt * 1e-3) / 1e9
+    butterflies = (1 << (log_n - 1)) * log_n
+    timad = butterflies * MODMUL_IMADS / (ms_ntt * 1e-3) / 1e12
+    out["ntt"] = {"log_n": log_n, "field": "r4 (MNT4-298 Fr)", "flavour": "coset_fft", "ms": ms_ntt, "GBps": gbs}
+    out["roofline_ntt"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
+                           "traffic": None, "imad_frac": timad / (imad_peak / 1e12),
+                           "note": "algorithmic bytes 2*N*40; a 298-bit NTT is bound by the integer pipe, see imad_frac"}
+    return out
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=5)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--log-n", type=int, default=int(os.environ.get("PCD_BENCH_LOG_N", "20")))
+    ap.add_argument("--msm-log-n", type=int, default=20)
+    ap.add_argument("--ntt-log-n", type=int, default=24)
+    ap.add_argument("--cpu-sample-log-n", type=int, default=17)
+    ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    args = ap.parse_args()
+    args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
+    rank = int(os.environ.get("RANK", "0"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if args.impl == "reference":
+        run_reference(args, rank, world)
+        return
+    if world > 1:
+        import torch
+        import torch.distributed as dist
+        torch.cuda.set_device(local_rank)
+        dist.init_process_group("nccl", device_id=torch.device("cuda", local_rank))
+    try:
+        run_gpu(args, rank, local_rank, world)
+    finally:
+        if world > 1:
+            import torch.distributed as dist
+            dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -147,6 +147,17 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
  * larger root", 6 = infinity on the last byte): 152 B (MNT4) / 190 B (MNT6).  out: >= 190 bytes. */
 int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affine, uint8_t* out, size_t* out_len);
 
+/* ---- profiling ----------------------------------------------------------------------------------
+ * CUDA-event spans around the library's kernel groups, on the context's stream.  Classes (array
+ * index): 0 MSM digit/sort, 1 MSM bucket accumulation G1, 2 same G2, 3 MSM bucket reduction,
+ * 4 MSM window Horner, 5 NTT (all passes of a transform), 6 CSR mat-vec + QAP combine, 7 proof
+ * assembly.  read() synchronises, returns per class the summed milliseconds, algorithmic units
+ * (bucket entries, butterflies, matrix rows, ...) and span count since the last read / enable, the
+ * number of kernels launched, and resets.  Arrays hold PCDGPU_PROF_CLASSES entries. */
+#define PCDGPU_PROF_CLASSES 8
+int pcdgpu_profile_enable(pcdgpu_ctx* ctx, int on);
+int pcdgpu_profile_read(pcdgpu_ctx* ctx, double* ms, double* units, uint64_t* spans, uint64_t* launches);
+
 /* ---- measurement helpers ----------------------------------------------------------------------
  * Integer-pipe microbenchmark: every thread runs `iters` rounds of 8 independent
  * mad.wide-style chains; returns achieved 32x32->64 multiply-adds per second (the IMAD roof of

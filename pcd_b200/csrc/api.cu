@@ -101,6 +101,11 @@ void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx) {
     if (ctx->slot[i]) cudaFree(ctx->slot[i]);
   for (auto& kv : ctx->ntt_tables) cudaFree(kv.second.twiddles);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
+  if (ctx->prof_pinned) cudaFreeHost(ctx->prof_pinned);
+  for (auto& sp : ctx->spans) {
+    cudaEventDestroy(sp.a);
+    cudaEventDestroy(sp.b);
+  }
   cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
@@ -555,6 +560,39 @@ int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affin
   PCD_CUDA(ctx, cudaMemcpyAsync(out, d_out, out_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   *out_len = out_bytes;
+  return 0;
+}
+
+int pcdgpu_profile_enable(pcdgpu_ctx* ctx, int on) {
+  if (!ctx) return PCDGPU_E_ARG;
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  if (on && !ctx->prof_pinned) PCD_CUDA(ctx, cudaMallocHost((void**)&ctx->prof_pinned, 4096 * sizeof(unsigned)));
+  ctx->profiling = on != 0;
+  ctx->spans_used = 0;
+  ctx->launches = 0;
+  return 0;
+}
+
+int pcdgpu_profile_read(pcdgpu_ctx* ctx, double* ms, double* units, uint64_t* spans, uint64_t* launches) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, ms && units && spans && launches, "null pointer");
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  for (int i = 0; i < PROF_NSLOT; i++) {
+    ms[i] = 0;
+    units[i] = 0;
+    spans[i] = 0;
+  }
+  for (size_t i = 0; i < ctx->spans_used; i++) {
+    ProfSpan& sp = ctx->spans[i];
+    float t = 0;
+    if (cudaEventElapsedTime(&t, sp.a, sp.b) != cudaSuccess) continue;
+    ms[sp.slot] += t;
+    units[sp.slot] += sp.units_pinned >= 0 ? (double)ctx->prof_pinned[sp.units_pinned] : sp.units;
+    spans[sp.slot] += 1;
+  }
+  *launches = ctx->launches;
+  ctx->spans_used = 0;
+  ctx->launches = 0;
   return 0;
 }
 

@@ -34,6 +34,28 @@ struct NttTables {
   void* coset_inv = nullptr;  // g^-i / n, i < n
 };
 
+// Profiling classes: CUDA-event spans recorded around groups of launches on the context's stream
+// (pcdgpu_profile_enable / pcdgpu_profile_read); bench.py derives per-kernel time shares and the
+// roofline figures from them.
+enum {
+  PROF_MSM_SORT = 0,  // digits + histogram, scan, scatter
+  PROF_MSM_ACC_G1,    // bucket accumulation (msm_accumulate + heavy), G1 curves
+  PROF_MSM_ACC_G2,    // same, G2 curves
+  PROF_MSM_REDUCE,    // bucket reduction, per-window tree sum
+  PROF_MSM_TAIL,      // Horner over windows
+  PROF_NTT,           // all passes of one transform
+  PROF_SPMV,          // CSR mat-vec + pointwise QAP combine
+  PROF_ASSEMBLE,      // proof assembly (scalar multiplications, normalisation)
+  PROF_NSLOT
+};
+
+struct ProfSpan {
+  cudaEvent_t a, b;
+  int slot;
+  double units;      // algorithmic units processed inside the span (entries, butterflies, rows)
+  int units_pinned;  // >= 0: index into ctx->prof_pinned holding the unit count read back from the device
+};
+
 struct pcdgpu_ctx {
   int device = 0;
   int sm_count = 148;
@@ -48,6 +70,32 @@ struct pcdgpu_ctx {
   std::map<int, NttTables> ntt_tables;  // key = field * 64 + log_n
   void* pinned = nullptr;               // small pinned staging buffer
   size_t pinned_bytes = 0;
+  // profiling / counters
+  bool profiling = false;
+  std::vector<ProfSpan> spans;
+  size_t spans_used = 0;
+  unsigned* prof_pinned = nullptr;  // 4096 u32, pinned
+  unsigned long long launches = 0;  // kernels launched by this context since the last read
+
+  int prof_begin(int slot, double units) {
+    if (!profiling) return -1;
+    if (spans_used == spans.size()) {
+      if (spans.size() >= 4096) return -1;
+      ProfSpan sp;
+      cudaEventCreate(&sp.a);
+      cudaEventCreate(&sp.b);
+      spans.push_back(sp);
+    }
+    ProfSpan& sp = spans[spans_used];
+    sp.slot = slot;
+    sp.units = units;
+    sp.units_pinned = -1;
+    cudaEventRecord(sp.a, stream);
+    return (int)spans_used++;
+  }
+  void prof_end(int id) {
+    if (id >= 0) cudaEventRecord(spans[id].b, stream);
+  }
 
   void set_error(const char* fmt, ...) {
     va_list ap;

@@ -76,20 +76,22 @@ struct XYZZ {
     return p;
   }
   // Out-of-line entry points: for the G2 curves (C::OUTLINE) every group operation is a call, so a
-  // kernel holds one copy of each formula instead of one per use.
-  PCD_NOINLINE static void dbl_out(XYZZ* dst, const XYZZ* src) { *dst = src->dbl_impl(); }
-  PCD_NOINLINE static void madd_out(XYZZ* self, const AffinePoint<F>* a) { self->madd_impl(*a); }
-  PCD_NOINLINE static void add_out(XYZZ* self, const XYZZ* o) { self->add_impl(*o); }
+  // kernel holds one copy of each formula instead of one per use.  Operands and results travel BY
+  // VALUE (param space): passing the addresses of locals let nvcc 12.9's stack colouring overlay a
+  // result temporary with the live accumulator (seen in PTX: to_affine_out(dst == src)).
+  PCD_NOINLINE static XYZZ dbl_out(XYZZ src) { return src.dbl_impl(); }
+  PCD_NOINLINE static XYZZ madd_out(XYZZ self, AffinePoint<F> a) { self.madd_impl(a); return self; }
+  PCD_NOINLINE static XYZZ add_out(XYZZ self, XYZZ o) { self.add_impl(o); return self; }
   PCD_HD XYZZ dbl() const {
-    if constexpr (C::OUTLINE) { XYZZ r; dbl_out(&r, this); return r; }
+    if constexpr (C::OUTLINE) return dbl_out(*this);
     else return dbl_impl();
   }
   PCD_HD void madd(const AffinePoint<F>& a) {
-    if constexpr (C::OUTLINE) madd_out(this, &a);
+    if constexpr (C::OUTLINE) *this = madd_out(*this, a);
     else madd_impl(a);
   }
   PCD_HD void add(const XYZZ& o) {
-    if constexpr (C::OUTLINE) add_out(this, &o);
+    if constexpr (C::OUTLINE) *this = add_out(*this, o);
     else add_impl(o);
   }
   // dbl-2008-s-1
@@ -152,12 +154,8 @@ struct XYZZ {
     zz = zz * o.zz * PP;
     zzz = zzz * o.zzz * PPP;
   }
-  PCD_NOINLINE static void to_affine_out(AffinePoint<F>* dst, const XYZZ* src) { *dst = src->to_affine_impl(); }
-  PCD_HD AffinePoint<F> to_affine() const {
-    AffinePoint<F> r;
-    to_affine_out(&r, this);
-    return r;
-  }
+  PCD_NOINLINE static AffinePoint<F> to_affine_out(XYZZ src) { return src.to_affine_impl(); }
+  PCD_HD AffinePoint<F> to_affine() const { return to_affine_out(*this); }
   PCD_HD AffinePoint<F> to_affine_impl() const {
     if (is_inf()) return AffinePoint<F>::inf();
     F i = zzz.inverse();
@@ -168,11 +166,13 @@ struct XYZZ {
     return a;
   }
   // [k]P, k = nlimbs 32-bit little-endian limbs (plain integer), MSB-first double-and-add
-  PCD_NOINLINE static void mul_out(XYZZ* dst, const XYZZ* p, const u32* k, int nlimbs) { *dst = mul_impl(*p, k, nlimbs); }
+  struct Scalar320 { u32 w[10]; };
+  PCD_NOINLINE static XYZZ mul_out(XYZZ p, Scalar320 k, int nlimbs) { return mul_impl(p, k.w, nlimbs); }
   PCD_HD static XYZZ mul(const XYZZ& p, const u32* k, int nlimbs) {
-    XYZZ r;
-    mul_out(&r, &p, k, nlimbs);
-    return r;
+    Scalar320 kk;
+#pragma unroll
+    for (int i = 0; i < 10; i++) kk.w[i] = i < nlimbs ? k[i] : 0u;
+    return mul_out(p, kk, nlimbs);
   }
   PCD_HD static XYZZ mul_impl(const XYZZ& p, const u32* k, int nlimbs) {
     XYZZ acc = inf();

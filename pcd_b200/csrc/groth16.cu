@@ -79,9 +79,12 @@ static int witness_map_t(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z,
   PCD_TRY(ctx->scratch(SLOT_WM_B, n * 40, &b));
   PCD_TRY(ctx->scratch(SLOT_WM_C, n * 40, &c));
   dim3 grid((unsigned)((n + 127) / 128), 3);
+  int ps = ctx->prof_begin(PROF_SPMV, (double)r->m * 3);
+  ctx->launches += 2;
   spmv_kernel<F><<<grid, 128, 0, ctx->stream>>>(r->A, r->B, r->C, (const u32*)d_z, r->m, r->num_inputs, n, (u32*)a,
                                                 (u32*)b, (u32*)c);
   PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
   void* v[3] = {a, b, c};
   for (int i = 0; i < 3; i++) {
     PCD_TRY(ntt_run(ctx, field, v[i], log_n, 1, 0));
@@ -193,9 +196,12 @@ __global__ void groth16_phase2_kernel(const void* __restrict__ c1, const void* _
 template <class G1, class G2>
 static int groth16_assemble_t(pcdgpu_ctx* ctx, cudaStream_t st, int phase, const void* c1, const void* c2,
                               const u32* d_rs, void* t1, void* t2, const void* sums1, const void* sum2, void* d_out) {
+  int ps = st == ctx->stream ? ctx->prof_begin(PROF_ASSEMBLE, 1.0) : -1;
+  ctx->launches += 1;
   if (phase == 1) groth16_phase1_kernel<G1, G2><<<1, 128, 0, st>>>(c1, c2, d_rs, t1, t2);
   else groth16_phase2_kernel<G1, G2><<<1, 64, 0, st>>>(c1, c2, d_rs, t1, t2, sums1, sum2, d_out);
   PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
   return 0;
 }
 
@@ -275,6 +281,31 @@ __global__ void __launch_bounds__(256) bench_imad_kernel(unsigned long long* out
   for (int j = 0; j < 8; j++) s ^= acc[j];
   if (s == 0x1234567ull) out[0] = s;
 }
+// the same multiply-adds written as carry chains (mad.lo.cc / madc.hi.cc -> IMAD.WIDE.U32.X): this is
+// the form a multi-limb product needs, and what fp.cuh's operator* is made of.
+__global__ void __launch_bounds__(256) bench_imadx_kernel(u32* out, int iters, u32 seed) {
+  u32 acc[18];
+  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+#pragma unroll
+  for (int j = 0; j < 18; j++) acc[j] = j + threadIdx.x;
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+      acc[0] = prims::mad_lo_cc(a, b, acc[0]);
+      acc[1] = prims::madc_hi_cc(a, b, acc[1]);
+#pragma unroll
+      for (int j = 2; j < 16; j += 2) {
+        acc[j] = prims::madc_lo_cc(a + j, b, acc[j]);
+        acc[j + 1] = prims::madc_hi_cc(a + j, b, acc[j + 1]);
+      }
+      acc[16] = prims::addc(acc[16], 0);
+    }
+  }
+  u32 s = 0;
+#pragma unroll
+  for (int j = 0; j < 18; j++) s ^= acc[j];
+  if (s == 0x1234567u) out[0] = s;
+}
 // dependent Montgomery products (the prover's inner loop): 2 independent chains per thread
 template <class F>
 __global__ void __launch_bounds__(256) bench_modmul_kernel(u32* out, int iters, u32 seed) {
@@ -295,11 +326,12 @@ int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double
   PCD_CUDA(ctx, cudaEventCreate(&e0));
   PCD_CUDA(ctx, cudaEventCreate(&e1));
   int blocks = ctx->sm_count * 8;
-  double per_thread = modmul ? 2.0 * iters : 64.0 * iters;
+  double per_thread = modmul == 3 ? 64.0 * iters : (modmul ? 2.0 * iters : 64.0 * iters);
   for (int rep = 0; rep < 2; rep++) {  // first round warms up
     PCD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     if (modmul == 1) bench_modmul_kernel<FpR4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else if (modmul == 2) bench_modmul_kernel<FpQ4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 3) bench_imadx_kernel<<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else bench_imad_kernel<<<blocks, 256, 0, ctx->stream>>>((unsigned long long*)d, iters, 7u);
     PCD_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     PCD_CUDA(ctx, cudaEventSynchronize(e1));

@@ -337,6 +337,9 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   u32* heavy = cursor + cstride;
   PCD_CUDA(ctx, cudaMemsetAsync(counts, 0, cstride * 4, st));
   PCD_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
+  const int acc_slot = sizeof(typename C::F) > 40 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1;
+  int ps = ctx->prof_begin(PROF_MSM_SORT, (double)n * nwin);
+  ctx->launches += 7 + 3;  // seven kernels of this file + cub's scan (init, scan) + one d2d copy
   msm_digits_kernel<SP><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const u32*)d_scalars, scalars_mont, n, c, nwin,
                                                                     shared, (int*)dig, counts);
   PCD_CUDA(ctx, cudaGetLastError());
@@ -349,6 +352,12 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   msm_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const int*)dig, n, c, nwin, shared,
                                                                       plan.stride, plan.offset, cursor, (u32*)ent);
   PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
+  ps = ctx->prof_begin(acc_slot, (double)n * nwin);
+  if (ps >= 0 && ctx->prof_pinned) {  // exact number of bucket entries (non-zero digits) for the roofline
+    ctx->spans[ps].units_pinned = ps;
+    cudaMemcpyAsync(ctx->prof_pinned + ps, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st);
+  }
   msm_accumulate_kernel<C><<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(d_bases, offsets, (const u32*)ent,
                                                                                nbuckets, bkt, heavy);
   PCD_CUDA(ctx, cudaGetLastError());
@@ -358,6 +367,8 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   msm_accumulate_heavy_kernel<C><<<ctx->sm_count, MSM_HEAVY_THREADS, heavy_smem, st>>>(d_bases, offsets,
                                                                                       (const u32*)ent, bkt, heavy);
   PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
+  ps = ctx->prof_begin(PROF_MSM_REDUCE, (double)nbuckets);
   // reduction: L buckets per thread
   int logL = c - 1 >= 12 ? 4 : (c - 1 >= 6 ? 2 : 0);
   size_t T = B >> logL;
@@ -369,7 +380,10 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                                      (int)heavy_smem));
   msm_window_sum_kernel<C><<<rwin, MSM_HEAVY_THREADS, heavy_smem, st>>>(seg, (u32)T, wsum);
   PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
+  ps = ctx->prof_begin(PROF_MSM_TAIL, (double)rwin);
   msm_horner_kernel<C><<<1, 32, 0, st>>>(wsum, c, rwin, d_out);
   PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
   return 0;
 }

@@ -251,6 +251,8 @@ static int ntt_run_t(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int in
   void* scratch = nullptr;
   if (passes > 1) PCD_TRY(ctx->scratch(SLOT_NTT, ((size_t)40) << log_n, &scratch));
   int s = 0;
+  int ps = ctx->prof_begin(PROF_NTT, (double)log_n * (double)((size_t)1 << (log_n - 1)));
+  ctx->launches += passes;
   for (int p = 0; p < passes; p++) {
     int r = (log_n - s + (passes - p) - 1) / (passes - p);  // spread stages evenly, larger first
     NttPass a;
@@ -274,6 +276,7 @@ static int ntt_run_t(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int in
     PCD_CUDA(ctx, cudaGetLastError());
     s += r;
   }
+  ctx->prof_end(ps);
   return 0;
 }
 

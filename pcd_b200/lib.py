@@ -33,7 +33,7 @@ EXPORTS = [
     "pcdgpu_xyzz_sum", "pcdgpu_xyzz_download", "pcdgpu_fixed_base_mul", "pcdgpu_fixed_base_mul_dev",
     "pcdgpu_r1cs_upload", "pcdgpu_r1cs_free", "pcdgpu_r1cs_domain_size", "pcdgpu_witness_map", "pcdgpu_pk_upload",
     "pcdgpu_pk_free", "pcdgpu_groth16_prove", "pcdgpu_groth16_prove_dev", "pcdgpu_serialize_proof",
-    "pcdgpu_bench_imad",
+    "pcdgpu_profile_enable", "pcdgpu_profile_read", "pcdgpu_bench_imad",
 ]
 
 
@@ -93,6 +93,9 @@ def load():
     lib.pcdgpu_groth16_prove.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.pcdgpu_groth16_prove_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.pcdgpu_serialize_proof.argtypes = [vp, ci, vp, vp, ctypes.POINTER(sz)]
+    lib.pcdgpu_profile_enable.argtypes = [vp, ci]
+    lib.pcdgpu_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                        ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     lib.pcdgpu_bench_imad.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib

@@ -74,3 +74,149 @@ def random_points_dev(ctx: L.Context, curve: int, n: int, seed: int):
     ctx.fixed_base_mul_dev(curve, generator(curve), k.data_ptr(), n, pts.data_ptr())
     ctx.sync()
     return pts
+
+
+# ---- synthetic Groth16 instances (benchmarks; no CPU reference code involved) -------------------------
+def _limbs_from_ints(vals) -> np.ndarray:
+    """list of ints < 2^320 -> (n, 5) u64 limbs"""
+    b = b"".join(int(v).to_bytes(40, "little") for v in vals)
+    return np.frombuffer(b, dtype="<u8").copy().reshape(-1, 5)
+
+
+def _omega(field: int, log_n: int) -> int:
+    p = FIELD_P[field]
+    gen, s = (10, 34) if field == L.FIELD_R4 else (17, 17)
+    return pow(pow(gen, (p - 1) >> s, p), 1 << (s - log_n), p)
+
+
+def make_groth16_instance(ctx: L.Context, pairing: int, log_n: int, seed: int = 20261017, bitlike: float = 0.4,
+                          verbose=None):
+    """Satisfiable synthetic R1CS with 2^log_n - 2 constraints and 2 instance variables (domain size
+    exactly 2^log_n), its assignment, and a Groth16 proving key with a KNOWN trapdoor.
+
+    Shape: a `bitlike` fraction of the constraints are booleanity checks b*b = b on a
+    fresh 0/1 witness (what real circuits are full of); the others are w = <A_i,z> * <B_i,z> with 1-2
+    terms per row over earlier variables, coefficients from {1, -1, uniform}.  The key's group
+    elements are [scalar]G computed by the GPU's fixed-base kernel from the trapdoor's scalars, so
+    every proof can be checked against its discrete logarithms (`expected_logs`).  Returns a dict."""
+    import random
+    import time
+    t0 = time.time()
+    field = L.SCALAR_FIELD_OF[pairing]
+    p = FIELD_P[field]
+    n = 1 << log_n
+    m = n - 2
+    ni = 2
+    rnd = random.Random(seed)
+    z = [1, rnd.randrange(p)]
+    rows_a, rows_b, rows_c = [], [], []
+    bit_thr = int(bitlike * 1000)
+    for i in range(m):
+        nv = len(z)
+        if rnd.randrange(1000) < bit_thr:
+            z.append(rnd.getrandbits(1))
+            rows_a.append(((1, nv),))
+            rows_b.append(((1, nv),))
+            rows_c.append(((1, nv),))
+            continue
+        u, v, w = rnd.randrange(nv), rnd.randrange(nv), rnd.randrange(nv)
+        sel = rnd.randrange(3)
+        ca = 1 if sel == 0 else (p - 1 if sel == 1 else rnd.randrange(1, p))
+        ra = ((1, u), (ca, v))
+        rb = ((rnd.randrange(1, p), w),) if rnd.randrange(2) else ((1, w), (1, 0))
+        a = (z[u] + ca * z[v]) % p
+        b = sum(c * z[j] for c, j in rb) % p
+        z.append(a * b % p)
+        rows_a.append(ra)
+        rows_b.append(rb)
+        rows_c.append(((1, nv),))
+    nvars = len(z)
+    if verbose:
+        verbose("synthetic R1CS: %d constraints, %d variables (%.1f s)" % (m, nvars, time.time() - t0))
+    R = _R % p
+
+    def csr(rows):
+        ptr = np.zeros(len(rows) + 1, dtype=np.uint32)
+        cols, vals = [], []
+        for i, r in enumerate(rows):
+            for c, j in r:
+                cols.append(j)
+                vals.append(c * R % p)
+            ptr[i + 1] = len(cols)
+        return ptr, np.array(cols, dtype=np.uint32), _limbs_from_ints(vals)
+
+    A, B, C = csr(rows_a), csr(rows_b), csr(rows_c)
+    z_mont = _limbs_from_ints([v * R % p for v in z])
+    # ---- trapdoor scalars -------------------------------------------------------------------------
+    alpha, beta, delta, tau = (rnd.randrange(1, p) for _ in range(4))
+    omega = _omega(field, log_n)
+    zt = (pow(tau, n, p) - 1) % p
+    ninv = pow(n, -1, p)
+    ws, dens = [1] * n, [0] * n
+    w = 1
+    for i in range(n):
+        ws[i] = w
+        dens[i] = (tau - w) % p
+        w = w * omega % p
+    pref = [1] * (n + 1)
+    for i in range(n):
+        pref[i + 1] = pref[i] * dens[i] % p
+    inv_all = pow(pref[n], -1, p)
+    lag = [0] * n
+    cst = zt * ninv % p
+    for i in range(n - 1, -1, -1):
+        lag[i] = cst * ws[i] % p * (inv_all * pref[i] % p) % p
+        inv_all = inv_all * dens[i] % p
+    At, Bt, Ct = [0] * nvars, [0] * nvars, [0] * nvars
+    for rows, acc in ((rows_a, At), (rows_b, Bt), (rows_c, Ct)):
+        for i, r in enumerate(rows):
+            li = lag[i]
+            for c, j in r:
+                acc[j] += c * li
+    for j in range(ni):
+        At[j] += lag[m + j]
+    At = [x % p for x in At]
+    Bt = [x % p for x in Bt]
+    Ct = [x % p for x in Ct]
+    dinv = pow(delta, -1, p)
+    h_sc, cur = [0] * (n - 1), zt * dinv % p
+    for i in range(n - 1):
+        h_sc[i] = cur
+        cur = cur * tau % p
+    l_sc = [(beta * At[j] + alpha * Bt[j] + Ct[j]) % p * dinv % p for j in range(ni, nvars)]
+    if verbose:
+        verbose("trapdoor scalars done (%.1f s)" % (time.time() - t0))
+    # ---- group elements on the GPU ----------------------------------------------------------------
+    g1, g2 = L.G1_OF[pairing], L.G2_OF[pairing]
+    fb = lambda curve, vals: ctx.fixed_base_mul(curve, generator(curve), _limbs_from_ints(vals))
+    small1 = fb(g1, [alpha, beta, delta])
+    small2 = fb(g2, [beta, delta])
+    pk = dict(alpha_g1=small1[0], beta_g1=small1[1], delta_g1=small1[2], beta_g2=small2[0], delta_g2=small2[1],
+              a_query=fb(g1, At), b_g1_query=fb(g1, Bt), b_g2_query=fb(g2, Bt), h_query=fb(g1, h_sc),
+              l_query=fb(g1, l_sc))
+    if verbose:
+        verbose("proving key built on the GPU (%.1f s)" % (time.time() - t0))
+    az = sum(a * b for a, b in zip(z, At)) % p
+    bz = sum(a * b for a, b in zip(z, Bt)) % p
+    cz = sum(a * b for a, b in zip(z, Ct)) % p
+    l_part = sum(z[ni + j] * l_sc[j] for j in range(nvars - ni)) % p
+
+    def expected_logs(r: int, s: int):
+        """discrete logs (base G1 / G2 generator) of the proof (A, B, C) for randomness r, s"""
+        a_log = (alpha + az + r * delta) % p
+        b_log = (beta + bz + s * delta) % p
+        h_part = (az * bz - cz) % p * dinv % p
+        c_log = (l_part + h_part + s * a_log + r * b_log - r * s % p * delta) % p
+        return a_log, b_log, c_log
+
+    return dict(pairing=pairing, log_n=log_n, m=m, num_inputs=ni, num_witness=nvars - ni, A=A, B=B, C=C, z=z_mont,
+                pk=pk, expected_logs=expected_logs, p=p)
+
+
+def expected_proof(ctx: L.Context, inst, r: int, s: int) -> np.ndarray:
+    """A || B || C affine limbs computed from the instance's known discrete logs (GPU fixed-base)."""
+    a_log, b_log, c_log = inst["expected_logs"](r, s)
+    g1, g2 = L.G1_OF[inst["pairing"]], L.G2_OF[inst["pairing"]]
+    ac = ctx.fixed_base_mul(g1, generator(g1), _limbs_from_ints([a_log, c_log]))
+    b = ctx.fixed_base_mul(g2, generator(g2), _limbs_from_ints([b_log]))
+    return np.concatenate([ac[0], b[0], ac[1]])

@@ -73,6 +73,7 @@ static void ec_op(int op, const u32* p, const u32* q, const u32* k, int klimbs, 
     case 5: { r = XYZZ<C>::from_affine(P).dbl(); r = r.dbl(); break; }      // 4P
     case 6: { r = XYZZ<C>::from_affine(P).dbl(); XYZZ<C> s = XYZZ<C>::dbl_affine(P); r.add(s.neg()); break; }  // 2P - 2P
     case 7: { r = XYZZ<C>::from_affine(P).dbl(); XYZZ<C> s = XYZZ<C>::dbl_affine(P); r.add(s); break; }  // 2P + 2P via add
+    case 8: { r = XYZZ<C>::inf(); for (int d = 0; d < klimbs; d++) { r.madd(P); (void)r.to_affine(); } break; }  // repeated madd of the same affine point (fixed-base table construction)
     default: r = XYZZ<C>::inf();
   }
   stx(out, r.to_affine());

@@ -33,7 +33,7 @@ def main():
     out = {}
     ctx = pcd_b200.Context(0)
     dev = torch.device("cuda:0")
-    for mode, name in ((0, "imad_wide"), (1, "modmul_r4"), (2, "modmul_q4")):
+    for mode, name in ((0, "imad_wide"), (3, "imad_wide_carry_chain"), (1, "modmul_r4"), (2, "modmul_q4")):
         ops, ms = ctx.bench_imad(mode, 4000 if mode == 0 else 2000)
         out[name] = {"ops_per_s": ops, "ms": ms}
         print(name, "%.3e ops/s  %.3f ms" % (ops, ms), flush=True)
