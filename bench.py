@@ -315,6 +315,7 @@ def run_gpu(args, rank, local_rank, world):
         "clocks": clocks,
         "roofline": roofline,
         "kernel_time_shares": shares,
+        "kernel_ms_per_step": {names[i]: round(prof["ms"][i] / args.steps, 3) for i in range(NC)},
         "imad_peak_measured": {"independent_TIMAD_s": imad_peak / 1e12, "carry_chain_TIMAD_s": imad_chain / 1e12},
         "hbm_peak_GBps": {"value": hbm_peak, "source": hbm_src},
     }

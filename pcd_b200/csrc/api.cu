@@ -166,7 +166,7 @@ int pcdgpu_msm_dev(pcdgpu_ctx* ctx, int curve, const void* d_bases, const void* 
   CHECK_ARG(ctx, ops, "unknown curve id");
   CHECK_ARG(ctx, d_out_xyzz && (n == 0 || (d_bases && d_scalars)), "null pointer");
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
-  return ops->run(ctx, d_bases, d_scalars, scalars_mont, n, plan_plain(ctx, n), d_out_xyzz);
+  return ops->run(ctx, d_bases, d_scalars, scalars_mont, n, nullptr, 0, plan_plain(ctx, n), d_out_xyzz);
 }
 
 static int finish_to_host(pcdgpu_ctx* ctx, const MsmOps* ops, void* d_xyzz, void* out_affine) {
@@ -189,7 +189,7 @@ int pcdgpu_msm(pcdgpu_ctx* ctx, int curve, const void* bases, const void* scalar
   PCD_TRY(ctx->scratch(SLOT_MISC, 4096, &dres));
   PCD_CUDA(ctx, cudaMemcpyAsync(db, bases, n * ops->affine_bytes, cudaMemcpyHostToDevice, ctx->stream));
   PCD_CUDA(ctx, cudaMemcpyAsync(ds, scalars, n * 40, cudaMemcpyHostToDevice, ctx->stream));
-  PCD_TRY(ops->run(ctx, db, ds, 0, n, plan_plain(ctx, n), dres));
+  PCD_TRY(ops->run(ctx, db, ds, 0, n, nullptr, 0, plan_plain(ctx, n), dres));
   return finish_to_host(ctx, ops, dres, out_affine);
 }
 
@@ -250,20 +250,33 @@ void pcdgpu_bases_free(pcdgpu_bases* b) {
   delete b;
 }
 
+// MSM over points [offset, offset + n) of a resident vector followed by its last n_extra points
+// (the per-proof constant pairs appended at key upload) with plain scalars d_extra.
+static int bases_msm(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* d_scalars, int scalars_mont,
+                     size_t n, const void* d_extra, size_t n_extra, void* d_out_xyzz) {
+  const MsmOps* ops = msm_ops(b->curve);
+  size_t avail = b->n - n_extra;  // ordinary points
+  if (offset > avail) offset = avail;
+  if (n > avail - offset) n = avail - offset;  // truncate to the shorter input, as arkworks does
+  if (n_extra && offset + n != avail) {
+    ctx->set_error("internal: extra pairs need the ordinary points to end where the extras begin");
+    return PCDGPU_E_ARG;
+  }
+  if (b->table) {
+    MsmPlanC plan{b->c, b->nwin, 1, b->n, offset};
+    return ops->run(ctx, b->table, d_scalars, scalars_mont, n, d_extra, n_extra, plan, d_out_xyzz);
+  }
+  return ops->run(ctx, (const char*)b->points + offset * ops->affine_bytes, d_scalars, scalars_mont, n, d_extra,
+                  n_extra, plan_plain(ctx, n + n_extra), d_out_xyzz);
+}
+
 int pcdgpu_msm_bases_dev(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* d_scalars, int scalars_mont,
                          size_t n, void* d_out_xyzz) {
   if (!ctx) return PCDGPU_E_ARG;
   CHECK_ARG(ctx, b && d_out_xyzz && (n == 0 || d_scalars), "null pointer");
   CHECK_ARG(ctx, offset <= b->n, "offset beyond the base vector");
-  const MsmOps* ops = msm_ops(b->curve);
-  if (n > b->n - offset) n = b->n - offset;  // truncate to the shorter input, as arkworks does
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
-  if (b->table) {
-    MsmPlanC plan{b->c, b->nwin, 1, b->n, offset};
-    return ops->run(ctx, b->table, d_scalars, scalars_mont, n, plan, d_out_xyzz);
-  }
-  return ops->run(ctx, (const char*)b->points + offset * ops->affine_bytes, d_scalars, scalars_mont, n,
-                  plan_plain(ctx, n), d_out_xyzz);
+  return bases_msm(ctx, b, offset, d_scalars, scalars_mont, n, nullptr, 0, d_out_xyzz);
 }
 
 int pcdgpu_msm_bases(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* scalars, size_t n,
@@ -449,27 +462,33 @@ int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_i
   pk->num_inputs = num_inputs;
   pk->h_len = h_len;
   int rc = 0;
-  // element 0 of a/b queries belongs to the constant 1 and is added outside the MSMs (prover.rs)
-  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, (const char*)a_query + s1, num_vars - 1, precompute, &pk->a_query);
-  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, (const char*)b_g1_query + s1, num_vars - 1, precompute, &pk->b_g1_query);
-  rc = rc ? rc : pcdgpu_bases_upload(ctx, g2, (const char*)b_g2_query + s2, num_vars - 1, precompute, &pk->b_g2_query);
+  // Element 0 of the a/b queries belongs to the constant 1 and ark-groth16 adds it, the vk elements
+  // and r*delta / s*delta outside its MSMs (prover.rs).  Here those pairs ride inside the MSMs: every
+  // query vector is uploaded with its constant points appended, and the prover supplies their
+  // scalars (r or s, 1, 1) as "extra" scalars -- no serial scalar multiplication is left for them.
+  //   a_query    : a[1..], delta_g1, a[0], alpha_g1          scalars z[1..], r, 1, 1
+  //   b_g1_query : b[1..], delta_g1, b[0], beta_g1           scalars z[1..], s, 1, 1
+  //   b_g2_query : b2[1..], delta_g2, b2[0], beta_g2         scalars z[1..], s, 1, 1
+  //   l_query    : l[..], delta_g1                           scalars z[num_inputs..], -(r s)
+  auto upload_ext = [&](int curve, const void* q, size_t skip, size_t n, const void* const* extra, int n_extra,
+                        pcdgpu_bases** out) -> int {
+    size_t pb = msm_ops(curve)->affine_bytes;
+    std::vector<char> buf((n + n_extra) * pb);
+    if (n) memcpy(buf.data(), (const char*)q + skip * pb, n * pb);
+    for (int i = 0; i < n_extra; i++) memcpy(buf.data() + (n + i) * pb, extra[i], pb);
+    return pcdgpu_bases_upload(ctx, curve, buf.data(), n + n_extra, precompute, out);
+  };
+  const void* ea[3] = {delta_g1, a_query, alpha_g1};
+  const void* eb1[3] = {delta_g1, b_g1_query, beta_g1};
+  const void* eb2[3] = {delta_g2, b_g2_query, beta_g2};
+  const void* el[1] = {delta_g1};
+  rc = rc ? rc : upload_ext(g1, a_query, 1, num_vars - 1, ea, 3, &pk->a_query);
+  rc = rc ? rc : upload_ext(g1, b_g1_query, 1, num_vars - 1, eb1, 3, &pk->b_g1_query);
+  rc = rc ? rc : upload_ext(g2, b_g2_query, 1, num_vars - 1, eb2, 3, &pk->b_g2_query);
   rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, h_query, h_len, precompute, &pk->h_query);
-  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, l_query, num_vars - num_inputs, precompute, &pk->l_query);
-  if (!rc && cudaMalloc(&pk->consts_g1, 5 * s1 + 3 * s2) != cudaSuccess) rc = PCDGPU_E_NOMEM;
-  if (!rc) {
-    pk->consts_g2 = (char*)pk->consts_g1 + 5 * s1;
-    const void* c1[5] = {alpha_g1, beta_g1, delta_g1, a_query, b_g1_query};
-    const void* c2[3] = {beta_g2, delta_g2, b_g2_query};
-    char* stage = (char*)ctx->pinned;
-    for (int i = 0; i < 5; i++) memcpy(stage + i * s1, c1[i], s1);
-    for (int i = 0; i < 3; i++) memcpy(stage + 5 * s1 + i * s2, c2[i], s2);
-    cudaError_t e = cudaMemcpyAsync(pk->consts_g1, stage, 5 * s1 + 3 * s2, cudaMemcpyHostToDevice, ctx->stream);
-    if (e == cudaSuccess) e = cudaStreamSynchronize(ctx->stream);
-    if (e != cudaSuccess) {
-      ctx->set_error("uploading key constants: %s", cudaGetErrorString(e));
-      rc = PCDGPU_E_CUDA;
-    }
-  }
+  rc = rc ? rc : upload_ext(g1, l_query, 0, num_vars - num_inputs, el, 1, &pk->l_query);
+  (void)s1;
+  (void)s2;
   if (rc) {
     pcdgpu_pk_free(pk);
     return rc;
@@ -485,7 +504,6 @@ void pcdgpu_pk_free(pcdgpu_pk* pk) {
   pcdgpu_bases_free(pk->b_g2_query);
   pcdgpu_bases_free(pk->h_query);
   pcdgpu_bases_free(pk->l_query);
-  if (pk->consts_g1) cudaFree(pk->consts_g1);
   delete pk;
 }
 
@@ -500,34 +518,31 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
   const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
   size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
-  // misc layout: rs (80 B) | t1: 3 G1 xyzz | sums1: 4 G1 xyzz | t2: 1 G2 xyzz | sum2: 1 G2 xyzz | proof
+  // misc layout: rs (80 B) | extras: 7 scalars | sums1: h, l', g_a, g1_b (G1 xyzz) | sum2: g2_b | proof
   void* misc;
   PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
   char* mb = (char*)misc;
   u32* d_rs = (u32*)mb;
-  void* t1 = mb + 128;
-  void* sums1 = (char*)t1 + 3 * x1;
-  void* t2 = (char*)sums1 + 4 * x1;
-  void* sum2 = (char*)t2 + x2;
+  char* extras = mb + 128;  // r, 1, 1, s, 1, 1, -(r s)
+  void* sums1 = mb + 512;
+  void* sum2 = (char*)sums1 + 4 * x1;
   void* d_proof = (char*)sum2 + x2;
   size_t proof_bytes = 2 * o1->affine_bytes + o2->affine_bytes;
   memcpy(ctx->pinned, r, 40);
   memcpy((char*)ctx->pinned + 40, s, 40);
   PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
-  PCD_TRY(groth16_assemble(ctx, ctx->stream, pk->pairing, 1, pk->consts_g1, pk->consts_g2, d_rs, t1, t2, sums1, sum2,
-                           d_proof));
+  PCD_TRY(groth16_prepare(ctx, pk->pairing, d_rs, (u32*)extras));
   void* d_h;
   PCD_TRY(witness_map_dev(ctx, r1cs, d_z, &d_h));
   const char* z = (const char*)d_z;
   size_t nv = pk->num_vars, ni = pk->num_inputs;
   // h: n coefficients vs n - 1 query points: truncated to the shorter
-  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->h_query, 0, d_h, 1, r1cs->n, (char*)sums1 + 0 * x1));
-  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->l_query, 0, z + 40 * ni, 1, nv - ni, (char*)sums1 + 1 * x1));
-  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->a_query, 0, z + 40, 1, nv - 1, (char*)sums1 + 2 * x1));
-  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->b_g1_query, 0, z + 40, 1, nv - 1, (char*)sums1 + 3 * x1));
-  PCD_TRY(pcdgpu_msm_bases_dev(ctx, pk->b_g2_query, 0, z + 40, 1, nv - 1, sum2));
-  PCD_TRY(groth16_assemble(ctx, ctx->stream, pk->pairing, 2, pk->consts_g1, pk->consts_g2, d_rs, t1, t2, sums1, sum2,
-                           d_proof));
+  PCD_TRY(bases_msm(ctx, pk->h_query, 0, d_h, 1, r1cs->n, nullptr, 0, (char*)sums1 + 0 * x1));
+  PCD_TRY(bases_msm(ctx, pk->l_query, 0, z + 40 * ni, 1, nv - ni, extras + 6 * 40, 1, (char*)sums1 + 1 * x1));
+  PCD_TRY(bases_msm(ctx, pk->a_query, 0, z + 40, 1, nv - 1, extras, 3, (char*)sums1 + 2 * x1));
+  PCD_TRY(bases_msm(ctx, pk->b_g1_query, 0, z + 40, 1, nv - 1, extras + 3 * 40, 3, (char*)sums1 + 3 * x1));
+  PCD_TRY(bases_msm(ctx, pk->b_g2_query, 0, z + 40, 1, nv - 1, extras + 3 * 40, 3, sum2));
+  PCD_TRY(groth16_assemble(ctx, pk->pairing, d_rs, sums1, sum2, d_proof));
   PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;

@@ -139,7 +139,8 @@ enum {
   SLOT_WM_C = 10,
   SLOT_Z = 11,       // assignment on device
   SLOT_MISC = 12,
-  SLOT_CUB = 13
+  SLOT_CUB = 13,
+  SLOT_MSM_HP = 14   // heavy-bucket partial sums
 };
 
 template <class T>

@@ -106,61 +106,59 @@ int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void
 }
 
 // ---- proof assembly ------------------------------------------------------------------------------
-// consts (affine, device): [0] alpha_g1 [1] beta_g1 [2] delta_g1 [3] a_query[0] [4] b_g1_query[0] as G1,
-// then beta_g2, delta_g2, b_g2_query[0] as G2.  sums (xyzz, device): h, l, a, b_g1 (G1), b_g2 (G2).
-// Scalars r, s: plain integers (10 x u32).
-//
-// Phase 1 (independent of the MSMs, runs beside the witness map): four scalar multiplications
-//   t0 = r delta1, t1 = s delta1, t2 = (r s mod p) delta1, t3 = s delta2    -- one thread each.
-template <class G1, class G2>
-__global__ void groth16_phase1_kernel(const void* __restrict__ c1, const void* __restrict__ c2, const u32* __restrict__ rs,
-                                      void* __restrict__ t1out, void* __restrict__ t2out) {
-  typedef Fp<typename G1::ScalarParams> Fr;
-  if (threadIdx.x & 31) return;
-  int w = threadIdx.x >> 5;
+// ark-groth16 prover.rs computes
+//   g_a  = r delta1 + a_query[0] + MSM(a_query[1..], z[1..]) + alpha
+//   g1_b = s delta1 + b_g1_query[0] + MSM(b_g1_query[1..], z[1..]) + beta1      (g2_b likewise in G2)
+//   g_c  = s g_a + r g1_b - (r s) delta1 + MSM(l_query, aux) + MSM(h_query, h)
+// Every term with a key point as its base is folded into the MSMs as an extra (point, scalar) pair
+// (pcdgpu_pk_upload appends the points; groth16_prepare writes the scalars), so that g_a, g1_b, g2_b
+// and l' = l_acc - (r s) delta1 come straight out of the bucket method.  What is left is the one
+// double-scalar multiplication s g_a + r g1_b on fresh points, done jointly (Straus).
+template <class SP>
+__global__ void groth16_prepare_kernel(const u32* __restrict__ rs, u32* __restrict__ extras) {
+  typedef Fp<SP> Fr;
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   Fr r, s;
 #pragma unroll
   for (int i = 0; i < 10; i++) {
     r.l[i] = rs[i];
     s.l[i] = rs[10 + i];
   }
-  if (w < 3) {
-    XYZZ<G1> d = XYZZ<G1>::from_affine(ld_aff<G1>(c1, 2));
-    Fr k = w == 0 ? r : s;
-    if (w == 2) k = (r.to_mont() * s.to_mont()).from_mont();
-    XYZZ<G1> o = XYZZ<G1>::mul(d, k.l, 10);
-    st_xyzz<G1>(t1out, w, o);
-  } else {
-    XYZZ<G2> d = XYZZ<G2>::from_affine(ld_aff<G2>(c2, 1));
-    XYZZ<G2> o = XYZZ<G2>::mul(d, s.l, 10);
-    st_xyzz<G2>(t2out, 0, o);
+  Fr nrs = (r.to_mont() * s.to_mont()).neg().from_mont();
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    u32 one = i == 0 ? 1u : 0u;
+    extras[0 * 10 + i] = r.l[i];
+    extras[1 * 10 + i] = one;
+    extras[2 * 10 + i] = one;
+    extras[3 * 10 + i] = s.l[i];
+    extras[4 * 10 + i] = one;
+    extras[5 * 10 + i] = one;
+    extras[6 * 10 + i] = nrs.l[i];
   }
 }
 
-// Phase 2: warp 0: g_a, g1_b, g_c (Straus double-scalar multiplication s g_a + r g1_b);
-//          warp 1: g2_b.  Output affine A || B || C.
+int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras) {
+  ctx->launches += 1;
+  if (pairing == PCDGPU_MNT4_298) groth16_prepare_kernel<ParamsR4><<<1, 32, 0, ctx->stream>>>(d_rs, d_extras);
+  else groth16_prepare_kernel<ParamsQ4><<<1, 32, 0, ctx->stream>>>(d_rs, d_extras);
+  PCD_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
+// warp 0: A = g_a, C = s g_a + r g1_b + l' + h;  warp 1: B = g2_b.  Output affine A || B || C.
 template <class G1, class G2>
-__global__ void groth16_phase2_kernel(const void* __restrict__ c1, const void* __restrict__ c2, const u32* __restrict__ rs,
-                                      const void* __restrict__ t1, const void* __restrict__ t2,
-                                      const void* __restrict__ sums1, const void* __restrict__ sum2,
-                                      void* __restrict__ out) {
+__global__ void groth16_assemble_kernel(const u32* __restrict__ rs, const void* __restrict__ sums1,
+                                        const void* __restrict__ sum2, void* __restrict__ out) {
   if (threadIdx.x & 31) return;
   int w = threadIdx.x >> 5;
   char* o = reinterpret_cast<char*>(out);
   typedef typename G1::F F1;
   typedef typename G2::F F2;
   if (w == 0) {
-    // g_a = r delta + a_query[0] + a_acc + alpha
-    XYZZ<G1> ga = ld_xyzz<G1>(t1, 0);
-    ga.madd(ld_aff<G1>(c1, 3));
-    ga.add(ld_xyzz<G1>(sums1, 2));
-    ga.madd(ld_aff<G1>(c1, 0));
-    // g1_b = s delta + b_g1_query[0] + b_acc + beta
-    XYZZ<G1> gb = ld_xyzz<G1>(t1, 1);
-    gb.madd(ld_aff<G1>(c1, 4));
-    gb.add(ld_xyzz<G1>(sums1, 3));
-    gb.madd(ld_aff<G1>(c1, 1));
-    // s g_a + r g1_b, jointly (Straus): one doubling chain, table {ga, gb, ga + gb}
+    XYZZ<G1> ga = ld_xyzz<G1>(sums1, 2);
+    XYZZ<G1> gb = ld_xyzz<G1>(sums1, 3);
+    // s g_a + r g1_b jointly (Straus): one doubling chain, table {ga, gb, ga + gb}
     XYZZ<G1> gab = ga;
     gab.add(gb);
     XYZZ<G1> acc = XYZZ<G1>::inf();
@@ -176,40 +174,27 @@ __global__ void groth16_phase2_kernel(const void* __restrict__ c1, const void* _
         }
       }
     }
-    // g_c = s g_a + r g1_b - (r s) delta + l_acc + h_acc
-    acc.add(ld_xyzz<G1>(t1, 2).neg());
     acc.add(ld_xyzz<G1>(sums1, 1));
     acc.add(ld_xyzz<G1>(sums1, 0));
     AffinePoint<F1> A = ga.to_affine(), Cc = acc.to_affine();
     st_aff<G1>(o, 0, A);
     st_aff<G1>(o + sizeof(AffinePoint<F1>) + sizeof(AffinePoint<F2>), 0, Cc);
   } else if (w == 1) {
-    // g2_b = s delta2 + b_g2_query[0] + b2_acc + beta2
-    XYZZ<G2> gb = ld_xyzz<G2>(t2, 0);
-    gb.madd(ld_aff<G2>(c2, 2));
-    gb.add(ld_xyzz<G2>(sum2, 0));
-    gb.madd(ld_aff<G2>(c2, 0));
+    XYZZ<G2> gb = ld_xyzz<G2>(sum2, 0);
     st_aff<G2>(o + sizeof(AffinePoint<F1>), 0, gb.to_affine());
   }
 }
 
-template <class G1, class G2>
-static int groth16_assemble_t(pcdgpu_ctx* ctx, cudaStream_t st, int phase, const void* c1, const void* c2,
-                              const u32* d_rs, void* t1, void* t2, const void* sums1, const void* sum2, void* d_out) {
-  int ps = st == ctx->stream ? ctx->prof_begin(PROF_ASSEMBLE, 1.0) : -1;
+int groth16_assemble(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, const void* sums1, const void* sum2, void* d_out) {
+  int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
   ctx->launches += 1;
-  if (phase == 1) groth16_phase1_kernel<G1, G2><<<1, 128, 0, st>>>(c1, c2, d_rs, t1, t2);
-  else groth16_phase2_kernel<G1, G2><<<1, 64, 0, st>>>(c1, c2, d_rs, t1, t2, sums1, sum2, d_out);
+  if (pairing == PCDGPU_MNT4_298)
+    groth16_assemble_kernel<CurveMnt4G1, CurveMnt4G2><<<1, 64, 0, ctx->stream>>>(d_rs, sums1, sum2, d_out);
+  else
+    groth16_assemble_kernel<CurveMnt6G1, CurveMnt6G2><<<1, 64, 0, ctx->stream>>>(d_rs, sums1, sum2, d_out);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   return 0;
-}
-
-int groth16_assemble(pcdgpu_ctx* ctx, cudaStream_t st, int pairing, int phase, const void* c1, const void* c2,
-                     const u32* d_rs, void* t1, void* t2, const void* sums1, const void* sum2, void* d_out) {
-  if (pairing == PCDGPU_MNT4_298)
-    return groth16_assemble_t<CurveMnt4G1, CurveMnt4G2>(ctx, st, phase, c1, c2, d_rs, t1, t2, sums1, sum2, d_out);
-  return groth16_assemble_t<CurveMnt6G1, CurveMnt6G2>(ctx, st, phase, c1, c2, d_rs, t1, t2, sums1, sum2, d_out);
 }
 
 // ---- ark-serialize compressed proof bytes -------------------------------------------------------

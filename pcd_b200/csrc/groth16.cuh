@@ -32,15 +32,16 @@ struct pcdgpu_pk {
   pcdgpu_ctx* ctx;
   int pairing;
   size_t num_vars, num_inputs, h_len;
+  // query vectors with their constant points appended (see pcdgpu_pk_upload)
   pcdgpu_bases *a_query, *b_g1_query, *b_g2_query, *h_query, *l_query;
-  void* consts_g1;  // alpha_g1, beta_g1, delta_g1, a_query[0], b_g1_query[0]
-  void* consts_g2;  // beta_g2, delta_g2, b_g2_query[0]
 };
 
 // a, b, c <- matrices x z; h = coset_ifft((coset_fft(ifft a) * coset_fft(ifft b) - coset_fft(ifft c)) / Z).
 // *d_h points into the context's scratch (n elements, Montgomery form).
 int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h);
-int groth16_assemble(pcdgpu_ctx* ctx, cudaStream_t st, int pairing, int phase, const void* c1, const void* c2,
-                     const u32* d_rs, void* t1, void* t2, const void* sums1, const void* sum2, void* d_out);
+// extras <- {r, 1, 1, s, 1, 1, -(r s) mod p} as plain integers (the scalars of the constant pairs)
+int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras);
+// sums1 = {h_acc, l_acc - (r s) delta, g_a, g1_b} (G1 xyzz), sum2 = g2_b: writes A || B || C affine
+int groth16_assemble(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, const void* sums1, const void* sum2, void* d_out);
 int groth16_serialize(pcdgpu_ctx* ctx, int pairing, const void* d_proof, unsigned char* d_out);
 int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double* ms_out);

@@ -29,17 +29,26 @@ static constexpr int MSM_SCALAR_BITS = 298;
 static constexpr int MSM_HEAVY = 1024;      // entries per bucket handled by one thread
 static constexpr int MSM_HEAVY_THREADS = 128;
 static constexpr int MSM_MAX_HEAVY = 4096;  // size of the heavy-bucket list
+static constexpr int MSM_HEAVY_CHUNK = 1024;  // entries of a heavy bucket summed by one CTA at a time
+static constexpr int MSM_SUM_PER_CTA = 2048;  // points folded by one CTA of msm_sum_kernel
+static constexpr int MSM_REDUCE_LOGL = 3;     // bucket reduction: 2^3 points per thread and level
 
 // ---- 1. digits ------------------------------------------------------------------------------
 // dig[w * n + i] = signed digit of scalar i in window w; counts[bucket]++ for non-zero digits.
 // shared != 0: all windows share one bucket set (precomputed bases).
+// Scalars i < n_main come from `scalars` (Montgomery form if mont), the n - n_main trailing ones from
+// `extra` (always plain integers): the per-proof pairs (delta, r), (a_query[0], 1), ... that the
+// Groth16 prover folds into its MSMs.
 template <class SP>
-__global__ void msm_digits_kernel(const u32* __restrict__ scalars, int mont, size_t n, int c, int nwin, int shared,
+__global__ void msm_digits_kernel(const u32* __restrict__ scalars, int mont, size_t n_main,
+                                  const u32* __restrict__ extra, size_t n, int c, int nwin, int shared,
                                   int* __restrict__ dig, u32* __restrict__ counts) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   Fp<SP> k;
-  const uint2* p = reinterpret_cast<const uint2*>(scalars + i * 10);
+  const bool is_extra = i >= n_main;
+  const uint2* p = reinterpret_cast<const uint2*>(is_extra ? extra + (i - n_main) * 10 : scalars + i * 10);
+  if (is_extra) mont = 0;
 #pragma unroll
   for (int j = 0; j < 5; j++) {
     uint2 v = __ldg(p + j);
@@ -123,79 +132,10 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
   st_vec(buckets, g, acc);
 }
 
+// CTA-wide tree sum of one xyzz point per thread (shared memory, MSM_HEAVY_THREADS entries)
 template <class C>
-__global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_accumulate_heavy_kernel(
-    const void* __restrict__ bases, const u32* __restrict__ offsets, const u32* __restrict__ entries,
-    void* __restrict__ buckets, const u32* __restrict__ heavy) {
-  typedef typename C::F F;
-  extern __shared__ uint4 sm4[];
-  XYZZ<C>* sm = reinterpret_cast<XYZZ<C>*>(sm4);
-  u32 nheavy = heavy[0] < (u32)MSM_MAX_HEAVY ? heavy[0] : (u32)MSM_MAX_HEAVY;
-  for (u32 h = blockIdx.x; h < nheavy; h += gridDim.x) {
-    u32 g = heavy[1 + h];
-    u32 lo = offsets[g], hi = offsets[g + 1];
-    XYZZ<C> acc = XYZZ<C>::inf();
-    for (u32 e = lo + threadIdx.x; e < hi; e += MSM_HEAVY_THREADS) {
-      u32 ent = entries[e];
-      AffinePoint<F> p = ld_vec<AffinePoint<F>>(bases, ent & 0x7fffffffu);
-      if (ent >> 31) p.y = p.y.neg();
-      acc.madd(p);
-    }
-    sm[threadIdx.x] = acc;
-    __syncthreads();
-    for (int s = MSM_HEAVY_THREADS / 2; s > 0; s >>= 1) {
-      if ((int)threadIdx.x < s) {
-        XYZZ<C> a = sm[threadIdx.x];
-        a.add(sm[threadIdx.x + s]);
-        sm[threadIdx.x] = a;
-      }
-      __syncthreads();
-    }
-    if (threadIdx.x == 0) st_vec(buckets, g, sm[0]);
-    __syncthreads();
-  }
-}
-
-// ---- 5. bucket reduction ----------------------------------------------------------------------
-// thread t of window w: seg[w * T + t] = sum_{b in [tL, tL+L)} (b + 1) * bucket[w * B + b]
-template <class C>
-__global__ void __launch_bounds__(128) msm_reduce_kernel(const void* __restrict__ buckets, int c, int logL, int nwin,
-                                                         void* __restrict__ seg) {
-  const u32 B = 1u << (c - 1);
-  const u32 L = 1u << logL;
-  const u32 T = B >> logL;
-  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= (size_t)T * nwin) return;
-  u32 w = (u32)(gid / T), t = (u32)(gid - (size_t)w * T);
-  size_t base = (size_t)w * B + (size_t)t * L;
-  XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
-  for (int b = (int)L - 1; b >= 0; b--) {
-    XYZZ<C> p = ld_vec_rw<XYZZ<C>>(buckets, base + b);
-    run.add(p);
-    acc.add(run);
-  }
-  // acc = sum (b - tL + 1) B_b ; add [tL] * run
-  u32 k = t * L;
-  if (k != 0 && !run.is_inf()) {
-    XYZZ<C> m = XYZZ<C>::mul(run, &k, 1);
-    acc.add(m);
-  }
-  st_vec(seg, gid, acc);
-}
-
-// ---- 6. per-window tree sum and Horner ----------------------------------------------------------
-template <class C>
-__global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_window_sum_kernel(const void* __restrict__ seg, u32 T,
-                                                                           void* __restrict__ wsum) {
-  extern __shared__ uint4 sm4[];
-  XYZZ<C>* sm = reinterpret_cast<XYZZ<C>*>(sm4);
-  u32 w = blockIdx.x;
-  XYZZ<C> acc = XYZZ<C>::inf();
-  for (u32 t = threadIdx.x; t < T; t += MSM_HEAVY_THREADS) {
-    XYZZ<C> p = ld_vec_rw<XYZZ<C>>(seg, (size_t)w * T + t);
-    acc.add(p);
-  }
-  sm[threadIdx.x] = acc;
+__device__ __forceinline__ void cta_tree_sum(XYZZ<C>* sm, const XYZZ<C>& mine) {
+  sm[threadIdx.x] = mine;
   __syncthreads();
   for (int s = MSM_HEAVY_THREADS / 2; s > 0; s >>= 1) {
     if ((int)threadIdx.x < s) {
@@ -205,18 +145,130 @@ __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_window_sum_kernel(const
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) st_vec(wsum, w, sm[0]);
 }
 
-// out = sum_w 2^(c w) wsum[w]  (+ *addend if given)
+// Heavy buckets (more than MSM_HEAVY entries: the "scalar == 1" bucket of a real witness holds a
+// fifth of all points) are cut into chunks of MSM_HEAVY_CHUNK entries; every CTA of the grid takes
+// chunks round-robin, sums one with a tree and appends (bucket, partial sum) to a list ...
 template <class C>
-__global__ void msm_horner_kernel(const void* __restrict__ wsum, int c, int nwin, void* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_accumulate_heavy_kernel(
+    const void* __restrict__ bases, const u32* __restrict__ offsets, const u32* __restrict__ entries,
+    const u32* __restrict__ heavy, u32* __restrict__ hp_count, u32* __restrict__ hp_id, void* __restrict__ hp_sum) {
+  typedef typename C::F F;
+  extern __shared__ uint4 sm4[];
+  XYZZ<C>* sm = reinterpret_cast<XYZZ<C>*>(sm4);
+  u32 nheavy = heavy[0] < (u32)MSM_MAX_HEAVY ? heavy[0] : (u32)MSM_MAX_HEAVY;
+  u32 job = 0;  // running (bucket, chunk) index, identical in every CTA
+  for (u32 h = 0; h < nheavy; h++) {
+    u32 g = heavy[1 + h];
+    u32 lo = offsets[g], hi = offsets[g + 1];
+    u32 nchunks = (hi - lo + MSM_HEAVY_CHUNK - 1) / MSM_HEAVY_CHUNK;
+    for (u32 ch = 0; ch < nchunks; ch++, job++) {
+      if (job % gridDim.x != blockIdx.x) continue;
+      u32 e0 = lo + ch * MSM_HEAVY_CHUNK;
+      u32 e1 = e0 + MSM_HEAVY_CHUNK < hi ? e0 + MSM_HEAVY_CHUNK : hi;
+      XYZZ<C> acc = XYZZ<C>::inf();
+      for (u32 e = e0 + threadIdx.x; e < e1; e += MSM_HEAVY_THREADS) {
+        u32 ent = entries[e];
+        AffinePoint<F> p = ld_vec<AffinePoint<F>>(bases, ent & 0x7fffffffu);
+        if (ent >> 31) p.y = p.y.neg();
+        acc.madd(p);
+      }
+      cta_tree_sum<C>(sm, acc);
+      if (threadIdx.x == 0) {
+        u32 slot = atomicAdd(hp_count, 1u);
+        hp_id[slot] = h;
+        st_vec(hp_sum, slot, sm[0]);
+      }
+      __syncthreads();
+    }
+  }
+}
+// ... and one CTA per heavy bucket adds up that bucket's partial sums.
+template <class C>
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_heavy_finish_kernel(
+    const u32* __restrict__ heavy, const u32* __restrict__ hp_count, const u32* __restrict__ hp_id,
+    const void* __restrict__ hp_sum, void* __restrict__ buckets) {
+  extern __shared__ uint4 sm4[];
+  XYZZ<C>* sm = reinterpret_cast<XYZZ<C>*>(sm4);
+  u32 nheavy = heavy[0] < (u32)MSM_MAX_HEAVY ? heavy[0] : (u32)MSM_MAX_HEAVY;
+  u32 np = *hp_count;
+  for (u32 h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    XYZZ<C> acc = XYZZ<C>::inf();
+    for (u32 s = threadIdx.x; s < np; s += MSM_HEAVY_THREADS)
+      if (hp_id[s] == h) acc.add(ld_vec_rw<XYZZ<C>>(hp_sum, s));
+    cta_tree_sum<C>(sm, acc);
+    if (threadIdx.x == 0) st_vec(buckets, heavy[1 + h], sm[0]);
+    __syncthreads();
+  }
+}
+
+// ---- 5. bucket reduction ----------------------------------------------------------------------
+// S(P) = sum_b (b + 1) P_b over `count` points per window.  With segments of L = 2^logL points,
+//   S(P) = sum_t acc_t + L * S(Q),   acc_t = sum_j (j + 1) P_{tL+j},   Q_u = R_{u+1},  R_t = sum_j P_{tL+j}
+// so one level turns `count` points into T = ceil(count / L) segment sums (the next level's input,
+// first one dropped) plus T "acc" points whose plain sum is this level's contribution.  Every
+// thread runs the running-sum trick on its L points: 2 L additions, no scalar multiplication.
+// Arrays are [window][index]; in_pitch / out_pitch are the per-window strides in points.
+template <class C>
+__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const void* __restrict__ in, size_t in_pitch,
+                                                               size_t in_skip, size_t count, int logL, int nwin,
+                                                               void* __restrict__ acc_out, void* __restrict__ run_out,
+                                                               size_t out_pitch) {
+  const size_t L = (size_t)1 << logL;
+  const size_t T = (count + L - 1) >> logL;
+  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (gid >= T * nwin) return;
+  size_t w = gid / T, t = gid - w * T;
+  size_t base = w * in_pitch + in_skip + t * L;
+  size_t lim = count - t * L < L ? count - t * L : L;
+  XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
+  for (size_t j = lim; j-- > 0;) {
+    XYZZ<C> p = ld_vec_rw<XYZZ<C>>(in, base + j);
+    run.add(p);
+    acc.add(run);
+  }
+  st_vec(acc_out, w * out_pitch + t, acc);
+  st_vec(run_out, w * out_pitch + t, run);
+}
+
+// out[w * out_pitch + blockIdx.x'] = sum of up to MSM_SUM_PER_CTA consecutive points of window w
+template <class C>
+__global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_sum_kernel(const void* __restrict__ in, size_t in_pitch,
+                                                                    size_t count, void* __restrict__ out,
+                                                                    size_t out_pitch, size_t ctas_per_win) {
+  extern __shared__ uint4 sm4[];
+  XYZZ<C>* sm = reinterpret_cast<XYZZ<C>*>(sm4);
+  size_t w = blockIdx.x / ctas_per_win, k = blockIdx.x - w * ctas_per_win;
+  size_t lo = k * MSM_SUM_PER_CTA;
+  size_t hi = lo + MSM_SUM_PER_CTA < count ? lo + MSM_SUM_PER_CTA : count;
+  XYZZ<C> acc = XYZZ<C>::inf();
+  for (size_t i = lo + threadIdx.x; i < hi; i += MSM_HEAVY_THREADS) acc.add(ld_vec_rw<XYZZ<C>>(in, w * in_pitch + i));
+  cta_tree_sum<C>(sm, acc);
+  if (threadIdx.x == 0) st_vec(out, w * out_pitch + k, sm[0]);
+}
+
+// ---- 6. combine levels and windows ----------------------------------------------------------------
+// lvl[(l * nwin + w)] = A_l of window w.  window sum = A_0 + L (A_1 + L (A_2 + ...)); result =
+// sum_w 2^(c w) window_sum[w] by Horner.  One thread per window for the first part.
+template <class C>
+__global__ void msm_combine_kernel(const void* __restrict__ lvl, int nlevels, int logL, int c, int nwin,
+                                   void* __restrict__ wsum, void* __restrict__ out) {
+  int w = threadIdx.x;
+  if (w < nwin) {
+    XYZZ<C> total = ld_vec_rw<XYZZ<C>>(lvl, (size_t)(nlevels - 1) * nwin + w);
+    for (int l = nlevels - 2; l >= 0; l--) {
+      for (int i = 0; i < logL; i++) total = total.dbl();
+      total.add(ld_vec_rw<XYZZ<C>>(lvl, (size_t)l * nwin + w));
+    }
+    st_vec(wsum, w, total);
+  }
+  __syncthreads();
+  if (threadIdx.x != 0) return;
   XYZZ<C> total = ld_vec_rw<XYZZ<C>>(wsum, nwin - 1);
-  for (int w = nwin - 2; w >= 0; w--) {
+  for (int ww = nwin - 2; ww >= 0; ww--) {
     for (int i = 0; i < c; i++) total = total.dbl();
-    XYZZ<C> p = ld_vec_rw<XYZZ<C>>(wsum, w);
-    total.add(p);
+    total.add(ld_vec_rw<XYZZ<C>>(wsum, ww));
   }
   st_vec(out, 0, total);
 }
@@ -308,8 +360,9 @@ struct MsmPlan {
 // bases: n affine points (or the precomputed table nwin x n when plan.shared); result: one xyzz
 // point at d_out.
 template <class C>
-static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, int scalars_mont, size_t n,
-                   MsmPlan plan, void* d_out) {
+static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, int scalars_mont, size_t n_main,
+                   const void* d_extra, size_t n_extra, MsmPlan plan, void* d_out) {
+  const size_t n = n_main + n_extra;
   typedef typename C::ScalarParams SP;
   cudaStream_t st = ctx->stream;
   if (n == 0) {
@@ -339,8 +392,10 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   PCD_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
   const int acc_slot = sizeof(typename C::F) > 40 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1;
   int ps = ctx->prof_begin(PROF_MSM_SORT, (double)n * nwin);
-  ctx->launches += 7 + 3;  // seven kernels of this file + cub's scan (init, scan) + one d2d copy
-  msm_digits_kernel<SP><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const u32*)d_scalars, scalars_mont, n, c, nwin,
+  ctx->launches += 6 + 2;  // digits, scatter, accumulate, heavy x2, combine + cub's scan (init, scan); the
+                           // reduction levels count themselves
+  msm_digits_kernel<SP><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const u32*)d_scalars, scalars_mont, n_main,
+                                                                    (const u32*)d_extra, n, c, nwin,
                                                                     shared, (int*)dig, counts);
   PCD_CUDA(ctx, cudaGetLastError());
   size_t cub_bytes = 0;
@@ -362,27 +417,83 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                                                                                nbuckets, bkt, heavy);
   PCD_CUDA(ctx, cudaGetLastError());
   size_t heavy_smem = MSM_HEAVY_THREADS * sizeof(XYZZ<C>);
+  // heavy-bucket partial list: at most one partial per MSM_HEAVY_CHUNK entries plus one per bucket
+  size_t hp_cap = total / MSM_HEAVY_CHUNK + MSM_MAX_HEAVY + 8;
+  void* hp;
+  PCD_TRY(ctx->scratch(SLOT_MSM_HP, hp_cap * (sizeof(XYZZ<C>) + 4) + 64, &hp));
+  u32* hp_count = (u32*)hp;
+  u32* hp_id = hp_count + 4;
+  void* hp_sum = (char*)hp + 64 + ((hp_cap * 4 + 63) & ~(size_t)63);
+  PCD_CUDA(ctx, cudaMemsetAsync(hp_count, 0, 4, st));
   PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)heavy_smem));
-  msm_accumulate_heavy_kernel<C><<<ctx->sm_count, MSM_HEAVY_THREADS, heavy_smem, st>>>(d_bases, offsets,
-                                                                                      (const u32*)ent, bkt, heavy);
+  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_heavy_finish_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)heavy_smem));
+  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_sum_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem));
+  msm_accumulate_heavy_kernel<C><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
+      d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
+  PCD_CUDA(ctx, cudaGetLastError());
+  msm_heavy_finish_kernel<C><<<64, MSM_HEAVY_THREADS, heavy_smem, st>>>(heavy, hp_count, hp_id, hp_sum, bkt);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   ps = ctx->prof_begin(PROF_MSM_REDUCE, (double)nbuckets);
-  // reduction: L buckets per thread
-  int logL = c - 1 >= 12 ? 4 : (c - 1 >= 6 ? 2 : 0);
-  size_t T = B >> logL;
-  PCD_TRY(ctx->scratch(SLOT_MSM_SEG, (T * rwin + rwin + 2) * sizeof(XYZZ<C>), &seg));
-  void* wsum = (char*)seg + T * rwin * sizeof(XYZZ<C>);
-  msm_reduce_kernel<C><<<(unsigned)((T * rwin + 127) / 128), 128, 0, st>>>(bkt, c, logL, rwin, seg);
-  PCD_CUDA(ctx, cudaGetLastError());
-  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_window_sum_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)heavy_smem));
-  msm_window_sum_kernel<C><<<rwin, MSM_HEAVY_THREADS, heavy_smem, st>>>(seg, (u32)T, wsum);
-  PCD_CUDA(ctx, cudaGetLastError());
+  // multi-level reduction (see msm_reduce_level_kernel).  seg layout, in points:
+  //   lvl   [MAXLVL][rwin]           level sums A_l
+  //   run   [2][rwin][T0]            ping-pong segment sums (next level's input)
+  //   acc   [rwin][T0]               this level's acc points
+  //   part  [rwin][T0 / SUM + 1]     partial sums while folding acc
+  const int logL = MSM_REDUCE_LOGL;
+  const size_t L = (size_t)1 << logL;
+  const size_t T0 = (B + L - 1) >> logL;
+  const int MAXLVL = 32;
+  const size_t part_pitch = T0 / MSM_SUM_PER_CTA + 2;
+  size_t seg_points = (size_t)MAXLVL * rwin + 3 * rwin * T0 + 2 * rwin * part_pitch + rwin + 8;
+  PCD_TRY(ctx->scratch(SLOT_MSM_SEG, seg_points * sizeof(XYZZ<C>), &seg));
+  char* sp = (char*)seg;
+  const size_t PB = sizeof(XYZZ<C>);
+  void* lvl = sp;
+  void* run_buf[2] = {sp + (size_t)MAXLVL * rwin * PB, sp + ((size_t)MAXLVL * rwin + (size_t)rwin * T0) * PB};
+  void* acc_buf = sp + ((size_t)MAXLVL * rwin + 2 * (size_t)rwin * T0) * PB;
+  void* part_buf[2] = {(char*)acc_buf + (size_t)rwin * T0 * PB, (char*)acc_buf + ((size_t)rwin * T0 + rwin * part_pitch) * PB};
+  void* wsum = (char*)part_buf[1] + (size_t)rwin * part_pitch * PB;
+  const void* in = bkt;
+  size_t in_pitch = B, in_skip = 0, count = B;
+  int nlevels = 0;
+  while (count > 0 && nlevels < MAXLVL) {
+    size_t T = (count + L - 1) >> logL;
+    void* run_out = run_buf[nlevels & 1];
+    msm_reduce_level_kernel<C><<<(unsigned)((T * rwin + 127) / 128), 128, 0, st>>>(in, in_pitch, in_skip, count, logL,
+                                                                                rwin, acc_buf, run_out, T0);
+    PCD_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    // fold the T acc points of every window down to one: lvl[nlevels][w]
+    const void* fin = acc_buf;
+    size_t fpitch = T0, fcount = T;
+    int pp = 0;
+    for (;;) {
+      size_t ctas = (fcount + MSM_SUM_PER_CTA - 1) / MSM_SUM_PER_CTA;
+      bool last = ctas == 1;
+      void* fout = last ? (char*)lvl + (size_t)nlevels * rwin * PB : part_buf[pp];
+      size_t opitch = last ? 1 : part_pitch;
+      msm_sum_kernel<C><<<(unsigned)(ctas * rwin), MSM_HEAVY_THREADS, heavy_smem, st>>>(fin, fpitch, fcount, fout, opitch,
+                                                                                     ctas);
+      PCD_CUDA(ctx, cudaGetLastError());
+      ctx->launches += 1;
+      if (last) break;
+      fin = fout;
+      fpitch = part_pitch;
+      fcount = ctas;
+      pp ^= 1;
+    }
+    nlevels++;
+    in = run_out;
+    in_pitch = T0;
+    in_skip = 1;
+    count = T - 1;
+  }
   ctx->prof_end(ps);
   ps = ctx->prof_begin(PROF_MSM_TAIL, (double)rwin);
-  msm_horner_kernel<C><<<1, 32, 0, st>>>(wsum, c, rwin, d_out);
+  msm_combine_kernel<C><<<1, 128, 0, st>>>(lvl, nlevels, logL, c, rwin, wsum, d_out);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   return 0;

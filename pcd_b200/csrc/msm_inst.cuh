@@ -5,9 +5,10 @@
 namespace {
 typedef PCD_CURVE CV;
 
-int run_(pcdgpu_ctx* ctx, const void* b, const void* s, int mont, size_t n, MsmPlanC p, void* out) {
+int run_(pcdgpu_ctx* ctx, const void* b, const void* s, int mont, size_t n, const void* extra, size_t n_extra,
+         MsmPlanC p, void* out) {
   MsmPlan plan{p.c, p.nwin, p.shared, p.stride, p.offset};
-  return msm_run<CV>(ctx, b, s, mont, n, plan, out);
+  return msm_run<CV>(ctx, b, s, mont, n, extra, n_extra, plan, out);
 }
 int to_affine_(pcdgpu_ctx* ctx, const void* in, size_t n, void* out) {
   if (n == 0) return 0;

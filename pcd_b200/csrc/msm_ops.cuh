@@ -11,8 +11,10 @@ struct MsmPlanC {
 struct MsmOps {
   size_t affine_bytes, xyzz_bytes;
   int scalar_field;
-  // sum_i scalars[i] * bases[i] -> one xyzz point at d_out
-  int (*run)(pcdgpu_ctx*, const void* d_bases, const void* d_scalars, int mont, size_t n, MsmPlanC plan, void* d_out);
+  // sum_i scalars[i] * bases[i] -> one xyzz point at d_out.  The first n scalars come from d_scalars
+  // (Montgomery form if mont), n_extra more from d_extra (plain integers); bases holds n + n_extra points.
+  int (*run)(pcdgpu_ctx*, const void* d_bases, const void* d_scalars, int mont, size_t n, const void* d_extra,
+             size_t n_extra, MsmPlanC plan, void* d_out);
   int (*to_affine)(pcdgpu_ctx*, const void* d_in, size_t n, void* d_out);
   int (*xyzz_sum)(pcdgpu_ctx*, const void* d_in, size_t n, void* d_out_affine);
   // d_table: 75 * 15 affine points (built from d_base by fixed_table); out[i] = scalars[i] * base
