@@ -261,9 +261,7 @@ def run_gpu(args, rank, local_rank, world):
     clocks = sampler.stop()
 
     # ---- kernel figures: G1 MSM at 2^20 points and the largest NTT --------------------------------------
-    extra = {}
-    if rank == 0:
-        extra = kernel_figures(args, ctx, dev, stream, imad_peak)
+    extra = kernel_figures(args, ctx, dev, stream, imad_peak, rank, world)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample_log = min(log_n, args.cpu_sample_log_n)
@@ -325,7 +323,7 @@ def run_gpu(args, rank, local_rank, world):
     print(json.dumps(line), flush=True)
 
 
-def kernel_figures(args, ctx, dev, stream, imad_peak):
+def kernel_figures(args, ctx, dev, stream, imad_peak, rank=0, world=1):
     """G1 MSM Mpts/s at 2^20 (uniform scalars; resident bases with and without the window tables) and
     the largest radix-2 NTT (coset FFT over r4), each timed with CUDA events on the launching stream."""
     import torch
@@ -354,6 +352,37 @@ def kernel_figures(args, ctx, dev, stream, imad_peak):
     ms_plain = timed(lambda: ctx.msm_dev(0, pts.data_ptr(), sc.data_ptr(), n, res.data_ptr()), 5)
     bases = pcd_b200.Bases(ctx, 0, pts.cpu().numpy().view(np.uint64), precompute=True)
     ms_pre = timed(lambda: bases.msm_dev(sc.data_ptr(), n, res.data_ptr()), 5)
+    if world > 1:
+        # the same MSM sharded by point range: every rank keeps n / world points resident, the xyzz
+        # partials are all-gathered (NCCL) and summed on every rank; time = max over ranks
+        import torch.distributed as dist
+        from pcd_b200.sharding import gather_partials, shard_range
+        lo, hi = shard_range(n, world, rank)
+        pts_host = pts.cpu().numpy().view(np.uint64)
+        shard = pcd_b200.Bases(ctx, 0, pts_host[lo:hi], precompute=True)
+        sc_shard = sc[lo:hi].contiguous()
+
+        def sharded():
+            shard.msm_dev(sc_shard.data_ptr(), hi - lo, res.data_ptr())
+            parts = gather_partials(ctx.xyzz_download(0, res.data_ptr()), device=dev)
+            return ctx.xyzz_sum(0, parts)
+
+        full = bases.msm(sc.cpu().numpy().view(np.uint64))
+        ok = bool(np.array_equal(sharded(), full))
+        for _ in range(2):
+            sharded()
+        dist.barrier()
+        torch.cuda.synchronize()
+        t0 = time.perf_counter()
+        for _ in range(5):
+            sharded()
+        torch.cuda.synchronize()
+        dt = torch.tensor([(time.perf_counter() - t0) / 5], dtype=torch.float64, device=dev)
+        dist.all_reduce(dt, op=dist.ReduceOp.MAX)
+        out["g1_msm_sharded"] = {"points": n, "gpus": world, "ms": float(dt.item()) * 1e3,
+                                 "mpts_per_s": n / float(dt.item()) / 1e6, "matches_single_gpu": ok,
+                                 "collective": "all_gather of one 160-byte xyzz partial per rank"}
+        shard.close()
     bases.close()
     del pts
     out["g1_msm"] = {"points": n, "scalars": "uniform 298-bit", "mpts_per_s": n / ms_pre / 1e3, "ms": ms_pre,
