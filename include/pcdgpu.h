@@ -70,6 +70,9 @@ int pcdgpu_sync(pcdgpu_ctx* ctx);
 /* use a caller-owned CUDA stream (e.g. torch's current stream) instead of the context's own;
  * stream = the cudaStream_t value; 0 restores the context's stream */
 int pcdgpu_set_stream(pcdgpu_ctx* ctx, void* stream);
+/* on (default): the five MSMs of a proof run on separate internal streams and overlap; off: every
+ * kernel runs on the context's stream in program order (used for per-kernel timing) */
+int pcdgpu_set_concurrency(pcdgpu_ctx* ctx, int on);
 /* MSM window override (0 = automatic); exposed for benchmarking */
 int pcdgpu_set_msm_window(pcdgpu_ctx* ctx, int c);
 

@@ -83,6 +83,14 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
     return PCDGPU_E_CUDA;
   }
   ctx->stream = ctx->own_stream;
+  bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
+  for (int l = 1; l < pcdgpu_ctx::NLANE && ok; l++)
+    ok = cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking) == cudaSuccess &&
+         cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming) == cudaSuccess;
+  if (!ok) {
+    delete ctx;
+    return PCDGPU_E_CUDA;
+  }
   ctx->pinned_bytes = 1 << 16;
   if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
     cudaStreamDestroy(ctx->own_stream);
@@ -96,9 +104,14 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
 void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx) {
   if (!ctx) return;
   cudaSetDevice(ctx->device);
-  cudaStreamSynchronize(ctx->stream);
+  cudaDeviceSynchronize();
   for (int i = 0; i < pcdgpu_ctx::NSLOT; i++)
     if (ctx->slot[i]) cudaFree(ctx->slot[i]);
+  for (int l = 1; l < pcdgpu_ctx::NLANE; l++) {
+    if (ctx->lane_stream[l]) cudaStreamDestroy(ctx->lane_stream[l]);
+    if (ctx->ev_join[l]) cudaEventDestroy(ctx->ev_join[l]);
+  }
+  if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
   for (auto& kv : ctx->ntt_tables) cudaFree(kv.second.twiddles);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->prof_pinned) cudaFreeHost(ctx->prof_pinned);
@@ -119,6 +132,12 @@ int pcdgpu_set_stream(pcdgpu_ctx* ctx, void* stream) {
   if (!ctx) return PCDGPU_E_ARG;
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->stream = stream ? (cudaStream_t)stream : ctx->own_stream;
+  return 0;
+}
+int pcdgpu_set_concurrency(pcdgpu_ctx* ctx, int on) {
+  if (!ctx) return PCDGPU_E_ARG;
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  ctx->concurrent = on != 0;
   return 0;
 }
 int pcdgpu_set_msm_window(pcdgpu_ctx* ctx, int c) {
@@ -532,16 +551,34 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   memcpy((char*)ctx->pinned + 40, s, 40);
   PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
   PCD_TRY(groth16_prepare(ctx, pk->pairing, d_rs, (u32*)extras));
-  void* d_h;
-  PCD_TRY(witness_map_dev(ctx, r1cs, d_z, &d_h));
   const char* z = (const char*)d_z;
   size_t nv = pk->num_vars, ni = pk->num_inputs;
+  // Fork: the four MSMs over the assignment only need z and the extra scalars, so they start on lanes
+  // 1-4 while lane 0 runs the witness map and then the h MSM (the G2 MSM, the longest, goes first).
+  const bool fork = ctx->concurrent;
+  if (fork) {
+    PCD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
+  }
+  struct Job { const pcdgpu_bases* b; const char* sc; size_t n; const char* ex; size_t nex; void* out; };
+  Job jobs[4] = {{pk->b_g2_query, z + 40, nv - 1, extras + 3 * 40, 3, sum2},
+                 {pk->a_query, z + 40, nv - 1, extras, 3, (char*)sums1 + 2 * x1},
+                 {pk->b_g1_query, z + 40, nv - 1, extras + 3 * 40, 3, (char*)sums1 + 3 * x1},
+                 {pk->l_query, z + 40 * ni, nv - ni, extras + 6 * 40, 1, (char*)sums1 + 1 * x1}};
+  int rc = 0;
+  for (int j = 0; j < 4 && rc == 0; j++) {
+    ctx->lane = fork ? j + 1 : 0;
+    rc = bases_msm(ctx, jobs[j].b, 0, jobs[j].sc, 1, jobs[j].n, jobs[j].ex, jobs[j].nex, jobs[j].out);
+    if (fork && rc == 0 && cudaEventRecord(ctx->ev_join[j + 1], ctx->lane_stream[j + 1]) != cudaSuccess) rc = PCDGPU_E_CUDA;
+  }
+  ctx->lane = 0;
+  if (rc) return rc;
+  void* d_h;
+  PCD_TRY(witness_map_dev(ctx, r1cs, d_z, &d_h));
   // h: n coefficients vs n - 1 query points: truncated to the shorter
   PCD_TRY(bases_msm(ctx, pk->h_query, 0, d_h, 1, r1cs->n, nullptr, 0, (char*)sums1 + 0 * x1));
-  PCD_TRY(bases_msm(ctx, pk->l_query, 0, z + 40 * ni, 1, nv - ni, extras + 6 * 40, 1, (char*)sums1 + 1 * x1));
-  PCD_TRY(bases_msm(ctx, pk->a_query, 0, z + 40, 1, nv - 1, extras, 3, (char*)sums1 + 2 * x1));
-  PCD_TRY(bases_msm(ctx, pk->b_g1_query, 0, z + 40, 1, nv - 1, extras + 3 * 40, 3, (char*)sums1 + 3 * x1));
-  PCD_TRY(bases_msm(ctx, pk->b_g2_query, 0, z + 40, 1, nv - 1, extras + 3 * 40, 3, sum2));
+  if (fork)
+    for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
   PCD_TRY(groth16_assemble(ctx, pk->pairing, d_rs, sums1, sum2, d_proof));
   PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

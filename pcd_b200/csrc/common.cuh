@@ -63,8 +63,18 @@ struct pcdgpu_ctx {
   cudaStream_t stream = nullptr;
   int msm_window = 0;
   char err[512] = {0};
-  // grow-only scratch slots (slot ids are fixed per use so concurrent phases never alias)
-  static const int NSLOT = 16;
+  // Lanes: the five MSMs of a proof are independent, so each runs on its own stream with its own
+  // scratch and their latency-bound phases (bucket reduction, window combination) overlap the
+  // other lanes' accumulation.  Lane 0 is the context's (or the caller's) stream.
+  static const int NLANE = 5;
+  static const int SLOTS_PER_LANE = 16;
+  int lane = 0;
+  bool concurrent = true;
+  cudaStream_t lane_stream[NLANE] = {nullptr};
+  cudaEvent_t ev_fork = nullptr, ev_join[NLANE] = {nullptr};
+  cudaStream_t cur() const { return lane == 0 ? stream : lane_stream[lane]; }
+  // grow-only scratch slots (slot ids are fixed per use and lane so concurrent phases never alias)
+  static const int NSLOT = SLOTS_PER_LANE * NLANE;
   void* slot[NSLOT] = {nullptr};
   size_t slot_bytes[NSLOT] = {0};
   std::map<int, NttTables> ntt_tables;  // key = field * 64 + log_n
@@ -90,11 +100,11 @@ struct pcdgpu_ctx {
     sp.slot = slot;
     sp.units = units;
     sp.units_pinned = -1;
-    cudaEventRecord(sp.a, stream);
+    cudaEventRecord(sp.a, cur());
     return (int)spans_used++;
   }
   void prof_end(int id) {
-    if (id >= 0) cudaEventRecord(spans[id].b, stream);
+    if (id >= 0) cudaEventRecord(spans[id].b, cur());
   }
 
   void set_error(const char* fmt, ...) {
@@ -105,9 +115,10 @@ struct pcdgpu_ctx {
   }
   // scratch: returns a device buffer of at least `bytes` for slot `id`
   int scratch(int id, size_t bytes, void** out) {
+    id += lane * SLOTS_PER_LANE;
     if (bytes > slot_bytes[id]) {
       if (slot[id]) {
-        cudaStreamSynchronize(stream);
+        cudaStreamSynchronize(cur());
         cudaFree(slot[id]);
         slot[id] = nullptr;
         slot_bytes[id] = 0;
@@ -140,7 +151,8 @@ enum {
   SLOT_Z = 11,       // assignment on device
   SLOT_MISC = 12,
   SLOT_CUB = 13,
-  SLOT_MSM_HP = 14   // heavy-bucket partial sums
+  SLOT_MSM_HP = 14,  // heavy-bucket partial sums
+  SLOT_CUB2 = 15
 };
 
 template <class T>

@@ -6,6 +6,7 @@
 // affine proof points are bit-identical to any correct CPU evaluation of the same formulas.
 #include "groth16.cuh"
 
+#include "fp30.cuh"
 #include "msm_ops.cuh"
 #include "ntt.cuh"
 
@@ -294,9 +295,15 @@ __global__ void __launch_bounds__(256) bench_imadx_kernel(u32* out, int iters, u
 // dependent Montgomery products (the prover's inner loop): 2 independent chains per thread
 template <class F>
 __global__ void __launch_bounds__(256) bench_modmul_kernel(u32* out, int iters, u32 seed) {
-  F x = F::one(), y = F::r2();
-  x.l[0] ^= (seed + threadIdx.x) & 0xffff;
-  y.l[0] ^= (seed + blockIdx.x) & 0xffff;
+  F x, y;
+  const u32* in = out + 64 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 20;  // per-thread operands
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    x.l[i] = in[i];
+    y.l[i] = in[10 + i] ^ seed;
+  }
+  x.l[9] &= 0xff;
+  y.l[9] &= 0xff;
   for (int i = 0; i < iters; i++) {
     x = x * y;
     y = y * x;
@@ -304,19 +311,56 @@ __global__ void __launch_bounds__(256) bench_modmul_kernel(u32* out, int iters, 
   if (x.l[0] == 0x12345u && y.l[3] == 7u) out[0] = x.l[1];
 }
 
+// the radix-2^30 carry-free product (fp30.cuh), same shape of benchmark
+template <class F, int CHAINS>
+__global__ void __launch_bounds__(256) bench_modmul30_kernel(u32* out, int iters, u32 seed) {
+  F x[CHAINS], y[CHAINS];
+  const u32* in = out + 64 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 20;  // per-thread operands
+#pragma unroll
+  for (int c = 0; c < CHAINS; c++) {
+#pragma unroll
+    for (int i = 0; i < 10; i++) {
+      x[c].l[i] = (in[i] + c) & 0x3fffffffu;
+      y[c].l[i] = (in[10 + i] ^ seed) & 0x3fffffffu;
+    }
+    x[c].l[9] &= 0xfffff;
+    y[c].l[9] &= 0xfffff;
+  }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) x[c] = x[c] * y[c];
+#pragma unroll
+    for (int c = 0; c < CHAINS; c++) y[c] = y[c] * x[c];
+  }
+  u32 acc = 0;
+#pragma unroll
+  for (int c = 0; c < CHAINS; c++) acc ^= x[c].l[0] ^ y[c].l[3];
+  if (acc == 0x12345u) out[0] = acc;
+}
+
 int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double* ms_out) {
   void* d;
-  PCD_TRY(ctx->scratch(SLOT_MISC, 4096, &d));
+  size_t bytes = 4096 + (size_t)ctx->sm_count * 8 * 256 * 80;
+  PCD_TRY(ctx->scratch(SLOT_IO, bytes, &d));
+  PCD_CUDA(ctx, cudaMemsetAsync(d, 0x5a, bytes, ctx->stream));
   cudaEvent_t e0, e1;
   PCD_CUDA(ctx, cudaEventCreate(&e0));
   PCD_CUDA(ctx, cudaEventCreate(&e1));
   int blocks = ctx->sm_count * 8;
+  if (modmul == 9) blocks = ctx->sm_count;
   double per_thread = modmul == 3 ? 64.0 * iters : (modmul ? 2.0 * iters : 64.0 * iters);
+  if (modmul == 6) per_thread = 4.0 * iters;
+  if (modmul >= 7) blocks = ctx->sm_count * (modmul == 7 ? 2 : 1);  // low occupancy: 16 / 8 warps per SM
   for (int rep = 0; rep < 2; rep++) {  // first round warms up
     PCD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     if (modmul == 1) bench_modmul_kernel<FpR4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else if (modmul == 2) bench_modmul_kernel<FpQ4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else if (modmul == 3) bench_imadx_kernel<<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 4) bench_modmul30_kernel<Fp30R4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 5) bench_modmul30_kernel<Fp30Q4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 6) bench_modmul30_kernel<Fp30Q4, 2><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 7 || modmul == 8) bench_modmul30_kernel<Fp30Q4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 9) bench_modmul_kernel<FpQ4><<<ctx->sm_count, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else bench_imad_kernel<<<blocks, 256, 0, ctx->stream>>>((unsigned long long*)d, iters, 7u);
     PCD_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     PCD_CUDA(ctx, cudaEventSynchronize(e1));

@@ -20,6 +20,7 @@
 // With precomputed bases (pcdgpu_bases_upload(..., precompute = 1)) the table holds 2^(c j) P for
 // every window j, all windows share ONE bucket set and step 6's doubling chain disappears.
 #pragma once
+#include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
 #include "common.cuh"
@@ -105,14 +106,28 @@ static __global__ void msm_scatter_kernel(const int* __restrict__ dig, size_t n,
 }
 
 // ---- 4. bucket accumulation -------------------------------------------------------------------
+// Buckets are visited in order of decreasing size (perm, from a radix sort of the clamped sizes): the 32
+// buckets of a warp then hold (almost) the same number of entries, so no lane idles while its
+// neighbours finish -- with buckets in natural order only 70 % of the lanes were active (ncu, round 1).
+static __global__ void msm_sizekey_kernel(const u32* __restrict__ counts, size_t nbuckets, u32* __restrict__ key,
+                                          u32* __restrict__ id) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nbuckets) return;
+  u32 c = counts[g];
+  key[g] = c < 2047u ? c : 2047u;
+  id[g] = (u32)g;
+}
+
 template <class C>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ bases,
                                                              const u32* __restrict__ offsets,
-                                                             const u32* __restrict__ entries, size_t nbuckets,
+                                                             const u32* __restrict__ entries,
+                                                             const u32* __restrict__ perm, size_t nbuckets,
                                                              void* __restrict__ buckets, u32* __restrict__ heavy) {
   typedef typename C::F F;
-  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (g >= nbuckets) return;
+  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (t >= nbuckets) return;
+  size_t g = perm[t];
   u32 lo = offsets[g], hi = offsets[g + 1];
   XYZZ<C> acc = XYZZ<C>::inf();
   if (hi - lo > (u32)MSM_HEAVY) {
@@ -364,7 +379,7 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                    const void* d_extra, size_t n_extra, MsmPlan plan, void* d_out) {
   const size_t n = n_main + n_extra;
   typedef typename C::ScalarParams SP;
-  cudaStream_t st = ctx->stream;
+  cudaStream_t st = ctx->cur();
   if (n == 0) {
     PCD_CUDA(ctx, cudaMemsetAsync(d_out, 0, sizeof(XYZZ<C>), st));
     return 0;
@@ -380,14 +395,18 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   void *dig, *ent, *cnt, *bkt, *seg, *cub_tmp;
   PCD_TRY(ctx->scratch(SLOT_MSM_DIG, (size_t)nwin * n * 4, &dig));
   PCD_TRY(ctx->scratch(SLOT_MSM_ENT, (size_t)nwin * n * 4, &ent));
-  // counts | offsets | cursor, each nbuckets + 1, then the heavy list
+  // counts | offsets | cursor | size keys (in, out) | bucket ids (in, out), each nbuckets + 1, then the heavy list
   size_t cstride = (nbuckets + 1 + 3) & ~(size_t)3;
-  PCD_TRY(ctx->scratch(SLOT_MSM_CNT, (3 * cstride + MSM_MAX_HEAVY + 4) * 4, &cnt));
+  PCD_TRY(ctx->scratch(SLOT_MSM_CNT, (7 * cstride + MSM_MAX_HEAVY + 4) * 4, &cnt));
   PCD_TRY(ctx->scratch(SLOT_MSM_BKT, nbuckets * sizeof(XYZZ<C>), &bkt));
   u32* counts = (u32*)cnt;
   u32* offsets = counts + cstride;
   u32* cursor = offsets + cstride;
-  u32* heavy = cursor + cstride;
+  u32* key_in = cursor + cstride;
+  u32* key_out = key_in + cstride;
+  u32* id_in = key_out + cstride;
+  u32* perm = id_in + cstride;
+  u32* heavy = perm + cstride;
   PCD_CUDA(ctx, cudaMemsetAsync(counts, 0, cstride * 4, st));
   PCD_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
   const int acc_slot = sizeof(typename C::F) > 40 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1;
@@ -403,6 +422,16 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   PCD_TRY(ctx->scratch(SLOT_CUB, cub_bytes + 16, &cub_tmp));
   PCD_CUDA(ctx, cub::DeviceScan::ExclusiveSum(cub_tmp, cub_bytes, counts, offsets, (int)(nbuckets + 1), st));
   PCD_CUDA(ctx, cudaMemcpyAsync(cursor, offsets, (nbuckets + 1) * 4, cudaMemcpyDeviceToDevice, st));
+  // bucket visiting order: decreasing size
+  msm_sizekey_kernel<<<(unsigned)((nbuckets + 255) / 256), 256, 0, st>>>(counts, nbuckets, key_in, id_in);
+  PCD_CUDA(ctx, cudaGetLastError());
+  size_t sort_bytes = 0;
+  cub::DeviceRadixSort::SortPairsDescending(nullptr, sort_bytes, key_in, key_out, id_in, perm, (int)nbuckets, 0, 11, st);
+  void* sort_tmp;
+  PCD_TRY(ctx->scratch(SLOT_CUB2, sort_bytes + 16, &sort_tmp));
+  PCD_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(sort_tmp, sort_bytes, key_in, key_out, id_in, perm,
+                                                          (int)nbuckets, 0, 11, st));
+  ctx->launches += 4;  // size keys + cub's radix sort passes
   size_t total = (size_t)nwin * n;
   msm_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const int*)dig, n, c, nwin, shared,
                                                                       plan.stride, plan.offset, cursor, (u32*)ent);
@@ -414,7 +443,7 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     cudaMemcpyAsync(ctx->prof_pinned + ps, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st);
   }
   msm_accumulate_kernel<C><<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(d_bases, offsets, (const u32*)ent,
-                                                                               nbuckets, bkt, heavy);
+                                                                               perm, nbuckets, bkt, heavy);
   PCD_CUDA(ctx, cudaGetLastError());
   size_t heavy_smem = MSM_HEAVY_THREADS * sizeof(XYZZ<C>);
   // heavy-bucket partial list: at most one partial per MSM_HEAVY_CHUNK entries plus one per bucket

@@ -28,7 +28,7 @@ TWO_ADICITY = {FIELD_R4: 34, FIELD_Q4: 17}
 
 EXPORTS = [
     "pcdgpu_strerror", "pcdgpu_last_error", "pcdgpu_affine_bytes", "pcdgpu_ctx_create", "pcdgpu_ctx_destroy",
-    "pcdgpu_sync", "pcdgpu_set_stream", "pcdgpu_set_msm_window", "pcdgpu_ntt", "pcdgpu_ntt_dev", "pcdgpu_msm",
+    "pcdgpu_sync", "pcdgpu_set_stream", "pcdgpu_set_concurrency", "pcdgpu_set_msm_window", "pcdgpu_ntt", "pcdgpu_ntt_dev", "pcdgpu_msm",
     "pcdgpu_msm_dev", "pcdgpu_bases_upload", "pcdgpu_bases_free", "pcdgpu_msm_bases", "pcdgpu_msm_bases_dev",
     "pcdgpu_xyzz_sum", "pcdgpu_xyzz_download", "pcdgpu_fixed_base_mul", "pcdgpu_fixed_base_mul_dev",
     "pcdgpu_r1cs_upload", "pcdgpu_r1cs_free", "pcdgpu_r1cs_domain_size", "pcdgpu_witness_map", "pcdgpu_pk_upload",
@@ -68,6 +68,7 @@ def load():
     lib.pcdgpu_sync.argtypes = [vp]
     lib.pcdgpu_set_stream.argtypes = [vp, vp]
     lib.pcdgpu_set_msm_window.argtypes = [vp, ci]
+    lib.pcdgpu_set_concurrency.argtypes = [vp, ci]
     lib.pcdgpu_ntt.argtypes = [vp, ci, vp, ctypes.c_uint32, ci, ci]
     lib.pcdgpu_ntt_dev.argtypes = [vp, ci, vp, ctypes.c_uint32, ci, ci]
     lib.pcdgpu_msm.argtypes = [vp, ci, vp, vp, sz, vp]
@@ -145,6 +146,9 @@ class Context:
 
     def set_stream(self, stream_ptr: int):
         self._check(self.lib.pcdgpu_set_stream(self.h, ctypes.c_void_p(stream_ptr)))
+
+    def set_concurrency(self, on: bool):
+        self._check(self.lib.pcdgpu_set_concurrency(self.h, int(on)))
 
     def set_msm_window(self, c: int):
         self._check(self.lib.pcdgpu_set_msm_window(self.h, c))
