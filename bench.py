@@ -221,8 +221,60 @@ def run_gpu(args, rank, local_rank, world):
         log("proof at 2^%d verified against the trapdoor" % log_n)
 
     rs = [(draw()[1], draw()[1]) for _ in range(args.warmup + 2 * args.steps)]
-    for i in range(args.warmup):
-        g.create_proof_dev(idx, z_dev.data_ptr(), *rs[i])
+    # Proofs in flight: independent proofs (PCD nodes of one tree depth) are issued from `inflight` host
+    # threads, each with its own context (streams + scratch) over the SAME resident key and matrices, so
+    # one proof's single-warp tail (window combination, proof assembly) overlaps the next one's MSMs.
+    nfl = max(1, args.inflight)
+    lanes = [(ctx, g, stream)]
+    for _ in range(nfl - 1):
+        c2 = pcd_b200.Context(local_rank)
+        s2 = torch.cuda.Stream(device=dev)
+        c2.set_stream(s2.cuda_stream)
+        lanes.append((c2, pcd_b200.Groth16(c2, pcd_b200.MNT4_298), s2))
+
+    def run_steps(first, count, host):
+        """prove rs[first : first + count], round-robin over the in-flight contexts; returns elapsed ms
+        measured with CUDA events on the launching streams (earliest start to latest end)"""
+        starts = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+        ends = [torch.cuda.Event(enable_timing=True) for _ in lanes]
+        errs = []
+
+        def worker(k):
+            try:
+                torch.cuda.set_device(local_rank)
+                c_, g_, s_ = lanes[k]
+                starts[k].record(s_)
+                for i in range(first + k, first + count, len(lanes)):
+                    r_l, s_l = rs[i]
+                    if host:
+                        out = np.zeros(40, dtype=np.uint64)
+                        c_._check(c_.lib.pcdgpu_groth16_prove(c_.h, idx.pk, idx.r1cs, z_host.data_ptr(), r_l.ctypes.data,
+                                                              s_l.ctypes.data, out.ctypes.data))
+                    else:
+                        g_.create_proof_dev(idx, z_dev.data_ptr(), r_l, s_l)
+                ends[k].record(s_)
+            except Exception as e:  # noqa: BLE001
+                errs.append(e)
+
+        ths = [threading.Thread(target=worker, args=(k,)) for k in range(len(lanes))]
+        t0 = time.perf_counter()
+        for t in ths:
+            t.start()
+        for t in ths:
+            t.join()
+        torch.cuda.synchronize()
+        wall = 1e3 * (time.perf_counter() - t0)
+        if errs:
+            raise errs[0]
+        dev_ms = max(a.elapsed_time(b) for a in starts for b in ends)
+        return dev_ms, wall
+
+    if args.no_concurrency:
+        for c_, _, _ in lanes:
+            c_.set_concurrency(False)
+    for k in range(len(lanes)):
+        for i in range(args.warmup):
+            lanes[k][1].create_proof_dev(idx, z_dev.data_ptr(), *rs[i])
 
     # ---- timed region 1: inputs resident in HBM -------------------------------------------------------
     sampler = ClockSampler(local_rank)
@@ -234,18 +286,23 @@ def run_gpu(args, rank, local_rank, world):
     spans = (ctypes.c_uint64 * NC)()
     launches = ctypes.c_uint64()
     ctx.lib.pcdgpu_profile_enable(ctx.h, 0)  # no event spans in the timed region; resets the launch counter
+    for c_, _, _ in lanes[1:]:
+        c_.lib.pcdgpu_profile_enable(c_.h, 0)
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     barrier()
-    e0.record(stream)
-    for i in range(args.steps):
-        g.create_proof_dev(idx, z_dev.data_ptr(), *rs[args.warmup + i])
-    e1.record(stream)
+    dev_ms, _ = run_steps(args.warmup, args.steps, host=False)
     barrier()
-    ms_dev = max_over_ranks(e0.elapsed_time(e1))
+    ms_dev = max_over_ranks(dev_ms)
     ctx._check(ctx.lib.pcdgpu_profile_read(ctx.h, ms, units, spans, ctypes.byref(launches)))
+    n_launches = int(launches.value)
+    for c_, _, _ in lanes[1:]:
+        l2 = ctypes.c_uint64()
+        c_._check(c_.lib.pcdgpu_profile_read(c_.h, ms, units, spans, ctypes.byref(l2)))
+        n_launches += int(l2.value)
     # per-kernel pass (same proofs again): the MSMs of a proof normally overlap on five streams, which
     # makes per-kernel durations meaningless, so this pass serialises them and records CUDA-event spans
     ctx.set_concurrency(False)
+    g.create_proof_dev(idx, z_dev.data_ptr(), *rs[0])  # grows lane 0's scratch outside the spans
     ctx.lib.pcdgpu_profile_enable(ctx.h, 1)
     e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e2.record(stream)
@@ -257,21 +314,14 @@ def run_gpu(args, rank, local_rank, world):
     launches2 = ctypes.c_uint64()
     ctx._check(ctx.lib.pcdgpu_profile_read(ctx.h, ms, units, spans, ctypes.byref(launches2)))
     ctx.lib.pcdgpu_profile_enable(ctx.h, 0)
-    ctx.set_concurrency(True)
+    ctx.set_concurrency(not args.no_concurrency)
     prof = {"ms": list(ms), "units": list(units), "spans": list(spans)}
 
     # ---- timed region 2: end to end through the C ABI with host buffers ---------------------------------
     barrier()
-    e0.record(stream)
-    t_wall = time.perf_counter()
-    for i in range(args.steps):
-        r_l, s_l = rs[args.warmup + args.steps + i]
-        out = np.zeros(40, dtype=np.uint64)
-        ctx._check(ctx.lib.pcdgpu_groth16_prove(ctx.h, idx.pk, idx.r1cs, z_host.data_ptr(), r_l.ctypes.data,
-                                                s_l.ctypes.data, out.ctypes.data))
-    e1.record(stream)
+    dev_ms, wall_ms = run_steps(args.warmup + args.steps, args.steps, host=True)
     barrier()
-    ms_e2e = max_over_ranks(max(e0.elapsed_time(e1), 1e3 * (time.perf_counter() - t_wall)))
+    ms_e2e = max_over_ranks(max(dev_ms, wall_ms))
     clocks = sampler.stop()
 
     # ---- kernel figures: G1 MSM at 2^20 points and the largest NTT --------------------------------------
@@ -319,11 +369,11 @@ def run_gpu(args, rank, local_rank, world):
                    "msm_lengths": {"h": (1 << log_n) - 1, "l": inst["num_witness"], "a": nvars - 1, "b_g1": nvars - 1,
                                    "b_g2": nvars - 1},
                    "per_gpu": "independent instance per GPU (PCD nodes), no collective",
-                   "precomputed_window_tables": not args.no_precompute,
+                   "precomputed_window_tables": not args.no_precompute, "proofs_in_flight": nfl,
                    "l2": "per-step inputs (proving-key tables, several GB) exceed the 126 MB L2"},
         "e2e": {"value": e2e_value, "unit": "proofs/s", "h2d_bytes_per_step": nvars * 40 + 80,
                 "d2h_bytes_per_step": 320, "ms_per_step": ms_e2e / args.steps},
-        "gpu_launches": int(launches.value),
+        "gpu_launches": n_launches,
         "clocks": clocks,
         "roofline": roofline,
         "kernel_time_shares": shares,
@@ -431,7 +481,10 @@ def main():
     ap.add_argument("--ntt-log-n", type=int, default=24)
     ap.add_argument("--cpu-sample-log-n", type=int, default=17)
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--inflight", type=int, default=int(os.environ.get("PCD_BENCH_INFLIGHT", "2")),
+                    help="independent proofs issued concurrently per GPU (each on its own context)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-concurrency", action="store_true", help="run the five MSMs of a proof on one stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup
     rank = int(os.environ.get("RANK", "0"))

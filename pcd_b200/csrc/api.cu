@@ -20,10 +20,15 @@ static int g2_of(int pairing) { return pairing == PCDGPU_MNT4_298 ? PCDGPU_MNT4_
 static const int MSM_BITS = 298;
 int msm_num_windows_c(int c) { return (MSM_BITS + 1 + c - 1) / c; }
 int msm_auto_window_c(size_t n, int shared) {
-  int lg = ilog2_ceil(n ? n : 1);
+  // lg = round(log2 n): a key query of 2^20 + 3 points must not be treated as 2^21
+  int lg = 0;
+  while (((size_t)3 << lg) < 2 * (n ? n : 1)) lg++;  // smallest lg with 1.5 * 2^lg >= n
   int c;
   if (shared) {
-    c = lg;  // one bucket set for all windows: ~2 * nwin entries per bucket
+    // One bucket set for all windows.  Accumulation time ~ nwin * n mixed additions (it is pipe-bound as
+    // long as there are >= ~2 * 10^5 buckets to give every SM its threads), reduction ~ 2^(c-1) buckets at
+    // ~14 x the cost of a mixed addition each: measured optimum c = lg - 1 (2^16: 15, 2^20: 19).
+    c = lg - 1;
     if (c < 6) c = 6;
     if (c > 21) c = 21;
   } else {

@@ -13,9 +13,10 @@
 //   4. msm_accumulate one thread per bucket walks its entries with XYZZ mixed additions
 //                     (8M + 2S); buckets beyond HEAVY entries (e.g. the "scalar == 1" bucket of a
 //                     real witness) are left to msm_accumulate_heavy, one CTA each;
-//   5. msm_reduce     per window sum_b (b+1) B_b: every thread takes L consecutive buckets with the
-//                     running-sum trick and adds [t L] * (its plain sum);
-//   6. msm_window_sum / msm_horner  tree-sum per window, then the 2^c Horner chain.
+//   5. msm_reduce_seg per window sum_b (b+1) B_b: every thread takes L consecutive buckets with the
+//                     running-sum trick and adds [t L] * (its plain sum); msm_sum folds the threads'
+//                     contributions (CTA tree sums);
+//   6. msm_combine    the 2^c Horner chain over the window sums (one window with precomputed tables).
 //
 // With precomputed bases (pcdgpu_bases_upload(..., precompute = 1)) the table holds 2^(c j) P for
 // every window j, all windows share ONE bucket set and step 6's doubling chain disappears.
@@ -31,8 +32,8 @@ static constexpr int MSM_HEAVY = 1024;      // entries per bucket handled by one
 static constexpr int MSM_HEAVY_THREADS = 128;
 static constexpr int MSM_MAX_HEAVY = 4096;  // size of the heavy-bucket list
 static constexpr int MSM_HEAVY_CHUNK = 1024;  // entries of a heavy bucket summed by one CTA at a time
-static constexpr int MSM_SUM_PER_CTA = 2048;  // points folded by one CTA of msm_sum_kernel
-static constexpr int MSM_REDUCE_LOGL = 3;     // bucket reduction: 2^3 points per thread and level
+static constexpr int MSM_SUM_PER_CTA = 256;   // points folded by one CTA of msm_sum_kernel (two per thread + tree)
+static constexpr int MSM_REDUCE_LOGL = 3;     // bucket reduction: 2^3 buckets per thread
 
 // ---- 1. digits ------------------------------------------------------------------------------
 // dig[w * n + i] = signed digit of scalar i in window w; counts[bucket]++ for non-zero digits.
@@ -118,33 +119,44 @@ static __global__ void msm_sizekey_kernel(const u32* __restrict__ counts, size_t
   id[g] = (u32)g;
 }
 
+// Persistent warps pull 32 buckets at a time from a global queue (dynamic scheduling): with one thread per
+// bucket and a plain grid the kernel ran in a few "waves" of equally long threads, and its time was
+// the wave count rounded up (c = 18 at 2^20: 2.3 waves cost 3).
 template <class C>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ bases,
                                                              const u32* __restrict__ offsets,
                                                              const u32* __restrict__ entries,
                                                              const u32* __restrict__ perm, size_t nbuckets,
-                                                             void* __restrict__ buckets, u32* __restrict__ heavy) {
+                                                             void* __restrict__ buckets, u32* __restrict__ heavy,
+                                                             u32* __restrict__ queue) {
   typedef typename C::F F;
-  size_t t = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (t >= nbuckets) return;
-  size_t g = perm[t];
-  u32 lo = offsets[g], hi = offsets[g + 1];
-  XYZZ<C> acc = XYZZ<C>::inf();
-  if (hi - lo > (u32)MSM_HEAVY) {
-    u32 slot = atomicAdd(&heavy[0], 1u);
-    if (slot < (u32)MSM_MAX_HEAVY) {
-      heavy[1 + slot] = (u32)g;
-      return;  // msm_accumulate_heavy writes the bucket
+  const unsigned lane = threadIdx.x & 31;
+  for (;;) {
+    u32 first = 0;
+    if (lane == 0) first = atomicAdd(queue, 32u);
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (first >= nbuckets) break;
+    size_t t = (size_t)first + lane;
+    if (t >= nbuckets) continue;
+    size_t g = perm[t];
+    u32 lo = offsets[g], hi = offsets[g + 1];
+    XYZZ<C> acc = XYZZ<C>::inf();
+    if (hi - lo > (u32)MSM_HEAVY) {
+      u32 slot = atomicAdd(&heavy[0], 1u);
+      if (slot < (u32)MSM_MAX_HEAVY) {
+        heavy[1 + slot] = (u32)g;
+        continue;  // msm_accumulate_heavy writes the bucket
+      }
+      // list full: fall through and do it serially (correct, slow)
     }
-    // list full: fall through and do it serially (correct, slow)
+    for (u32 e = lo; e < hi; e++) {
+      u32 ent = entries[e];
+      AffinePoint<F> p = ld_vec<AffinePoint<F>>(bases, ent & 0x7fffffffu);
+      if (ent >> 31) p.y = p.y.neg();
+      acc.madd(p);
+    }
+    st_vec(buckets, g, acc);
   }
-  for (u32 e = lo; e < hi; e++) {
-    u32 ent = entries[e];
-    AffinePoint<F> p = ld_vec<AffinePoint<F>>(bases, ent & 0x7fffffffu);
-    if (ent >> 31) p.y = p.y.neg();
-    acc.madd(p);
-  }
-  st_vec(buckets, g, acc);
 }
 
 // CTA-wide tree sum of one xyzz point per thread (shared memory, MSM_HEAVY_THREADS entries)
@@ -219,32 +231,30 @@ __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_heavy_finish_kernel(
 }
 
 // ---- 5. bucket reduction ----------------------------------------------------------------------
-// S(P) = sum_b (b + 1) P_b over `count` points per window.  With segments of L = 2^logL points,
-//   S(P) = sum_t acc_t + L * S(Q),   acc_t = sum_j (j + 1) P_{tL+j},   Q_u = R_{u+1},  R_t = sum_j P_{tL+j}
-// so one level turns `count` points into T = ceil(count / L) segment sums (the next level's input,
-// first one dropped) plus T "acc" points whose plain sum is this level's contribution.  Every
-// thread runs the running-sum trick on its L points: 2 L additions, no scalar multiplication.
-// Arrays are [window][index]; in_pitch / out_pitch are the per-window strides in points.
+// S = sum_b (b + 1) B_b per window.  Thread t of a window takes the L = 2^logL buckets [tL, tL + L) from
+// the top down with the running-sum trick (2 L general additions):
+//   run = sum_j B_{tL+j},  acc = sum_j (j + 1) B_{tL+j},  contribution = acc + [t L] run
+// ([t L] run by double-and-add, t L < 2^c); the T = B / L contributions of a window are then folded by
+// msm_sum_kernel.  Short dependent chains and three launches: this phase is latency-bound.
 template <class C>
-__global__ void __launch_bounds__(128) msm_reduce_level_kernel(const void* __restrict__ in, size_t in_pitch,
-                                                               size_t in_skip, size_t count, int logL, int nwin,
-                                                               void* __restrict__ acc_out, void* __restrict__ run_out,
-                                                               size_t out_pitch) {
+__global__ void __launch_bounds__(128, 4) msm_reduce_seg_kernel(const void* __restrict__ buckets, size_t B, int logL,
+                                                             int nwin, void* __restrict__ seg) {
   const size_t L = (size_t)1 << logL;
-  const size_t T = (count + L - 1) >> logL;
+  const size_t T = (B + L - 1) >> logL;
   size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (gid >= T * nwin) return;
   size_t w = gid / T, t = gid - w * T;
-  size_t base = w * in_pitch + in_skip + t * L;
-  size_t lim = count - t * L < L ? count - t * L : L;
+  size_t base = w * B + t * L;
+  size_t lim = B - t * L < L ? B - t * L : L;
   XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
   for (size_t j = lim; j-- > 0;) {
-    XYZZ<C> p = ld_vec_rw<XYZZ<C>>(in, base + j);
+    XYZZ<C> p = ld_vec_rw<XYZZ<C>>(buckets, base + j);
     run.add(p);
     acc.add(run);
   }
-  st_vec(acc_out, w * out_pitch + t, acc);
-  st_vec(run_out, w * out_pitch + t, run);
+  u32 k = (u32)(t * L);
+  if (k != 0 && !run.is_inf()) acc.add(XYZZ<C>::mul(run, &k, 1));
+  st_vec(seg, gid, acc);
 }
 
 // out[w * out_pitch + blockIdx.x'] = sum of up to MSM_SUM_PER_CTA consecutive points of window w
@@ -263,23 +273,11 @@ __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_sum_kernel(const void* 
   if (threadIdx.x == 0) st_vec(out, w * out_pitch + k, sm[0]);
 }
 
-// ---- 6. combine levels and windows ----------------------------------------------------------------
-// lvl[(l * nwin + w)] = A_l of window w.  window sum = A_0 + L (A_1 + L (A_2 + ...)); result =
-// sum_w 2^(c w) window_sum[w] by Horner.  One thread per window for the first part.
+// ---- 6. combine windows ---------------------------------------------------------------------------
+// result = sum_w 2^(c w) wsum[w] by Horner (one thread; nwin = 1 with precomputed tables)
 template <class C>
-__global__ void msm_combine_kernel(const void* __restrict__ lvl, int nlevels, int logL, int c, int nwin,
-                                   void* __restrict__ wsum, void* __restrict__ out) {
-  int w = threadIdx.x;
-  if (w < nwin) {
-    XYZZ<C> total = ld_vec_rw<XYZZ<C>>(lvl, (size_t)(nlevels - 1) * nwin + w);
-    for (int l = nlevels - 2; l >= 0; l--) {
-      for (int i = 0; i < logL; i++) total = total.dbl();
-      total.add(ld_vec_rw<XYZZ<C>>(lvl, (size_t)l * nwin + w));
-    }
-    st_vec(wsum, w, total);
-  }
-  __syncthreads();
-  if (threadIdx.x != 0) return;
+__global__ void msm_combine_kernel(const void* __restrict__ wsum, int c, int nwin, void* __restrict__ out) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
   XYZZ<C> total = ld_vec_rw<XYZZ<C>>(wsum, nwin - 1);
   for (int ww = nwin - 2; ww >= 0; ww--) {
     for (int i = 0; i < c; i++) total = total.dbl();
@@ -397,7 +395,7 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   PCD_TRY(ctx->scratch(SLOT_MSM_ENT, (size_t)nwin * n * 4, &ent));
   // counts | offsets | cursor | size keys (in, out) | bucket ids (in, out), each nbuckets + 1, then the heavy list
   size_t cstride = (nbuckets + 1 + 3) & ~(size_t)3;
-  PCD_TRY(ctx->scratch(SLOT_MSM_CNT, (7 * cstride + MSM_MAX_HEAVY + 4) * 4, &cnt));
+  PCD_TRY(ctx->scratch(SLOT_MSM_CNT, (7 * cstride + MSM_MAX_HEAVY + 8) * 4, &cnt));
   PCD_TRY(ctx->scratch(SLOT_MSM_BKT, nbuckets * sizeof(XYZZ<C>), &bkt));
   u32* counts = (u32*)cnt;
   u32* offsets = counts + cstride;
@@ -409,6 +407,8 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   u32* heavy = perm + cstride;
   PCD_CUDA(ctx, cudaMemsetAsync(counts, 0, cstride * 4, st));
   PCD_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
+  u32* queue = heavy + MSM_MAX_HEAVY + 2;
+  PCD_CUDA(ctx, cudaMemsetAsync(queue, 0, 4, st));
   const int acc_slot = sizeof(typename C::F) > 40 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1;
   int ps = ctx->prof_begin(PROF_MSM_SORT, (double)n * nwin);
   ctx->launches += 6 + 2;  // digits, scatter, accumulate, heavy x2, combine + cub's scan (init, scan); the
@@ -442,8 +442,13 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     ctx->spans[ps].units_pinned = ps;
     cudaMemcpyAsync(ctx->prof_pinned + ps, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st);
   }
-  msm_accumulate_kernel<C><<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(d_bases, offsets, (const u32*)ent,
-                                                                               perm, nbuckets, bkt, heavy);
+  int acc_ctas = 0;
+  PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C>, 128, 0));
+  if (acc_ctas < 1) acc_ctas = 1;
+  size_t acc_grid = (size_t)acc_ctas * ctx->sm_count;
+  if (acc_grid > (nbuckets + 127) / 128) acc_grid = (nbuckets + 127) / 128;
+  msm_accumulate_kernel<C><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets, bkt,
+                                                             heavy, queue);
   PCD_CUDA(ctx, cudaGetLastError());
   size_t heavy_smem = MSM_HEAVY_THREADS * sizeof(XYZZ<C>);
   // heavy-bucket partial list: at most one partial per MSM_HEAVY_CHUNK entries plus one per bucket
@@ -466,63 +471,40 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   ps = ctx->prof_begin(PROF_MSM_REDUCE, (double)nbuckets);
-  // multi-level reduction (see msm_reduce_level_kernel).  seg layout, in points:
-  //   lvl   [MAXLVL][rwin]           level sums A_l
-  //   run   [2][rwin][T0]            ping-pong segment sums (next level's input)
-  //   acc   [rwin][T0]               this level's acc points
-  //   part  [rwin][T0 / SUM + 1]     partial sums while folding acc
+  // seg layout, in points: contributions [rwin][T] | partial sums 2 x [rwin][T / SUM + 2] | wsum [rwin]
   const int logL = MSM_REDUCE_LOGL;
   const size_t L = (size_t)1 << logL;
-  const size_t T0 = (B + L - 1) >> logL;
-  const int MAXLVL = 32;
-  const size_t part_pitch = T0 / MSM_SUM_PER_CTA + 2;
-  size_t seg_points = (size_t)MAXLVL * rwin + 3 * rwin * T0 + 2 * rwin * part_pitch + rwin + 8;
-  PCD_TRY(ctx->scratch(SLOT_MSM_SEG, seg_points * sizeof(XYZZ<C>), &seg));
-  char* sp = (char*)seg;
+  const size_t T = (B + L - 1) >> logL;
+  const size_t part_pitch = T / MSM_SUM_PER_CTA + 2;
   const size_t PB = sizeof(XYZZ<C>);
-  void* lvl = sp;
-  void* run_buf[2] = {sp + (size_t)MAXLVL * rwin * PB, sp + ((size_t)MAXLVL * rwin + (size_t)rwin * T0) * PB};
-  void* acc_buf = sp + ((size_t)MAXLVL * rwin + 2 * (size_t)rwin * T0) * PB;
-  void* part_buf[2] = {(char*)acc_buf + (size_t)rwin * T0 * PB, (char*)acc_buf + ((size_t)rwin * T0 + rwin * part_pitch) * PB};
+  PCD_TRY(ctx->scratch(SLOT_MSM_SEG, ((size_t)rwin * T + 2 * rwin * part_pitch + rwin + 8) * PB, &seg));
+  char* sp = (char*)seg;
+  void* part_buf[2] = {sp + (size_t)rwin * T * PB, sp + ((size_t)rwin * T + rwin * part_pitch) * PB};
   void* wsum = (char*)part_buf[1] + (size_t)rwin * part_pitch * PB;
-  const void* in = bkt;
-  size_t in_pitch = B, in_skip = 0, count = B;
-  int nlevels = 0;
-  while (count > 0 && nlevels < MAXLVL) {
-    size_t T = (count + L - 1) >> logL;
-    void* run_out = run_buf[nlevels & 1];
-    msm_reduce_level_kernel<C><<<(unsigned)((T * rwin + 127) / 128), 128, 0, st>>>(in, in_pitch, in_skip, count, logL,
-                                                                                rwin, acc_buf, run_out, T0);
+  msm_reduce_seg_kernel<C><<<(unsigned)((T * rwin + 127) / 128), 128, 0, st>>>(bkt, B, logL, rwin, seg);
+  PCD_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  const void* fin = seg;
+  size_t fpitch = T, fcount = T;
+  int pp = 0;
+  for (;;) {
+    size_t ctas = (fcount + MSM_SUM_PER_CTA - 1) / MSM_SUM_PER_CTA;
+    bool last = ctas == 1;
+    void* fout = last ? wsum : part_buf[pp];
+    size_t opitch = last ? 1 : part_pitch;
+    msm_sum_kernel<C><<<(unsigned)(ctas * rwin), MSM_HEAVY_THREADS, heavy_smem, st>>>(fin, fpitch, fcount, fout, opitch,
+                                                                                   ctas);
     PCD_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
-    // fold the T acc points of every window down to one: lvl[nlevels][w]
-    const void* fin = acc_buf;
-    size_t fpitch = T0, fcount = T;
-    int pp = 0;
-    for (;;) {
-      size_t ctas = (fcount + MSM_SUM_PER_CTA - 1) / MSM_SUM_PER_CTA;
-      bool last = ctas == 1;
-      void* fout = last ? (char*)lvl + (size_t)nlevels * rwin * PB : part_buf[pp];
-      size_t opitch = last ? 1 : part_pitch;
-      msm_sum_kernel<C><<<(unsigned)(ctas * rwin), MSM_HEAVY_THREADS, heavy_smem, st>>>(fin, fpitch, fcount, fout, opitch,
-                                                                                     ctas);
-      PCD_CUDA(ctx, cudaGetLastError());
-      ctx->launches += 1;
-      if (last) break;
-      fin = fout;
-      fpitch = part_pitch;
-      fcount = ctas;
-      pp ^= 1;
-    }
-    nlevels++;
-    in = run_out;
-    in_pitch = T0;
-    in_skip = 1;
-    count = T - 1;
+    if (last) break;
+    fin = fout;
+    fpitch = part_pitch;
+    fcount = ctas;
+    pp ^= 1;
   }
   ctx->prof_end(ps);
   ps = ctx->prof_begin(PROF_MSM_TAIL, (double)rwin);
-  msm_combine_kernel<C><<<1, 128, 0, st>>>(lvl, nlevels, logL, c, rwin, wsum, d_out);
+  msm_combine_kernel<C><<<1, 32, 0, st>>>(wsum, c, rwin, d_out);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   return 0;
