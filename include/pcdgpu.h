@@ -160,6 +160,9 @@ int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affin
 #define PCDGPU_PROF_CLASSES 8
 int pcdgpu_profile_enable(pcdgpu_ctx* ctx, int on);
 int pcdgpu_profile_read(pcdgpu_ctx* ctx, double* ms, double* units, uint64_t* spans, uint64_t* launches);
+/* start / end (ms after the first span's start) and class of every span recorded since the last read:
+ * the timeline of a proof whose MSMs overlap on the context's internal streams.  Does not reset. */
+int pcdgpu_profile_timeline(pcdgpu_ctx* ctx, double* t0_ms, double* t1_ms, int* cls, size_t cap, size_t* count);
 
 /* ---- measurement helpers ----------------------------------------------------------------------
  * Integer-pipe microbenchmark: every thread runs `iters` rounds of 8 independent

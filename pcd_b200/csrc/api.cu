@@ -25,10 +25,10 @@ int msm_auto_window_c(size_t n, int shared) {
   while (((size_t)3 << lg) < 2 * (n ? n : 1)) lg++;  // smallest lg with 1.5 * 2^lg >= n
   int c;
   if (shared) {
-    // One bucket set for all windows.  Accumulation time ~ nwin * n mixed additions (it is pipe-bound as
-    // long as there are >= ~2 * 10^5 buckets to give every SM its threads), reduction ~ 2^(c-1) buckets at
-    // ~14 x the cost of a mixed addition each: measured optimum c = lg - 1 (2^16: 15, 2^20: 19).
-    c = lg - 1;
+    // One bucket set for all windows (balanced widths, msm_win_start).  Accumulation costs ~ nwin * n mixed
+    // additions and needs >= ~2 * 10^5 buckets to give every SM its threads; the reduction costs ~ 2^(c-1)
+    // buckets at ~14 x a mixed addition.  Measured optimum (tools/probe_msm.py): c = lg up to 2^18, 19 at 2^20.
+    c = lg <= 18 ? lg : lg - 1;
     if (c < 6) c = 6;
     if (c > 21) c = 21;
   } else {
@@ -650,6 +650,23 @@ int pcdgpu_profile_read(pcdgpu_ctx* ctx, double* ms, double* units, uint64_t* sp
   *launches = ctx->launches;
   ctx->spans_used = 0;
   ctx->launches = 0;
+  return 0;
+}
+
+int pcdgpu_profile_timeline(pcdgpu_ctx* ctx, double* t0_ms, double* t1_ms, int* cls, size_t cap, size_t* count) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, t0_ms && t1_ms && cls && count, "null pointer");
+  PCD_CUDA(ctx, cudaDeviceSynchronize());
+  size_t n = ctx->spans_used < cap ? ctx->spans_used : cap;
+  for (size_t i = 0; i < n; i++) {
+    float a = 0, b = 0;
+    cudaEventElapsedTime(&a, ctx->spans[0].a, ctx->spans[i].a);
+    cudaEventElapsedTime(&b, ctx->spans[0].a, ctx->spans[i].b);
+    t0_ms[i] = a;
+    t1_ms[i] = b;
+    cls[i] = ctx->spans[i].slot;
+  }
+  *count = n;
   return 0;
 }
 

@@ -28,12 +28,22 @@
 #include "vecio.cuh"
 
 static constexpr int MSM_SCALAR_BITS = 298;
-static constexpr int MSM_HEAVY = 1024;      // entries per bucket handled by one thread
+static constexpr int MSM_HEAVY = 1024;      // upper limit of the entries one thread may walk (see heavy_thr)
 static constexpr int MSM_HEAVY_THREADS = 128;
-static constexpr int MSM_MAX_HEAVY = 4096;  // size of the heavy-bucket list
+static constexpr int MSM_MAX_HEAVY = 16384;  // size of the heavy-bucket list
 static constexpr int MSM_HEAVY_CHUNK = 1024;  // entries of a heavy bucket summed by one CTA at a time
 static constexpr int MSM_SUM_PER_CTA = 256;   // points folded by one CTA of msm_sum_kernel (two per thread + tree)
 static constexpr int MSM_REDUCE_LOGL = 3;     // bucket reduction: 2^3 buckets per thread
+
+// Window layout.  Plain MSMs use windows of c bits from bit 0 up.  With precomputed tables all windows
+// share one bucket set, and a short top window (299 mod c real bits) would pile every scalar's top digit
+// into the first few buckets (c = 17 at 2^18: 2^10 buckets receive 2^18 / 2^10 extra entries each, which
+// tripled the accumulation time); there the 299 bits are cut into nwin windows of equal width +- 1.
+__host__ __device__ __forceinline__ int msm_win_start(int j, int c, int nwin, int balanced) {
+  if (!balanced) return j * c;
+  int base = (MSM_SCALAR_BITS + 1) / nwin, rem = (MSM_SCALAR_BITS + 1) % nwin;
+  return j * base + (j < rem ? j : rem);
+}
 
 // ---- 1. digits ------------------------------------------------------------------------------
 // dig[w * n + i] = signed digit of scalar i in window w; counts[bucket]++ for non-zero digits.
@@ -63,11 +73,13 @@ __global__ void msm_digits_kernel(const u32* __restrict__ scalars, int mont, siz
   for (int j = 0; j < 10; j++) w32[j] = k.l[j];
   w32[10] = 0;
   w32[11] = 0;
-  const u32 B = 1u << (c - 1);
-  const u32 mask = (1u << c) - 1;
+  const u32 B = 1u << (c - 1);  // buckets per window (bucket-set pitch)
   u32 carry = 0;
   for (int w = 0; w < nwin; w++) {
-    int bit = w * c;
+    int bit = msm_win_start(w, c, nwin, shared);
+    int cw = (w + 1 < nwin ? msm_win_start(w + 1, c, nwin, shared) : (shared ? MSM_SCALAR_BITS + 1 : bit + c)) - bit;
+    const u32 mask = (1u << cw) - 1;
+    const u32 half = 1u << (cw - 1);
     int limb = bit >> 5, off = bit & 31;
     u32 d = 0;
     if (limb < 10) {
@@ -76,8 +88,8 @@ __global__ void msm_digits_kernel(const u32* __restrict__ scalars, int mont, siz
     }
     d += carry;
     int sd;
-    if (d > B) {
-      sd = (int)d - (int)(1u << c);
+    if (d > half) {
+      sd = (int)d - (int)(1u << cw);
       carry = 1;
     } else {
       sd = (int)d;
@@ -128,7 +140,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
                                                              const u32* __restrict__ entries,
                                                              const u32* __restrict__ perm, size_t nbuckets,
                                                              void* __restrict__ buckets, u32* __restrict__ heavy,
-                                                             u32* __restrict__ queue) {
+                                                             u32* __restrict__ queue, u32 heavy_thr) {
   typedef typename C::F F;
   const unsigned lane = threadIdx.x & 31;
   for (;;) {
@@ -141,7 +153,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
     size_t g = perm[t];
     u32 lo = offsets[g], hi = offsets[g + 1];
     XYZZ<C> acc = XYZZ<C>::inf();
-    if (hi - lo > (u32)MSM_HEAVY) {
+    if (hi - lo > heavy_thr) {
       u32 slot = atomicAdd(&heavy[0], 1u);
       if (slot < (u32)MSM_MAX_HEAVY) {
         heavy[1 + slot] = (u32)g;
@@ -346,7 +358,7 @@ __global__ void __launch_bounds__(128) fixed_mul_kernel(const void* __restrict__
   st_vec(out, i, acc.to_affine());
 }
 
-// pre[j * n + i] = 2^(c j) * bases[i]  (affine), j < nwin
+// pre[j * n + i] = 2^(start_j) * bases[i]  (affine), j < nwin, start_j = msm_win_start(j, c, nwin, balanced)
 template <class C>
 __global__ void __launch_bounds__(128) precompute_kernel(const void* __restrict__ bases, size_t n, int c, int nwin,
                                                          void* __restrict__ pre) {
@@ -357,7 +369,8 @@ __global__ void __launch_bounds__(128) precompute_kernel(const void* __restrict_
   st_vec(pre, i, a);
   XYZZ<C> p = XYZZ<C>::from_affine(a);
   for (int j = 1; j < nwin; j++) {
-    for (int b = 0; b < c; b++) p = p.dbl();
+    int nd = msm_win_start(j, c, nwin, 1) - msm_win_start(j - 1, c, nwin, 1);
+    for (int b = 0; b < nd; b++) p = p.dbl();
     a = p.to_affine();
     st_vec(pre, (size_t)j * n + i, a);
     p = XYZZ<C>::from_affine(a);
@@ -445,10 +458,18 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   int acc_ctas = 0;
   PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C>, 128, 0));
   if (acc_ctas < 1) acc_ctas = 1;
+  // two CTAs (8 warps) per SM already saturate the multiply pipe (tools/probe_modmul.py); the registers left
+  // free let the other lanes' latency-bound kernels (reduction, sorting, assembly) run beside this one
+  if (ctx->concurrent && acc_ctas > 2) acc_ctas = 2;
   size_t acc_grid = (size_t)acc_ctas * ctx->sm_count;
   if (acc_grid > (nbuckets + 127) / 128) acc_grid = (nbuckets + 127) / 128;
+  // One thread walks a bucket only up to 4 x the average size.  Real witnesses repeat values (0, 1, 2, -1,
+  // ...): every copy of a value lands in the same bucket of each window, and a 500-entry bucket walked by
+  // one thread (7 ms) would set the kernel's duration; such buckets go to the CTA-parallel heavy path.
+  size_t avg_entries = total / nbuckets;
+  u32 heavy_thr = (u32)(4 * avg_entries < 64 ? 64 : (4 * avg_entries > (size_t)MSM_HEAVY ? (size_t)MSM_HEAVY : 4 * avg_entries));
   msm_accumulate_kernel<C><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets, bkt,
-                                                             heavy, queue);
+                                                             heavy, queue, heavy_thr);
   PCD_CUDA(ctx, cudaGetLastError());
   size_t heavy_smem = MSM_HEAVY_THREADS * sizeof(XYZZ<C>);
   // heavy-bucket partial list: at most one partial per MSM_HEAVY_CHUNK entries plus one per bucket

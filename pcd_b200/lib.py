@@ -33,7 +33,7 @@ EXPORTS = [
     "pcdgpu_xyzz_sum", "pcdgpu_xyzz_download", "pcdgpu_fixed_base_mul", "pcdgpu_fixed_base_mul_dev",
     "pcdgpu_r1cs_upload", "pcdgpu_r1cs_free", "pcdgpu_r1cs_domain_size", "pcdgpu_witness_map", "pcdgpu_pk_upload",
     "pcdgpu_pk_free", "pcdgpu_groth16_prove", "pcdgpu_groth16_prove_dev", "pcdgpu_serialize_proof",
-    "pcdgpu_profile_enable", "pcdgpu_profile_read", "pcdgpu_bench_imad",
+    "pcdgpu_profile_enable", "pcdgpu_profile_read", "pcdgpu_profile_timeline", "pcdgpu_bench_imad",
 ]
 
 
@@ -97,6 +97,8 @@ def load():
     lib.pcdgpu_profile_enable.argtypes = [vp, ci]
     lib.pcdgpu_profile_read.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                         ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
+    lib.pcdgpu_profile_timeline.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
+                                            ctypes.POINTER(ctypes.c_int), sz, ctypes.POINTER(sz)]
     lib.pcdgpu_bench_imad.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
