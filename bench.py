@@ -352,9 +352,17 @@ def run_gpu(args, rank, local_rank, world):
     imads = prof["units"][dom] * MADD_MODMULS[deg] * MODMUL_IMADS
     achieved = imads / (prof["ms"][dom] * 1e-3) / 1e12 if prof["ms"][dom] > 0 else 0.0
     hbm_peak, hbm_src = load_peaks()
+    traffic = None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r01_traffic.json")) as f:
+            traffic = json.load(f).get(names[dom], {}).get("bytes_per_launch")
+    except Exception:
+        pass
     roofline = {
         "kernel": names[dom], "bound": "imad", "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
-        "frac": achieved / (imad_peak / 1e12), "traffic": None,
+        "frac": achieved / (imad_peak / 1e12), "traffic": traffic,
+        "traffic_note": "DRAM bytes of one launch from the committed ncu capture (2^20 points, uniform scalars); "
+                        "algorithmic: 80 B per gathered point + 4 B per entry",
         "peak_source": "measured live: independent IMAD.WIDE.U32 chains (carry-chain form: %.2f TIMAD/s)" % (imad_chain / 1e12),
         "launch_ms_avg": prof["ms"][dom] / max(prof["spans"][dom], 1),
         "work": "bucket entries x %d Montgomery products (XYZZ mixed add 8M+2S) x %d IMAD" % (MADD_MODMULS[deg], MODMUL_IMADS),
