@@ -1,0 +1,249 @@
+// pcdgpu_snark.hpp -- C++ host mirror of the reference's SNARK interface for the Groth16 proving path,
+// on top of the C ABI (pcdgpu.h).  Header only.
+//
+// The reference binds its SNARKs through ark-snark's traits (re-exported by ark-crypto-primitives):
+//     trait SNARK<F> { type ProvingKey; type VerifyingKey; type Proof; type ProcessedVerifyingKey; type Error;
+//                      fn circuit_specific_setup(circuit, rng) -> Result<(PK, VK), Error>;
+//                      fn prove(pk, circuit, rng) -> Result<Proof, Error>;
+//                      fn verify(vk, x, proof) -> Result<bool, Error>; ... }
+// used at /root/reference/src/ec_cycle_pcd/mod.rs:69,71,78,171,179,239 with
+// MainSNARK = Groth16<MNT4_298>, HelpSNARK = Groth16<MNT6_298> (/root/reference/tests/mnt4_groth16.rs:23-30).
+// The Rust toolchain is absent from the build environment, so this mirror is C++ (the reference is
+// compiled code); INTEGRATION.md holds the Rust shim a maintainer would add.  Names and argument meaning
+// follow ark-groth16 / ark-relations: ProvingKey, VerifyingKey parts, Proof {a, b, c},
+// ConstraintMatrices (rows of (coeff, column); instance variables first, column 0 = constant 1),
+// Groth16::prove draws r then s from the caller's rng (create_random_proof) and calls
+// create_proof_with_reduction.  Setup and verification stay with the CPU implementation on the other side
+// of the boundary and report Error::Unsupported here.
+//
+// Error behaviour: like the Rust `Result`, every operation returns a Result<T>; nothing throws.
+#ifndef PCDGPU_SNARK_HPP
+#define PCDGPU_SNARK_HPP
+
+#include <array>
+#include <cstdint>
+#include <cstring>
+#include <string>
+#include <utility>
+#include <vector>
+
+#include "pcdgpu.h"
+
+namespace pcdgpu {
+
+// ---- Result / Error (ark-relations SynthesisError + backend errors) --------------------------------
+enum class ErrorKind { None, Unsupported, AssignmentMissing, MalformedKey, DomainTooLarge, Backend };
+struct Error {
+  ErrorKind kind = ErrorKind::None;
+  int code = 0;          // PCDGPU_E_* for Backend errors
+  std::string message;
+};
+template <class T>
+struct Result {
+  T value{};
+  Error error;
+  bool is_ok() const { return error.kind == ErrorKind::None; }
+  explicit operator bool() const { return is_ok(); }
+};
+
+// ---- curve cycle configuration (ark-mnt4-298 / ark-mnt6-298) ------------------------------------------
+using Fr = std::array<uint64_t, 5>;  // BigInteger320 limbs; Montgomery form for field elements
+struct MNT4_298 {
+  static constexpr int PAIRING = PCDGPU_MNT4_298;
+  static constexpr size_t G1_LIMBS = 10, G2_LIMBS = 20, PROOF_BYTES = 152;
+};
+struct MNT6_298 {
+  static constexpr int PAIRING = PCDGPU_MNT6_298;
+  static constexpr size_t G1_LIMBS = 10, G2_LIMBS = 30, PROOF_BYTES = 190;
+};
+template <class E> using G1Affine = std::array<uint64_t, E::G1_LIMBS>;  // x || y, infinity = zeros
+template <class E> using G2Affine = std::array<uint64_t, E::G2_LIMBS>;
+
+// ---- ark-relations ------------------------------------------------------------------------------------
+// ConstraintMatrices<F>: a, b, c as rows of (coefficient, column index)
+struct ConstraintMatrices {
+  size_t num_instance_variables = 0;  // includes the constant 1
+  size_t num_witness_variables = 0;
+  size_t num_constraints = 0;
+  std::vector<std::vector<std::pair<Fr, size_t>>> a, b, c;
+};
+// What synthesis (`ConstraintSynthesizer::generate_constraints` + `finalize`) leaves behind: the matrices
+// and the two assignment vectors.  Circuits stay on the CPU; this is the object that crosses the boundary.
+struct SynthesizedCircuit {
+  ConstraintMatrices matrices;
+  std::vector<Fr> instance_assignment;  // instance_assignment[0] = 1
+  std::vector<Fr> witness_assignment;
+};
+
+// ---- ark-groth16 data structures ------------------------------------------------------------------------
+template <class E>
+struct VerifyingKey {
+  G1Affine<E> alpha_g1{};
+  G2Affine<E> beta_g2{}, gamma_g2{}, delta_g2{};
+  std::vector<G1Affine<E>> gamma_abc_g1;
+};
+template <class E>
+struct ProvingKey {
+  VerifyingKey<E> vk;
+  G1Affine<E> beta_g1{}, delta_g1{};
+  std::vector<G1Affine<E>> a_query, b_g1_query, h_query, l_query;
+  std::vector<G2Affine<E>> b_g2_query;
+};
+template <class E>
+struct Proof {
+  G1Affine<E> a{};
+  G2Affine<E> b{};
+  G1Affine<E> c{};
+};
+
+// one GPU context per host thread (the ABI's rule); shared by every Groth16<E> call on that thread
+class Backend {
+ public:
+  static Result<pcdgpu_ctx*> get(int device = 0) {
+    thread_local pcdgpu_ctx* ctx = nullptr;
+    Result<pcdgpu_ctx*> r;
+    if (!ctx) {
+      int rc = pcdgpu_ctx_create(device, &ctx);
+      if (rc != PCDGPU_OK) {
+        r.error = {ErrorKind::Backend, rc, pcdgpu_strerror(rc)};  // no CPU fallback: the error surfaces
+        return r;
+      }
+    }
+    r.value = ctx;
+    return r;
+  }
+};
+
+// ---- Groth16<E>: SNARK + CircuitSpecificSetupSNARK --------------------------------------------------------
+template <class E>
+class Groth16 {
+ public:
+  using ProvingKeyT = ProvingKey<E>;
+  using VerifyingKeyT = VerifyingKey<E>;
+  using ProofT = Proof<E>;
+
+  // Device-resident key + matrices; built once per circuit shape and reused by every prove()
+  // (upstream rebuilds the matrices and re-reads the key on every call).
+  struct Index {
+    pcdgpu_pk* pk = nullptr;
+    pcdgpu_r1cs* r1cs = nullptr;
+    size_t num_vars = 0;
+    ~Index() {
+      if (pk) pcdgpu_pk_free(pk);
+      if (r1cs) pcdgpu_r1cs_free(r1cs);
+    }
+    Index() = default;
+    Index(const Index&) = delete;
+    Index& operator=(const Index&) = delete;
+  };
+
+  // SNARK::circuit_specific_setup / verify: CPU side of the boundary
+  template <class C, class R>
+  static Result<std::pair<ProvingKeyT, VerifyingKeyT>> circuit_specific_setup(const C&, R&) {
+    Result<std::pair<ProvingKeyT, VerifyingKeyT>> r;
+    r.error = {ErrorKind::Unsupported, 0, "Groth16 setup stays with the CPU generator (ark-groth16 generate_random_parameters)"};
+    return r;
+  }
+  static Result<bool> verify(const VerifyingKeyT&, const std::vector<Fr>&, const ProofT&) {
+    Result<bool> r;
+    r.error = {ErrorKind::Unsupported, 0, "verification (one pairing check) stays on the CPU"};
+    return r;
+  }
+
+  static Result<bool> index(const ProvingKeyT& pk, const ConstraintMatrices& m, Index* out, bool precompute = true) {
+    Result<bool> res;
+    auto ctx = Backend::get();
+    if (!ctx) { res.error = ctx.error; return res; }
+    const size_t nv = m.num_instance_variables + m.num_witness_variables;
+    if (pk.a_query.size() != nv || pk.b_g1_query.size() != nv || pk.b_g2_query.size() != nv ||
+        pk.l_query.size() != m.num_witness_variables) {
+      res.error = {ErrorKind::MalformedKey, 0, "query lengths do not match the constraint system"};
+      return res;
+    }
+    std::vector<uint32_t> ptr[3], col[3];
+    std::vector<Fr> val[3];
+    const std::vector<std::vector<std::pair<Fr, size_t>>>* mats[3] = {&m.a, &m.b, &m.c};
+    for (int k = 0; k < 3; k++) {
+      ptr[k].push_back(0);
+      for (const auto& row : *mats[k]) {
+        for (const auto& e : row) {
+          val[k].push_back(e.first);
+          col[k].push_back((uint32_t)e.second);
+        }
+        ptr[k].push_back((uint32_t)col[k].size());
+      }
+      ptr[k].resize(m.num_constraints + 1, (uint32_t)col[k].size());
+    }
+    int rc = pcdgpu_r1cs_upload(ctx.value, E::PAIRING, m.num_constraints, m.num_instance_variables,
+                                m.num_witness_variables, ptr[0].data(), col[0].data(), val[0].data(), ptr[1].data(),
+                                col[1].data(), val[1].data(), ptr[2].data(), col[2].data(), val[2].data(), &out->r1cs);
+    if (rc == PCDGPU_OK)
+      rc = pcdgpu_pk_upload(ctx.value, E::PAIRING, nv, m.num_instance_variables, pk.h_query.size(),
+                            pk.vk.alpha_g1.data(), pk.beta_g1.data(), pk.delta_g1.data(), pk.vk.beta_g2.data(),
+                            pk.vk.delta_g2.data(), pk.a_query.data(), pk.b_g1_query.data(), pk.b_g2_query.data(),
+                            pk.h_query.data(), pk.l_query.data(), precompute ? 1 : 0, &out->pk);
+    if (rc != PCDGPU_OK) {
+      res.error = {ErrorKind::Backend, rc, pcdgpu_last_error(ctx.value)};
+      return res;
+    }
+    out->num_vars = nv;
+    res.value = true;
+    return res;
+  }
+
+  // ark-groth16 create_proof_with_reduction(circuit, pk, r, s); r, s as plain integers (into_repr)
+  static Result<ProofT> create_proof_with_reduction(const Index& idx, const SynthesizedCircuit& circuit, const Fr& r,
+                                                    const Fr& s) {
+    Result<ProofT> res;
+    auto ctx = Backend::get();
+    if (!ctx) { res.error = ctx.error; return res; }
+    std::vector<Fr> z(circuit.instance_assignment);
+    z.insert(z.end(), circuit.witness_assignment.begin(), circuit.witness_assignment.end());
+    if (z.size() != idx.num_vars || z.empty()) {
+      res.error = {ErrorKind::AssignmentMissing, 0, "assignment length does not match the indexed circuit"};
+      return res;
+    }
+    std::vector<uint64_t> out(2 * E::G1_LIMBS + E::G2_LIMBS);
+    int rc = pcdgpu_groth16_prove(ctx.value, idx.pk, idx.r1cs, z.data(), r.data(), s.data(), out.data());
+    if (rc != PCDGPU_OK) {
+      res.error = {rc == PCDGPU_E_DOMAIN ? ErrorKind::DomainTooLarge : ErrorKind::Backend, rc, pcdgpu_last_error(ctx.value)};
+      return res;
+    }
+    std::memcpy(res.value.a.data(), out.data(), 8 * E::G1_LIMBS);
+    std::memcpy(res.value.b.data(), out.data() + E::G1_LIMBS, 8 * E::G2_LIMBS);
+    std::memcpy(res.value.c.data(), out.data() + E::G1_LIMBS + E::G2_LIMBS, 8 * E::G1_LIMBS);
+    return res;
+  }
+
+  // SNARK::prove(pk, circuit, rng): r = Fr::rand(rng), then s = Fr::rand(rng) (create_random_proof's order).
+  // Rng: any type with `Fr next_scalar(int pairing)` returning a uniform scalar as plain-integer limbs.
+  template <class Rng>
+  static Result<ProofT> prove(const Index& idx, const SynthesizedCircuit& circuit, Rng& rng) {
+    Fr r = rng.next_scalar(E::PAIRING);
+    Fr s = rng.next_scalar(E::PAIRING);
+    return create_proof_with_reduction(idx, circuit, r, s);
+  }
+
+  // CanonicalSerialize for Proof<E>: a || b || c compressed
+  static Result<std::vector<uint8_t>> serialize(const ProofT& p) {
+    Result<std::vector<uint8_t>> res;
+    auto ctx = Backend::get();
+    if (!ctx) { res.error = ctx.error; return res; }
+    std::vector<uint64_t> in(2 * E::G1_LIMBS + E::G2_LIMBS);
+    std::memcpy(in.data(), p.a.data(), 8 * E::G1_LIMBS);
+    std::memcpy(in.data() + E::G1_LIMBS, p.b.data(), 8 * E::G2_LIMBS);
+    std::memcpy(in.data() + E::G1_LIMBS + E::G2_LIMBS, p.c.data(), 8 * E::G1_LIMBS);
+    res.value.resize(192);
+    size_t len = 0;
+    int rc = pcdgpu_serialize_proof(ctx.value, E::PAIRING, in.data(), res.value.data(), &len);
+    if (rc != PCDGPU_OK) {
+      res.error = {ErrorKind::Backend, rc, pcdgpu_last_error(ctx.value)};
+      return res;
+    }
+    res.value.resize(len);
+    return res;
+  }
+};
+
+}  // namespace pcdgpu
+#endif  // PCDGPU_SNARK_HPP
