@@ -326,6 +326,9 @@ def run_gpu(args, rank, local_rank, world):
 
     # ---- kernel figures: G1 MSM at 2^20 points and the largest NTT --------------------------------------
     extra = kernel_figures(args, ctx, dev, stream, imad_peak, rank, world)
+    if rank == 0 and not args.no_pcd_step:
+        idx.close()
+        extra["pcd_step"] = pcd_step_figure(args, ctx, dev, stream, log)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample_log = min(log_n, args.cpu_sample_log_n)
@@ -396,6 +399,64 @@ def run_gpu(args, rank, local_rank, world):
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
     print(json.dumps(line), flush=True)
+
+
+def pcd_step_figure(args, ctx, dev, stream, log):
+    """One PCD step as ECCyclePCD::prove issues it (mod.rs:171,179): the main proof on MNT4-298, then --
+    strictly after it, because the helper circuit's witness contains the main proof -- the helper proof on
+    MNT6-298 (G2 over Fq3).  Synthetic circuits of PCD-like size: main domain 2^18, helper
+    2^16; constraint synthesis and the CRH (CPU work above the SNARK seam) are not part of the figure."""
+    import torch
+
+    import pcd_b200
+    from pcd_b200 import synthetic
+    sides = []
+    for pairing, log_n in ((pcd_b200.MNT4_298, args.pcd_main_log_n), (pcd_b200.MNT6_298, args.pcd_help_log_n)):
+        inst = synthetic.make_groth16_instance(ctx, pairing, log_n, seed=77 + pairing)
+        g = pcd_b200.Groth16(ctx, pairing)
+        idx = g.index(pcd_b200.ProvingKey(pairing=pairing, **inst["pk"]),
+                      pcd_b200.ConstraintMatrices(pairing, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"],
+                                                  inst["C"]), precompute=True)
+        z = torch.from_numpy(inst["z"].view(np.int64)).to(dev)
+        p = inst["p"]
+        r_i, s_i = 0x1234567 * 3 ** 70 % p, 0x7654321 * 5 ** 60 % p
+        lim = lambda v: np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(5)], dtype=np.uint64)
+        proof = g.create_proof_dev(idx, z.data_ptr(), lim(r_i), lim(s_i))
+        if not np.array_equal(proof.affine_limbs(), synthetic.expected_proof(ctx, inst, r_i, s_i)):
+            raise SystemExit("bench: PCD-step proof (pairing %d) does not match its discrete logarithms" % pairing)
+        sides.append((g, idx, z, lim(r_i), lim(s_i)))
+    if log:
+        log("PCD step: main 2^%d (MNT4-298) and helper 2^%d (MNT6-298) proofs verified" % (args.pcd_main_log_n,
+                                                                                        args.pcd_help_log_n))
+
+    def step():
+        for g, idx, z, r, s in sides:  # helper strictly after main
+            g.create_proof_dev(idx, z.data_ptr(), r, s)
+
+    for _ in range(3):
+        step()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    e0.record(stream)
+    reps = 5
+    per = []
+    for _ in range(reps):
+        step()
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    for g, idx, z, r, s in sides:
+        a, b = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        a.record(stream)
+        g.create_proof_dev(idx, z.data_ptr(), r, s)
+        b.record(stream)
+        torch.cuda.synchronize()
+        per.append(a.elapsed_time(b))
+        idx.close()
+    return {"steps_per_s": 1e3 / ms, "ms_per_step": ms, "main": {"pairing": "MNT4-298", "domain": "2^%d" % args.pcd_main_log_n,
+            "ms": per[0]}, "helper": {"pairing": "MNT6-298", "domain": "2^%d" % args.pcd_help_log_n, "ms": per[1]},
+            "note": "prover kernels only (witness map + 4 G1 MSM + 1 G2 MSM + assembly per proof); main then helper, "
+                    "sequential as in ECCyclePCD::prove"}
 
 
 def kernel_figures(args, ctx, dev, stream, imad_peak, rank=0, world=1):
@@ -492,6 +553,9 @@ def main():
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("PCD_BENCH_INFLIGHT", "2")),
                     help="independent proofs issued concurrently per GPU (each on its own context)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-pcd-step", action="store_true")
+    ap.add_argument("--pcd-main-log-n", type=int, default=18)
+    ap.add_argument("--pcd-help-log-n", type=int, default=16)
     ap.add_argument("--no-concurrency", action="store_true", help="run the five MSMs of a proof on one stream")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3) if args.impl == "b200" else args.warmup

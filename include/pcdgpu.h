@@ -83,6 +83,12 @@ int pcdgpu_set_msm_window(pcdgpu_ctx* ctx, int c);
  * transformed in place.  log_n <= 34 (r4) / 17 (q4), else PCDGPU_E_DOMAIN. */
 int pcdgpu_ntt(pcdgpu_ctx* ctx, int field, void* data, uint32_t log_n, int inverse, int coset);
 int pcdgpu_ntt_dev(pcdgpu_ctx* ctx, int field, void* d_data, uint32_t log_n, int inverse, int coset);
+/* ark-poly GeneralEvaluationDomain::new(min_size): radix-2 when log2 fits the field's 2-adicity, otherwise
+ * (q4 only: its multiplicative group has a subgroup of order 7^2) the smallest 7^a 2^b >= min_size
+ * (MixedRadixEvaluationDomain).  Returns the size (0: none) and its exponents. */
+size_t pcdgpu_domain_size(int field, size_t min_size, int* pow7, int* pow2);
+/* the four transforms on the domain 7^pow7 * 2^pow2 (pow7 = 0: same as pcdgpu_ntt) */
+int pcdgpu_ntt_general(pcdgpu_ctx* ctx, int field, void* data, int pow7, int pow2, int inverse, int coset);
 
 /* ---- variable-base MSM ----------------------------------------------------------------------
  * Replaces ark-ec VariableBaseMSM::multi_scalar_mul(bases, scalars): sum_i scalars[i] * bases[i]
@@ -125,7 +131,7 @@ int pcdgpu_r1cs_upload(pcdgpu_ctx* ctx, int pairing, size_t num_constraints, siz
                        const uint32_t* b_col, const void* b_val, const uint32_t* c_ptr, const uint32_t* c_col,
                        const void* c_val, pcdgpu_r1cs** out);
 void pcdgpu_r1cs_free(pcdgpu_r1cs* r);
-/* domain size n = next_pow2(num_constraints + num_inputs) of an uploaded system */
+/* domain size n = |GeneralEvaluationDomain::new(num_constraints + num_inputs)| of an uploaded system */
 size_t pcdgpu_r1cs_domain_size(const pcdgpu_r1cs* r);
 /* z: num_inputs + num_witness elements (instance || witness, z[0] = 1); h: n elements */
 int pcdgpu_witness_map(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* z, void* h);

@@ -539,6 +539,129 @@ static void domain_transform(Fp<P>* a, int log_n, int inverse, int coset, int th
 }
 
 // ------------------------------------------------------------------------------------------
+// GeneralEvaluationDomain: radix-2 when the size's log fits the field's 2-adicity,
+// otherwise -- on q4, whose multiplicative group also has a subgroup of order 7^2 -- the smallest
+// 7^a 2^b >= m (ark-poly MixedRadixEvaluationDomain).  The group generator of a mixed domain is
+// LARGE_SUBGROUP_ROOT^((2^s 7^2) / n), LARGE_SUBGROUP_ROOT = GENERATOR^((p-1) / (2^s 7^2)), whose 49th
+// power is TWO_ADIC_ROOT.  Any correct DFT with that generator gives the same (canonical) values; this
+// one is Cooley-Tukey: split off factors of 7 (naive 7-point DFTs + twiddles), radix-2 below.
+// ------------------------------------------------------------------------------------------
+struct DomainShape {
+  size_t n;
+  int a;  // power of 7
+  int b;  // power of 2
+};
+
+template <class P>
+static bool domain_shape(size_t min_size, DomainShape* out) {
+  const FieldConsts& c = P::C();
+  int lg = 0;
+  while (((size_t)1 << lg) < (min_size ? min_size : 1)) lg++;
+  if (lg <= c.two_adicity) {
+    *out = {(size_t)1 << lg, 0, lg};
+    return true;
+  }
+  if (c.two_adicity != 17) return false;  // only q4 has the small subgroup (7, adicity 2)
+  bool found = false;
+  for (int a = 0; a <= 2; a++)
+    for (int b = 0; b <= c.two_adicity; b++) {
+      size_t s = (a == 0 ? 1 : (a == 1 ? 7 : 49)) * ((size_t)1 << b);
+      if (s >= min_size && (!found || s < out->n)) {
+        *out = {s, a, b};
+        found = true;
+      }
+    }
+  return found;
+}
+
+template <class P>
+static Fp<P> omega_general(const DomainShape& d) {
+  if (d.a == 0) return omega_for<P>(d.b);
+  const FieldConsts& c = P::C();
+  // e = (p - 1) / (2^s * 49): exact division, done limb-wise
+  u64 e[5];
+  memcpy(e, c.mod, 40);
+  e[0] -= 1;
+  int s = c.two_adicity;
+  u64 sh[5];
+  for (int i = 0; i < 5; i++) {
+    u64 v = e[i] >> s;
+    if (i + 1 < 5) v |= e[i + 1] << (64 - s);
+    sh[i] = v;
+  }
+  u64 q[5];
+  u128 rem = 0;
+  for (int i = 4; i >= 0; i--) {
+    u128 cur = (rem << 64) | sh[i];
+    q[i] = (u64)(cur / 49);
+    rem = cur % 49;
+  }
+  Fp<P> w = Fp<P>::generator().pow(q, 5);  // LARGE_SUBGROUP_ROOT, order 2^s * 49
+  u64 k = (((u64)1 << s) * 49) / (u64)d.n;
+  return w.pow_u64(k);
+}
+
+// out-of-place mixed-radix DFT of x (length n = 7^a 2^b) with generator w; x is overwritten
+template <class P>
+static void mixed_fft(std::vector<Fp<P>>& x, int a, int b, const Fp<P>& w, int threads) {
+  typedef Fp<P> F;
+  size_t n = x.size();
+  if (a == 0) {
+    if (b > 0) fft_in_place(x.data(), b, w, threads);
+    return;
+  }
+  size_t M = n / 7;
+  F w7 = w.pow_u64((u64)M);  // primitive 7th root
+  F w7p[7];
+  w7p[0] = F::one();
+  for (int i = 1; i < 7; i++) w7p[i] = w7p[i - 1] * w7;
+  std::vector<std::vector<F>> y(7, std::vector<F>(M));
+  parallel_for(M, threads, [&](size_t lo, size_t hi, int) {
+    F tw = w.pow_u64((u64)lo);  // w^{n2}
+    for (size_t n2 = lo; n2 < hi; n2++) {
+      F twk = F::one();  // w^{n2 k1}
+      for (int k1 = 0; k1 < 7; k1++) {
+        F acc = F::zero();
+        for (int n1 = 0; n1 < 7; n1++) acc = acc + x[M * n1 + n2] * w7p[(n1 * k1) % 7];
+        y[k1][n2] = acc * twk;
+        twk = twk * tw;
+      }
+      tw = tw * w;
+    }
+  });
+  F wsub = w.pow_u64(7);
+  for (int k1 = 0; k1 < 7; k1++) mixed_fft<P>(y[k1], a - 1, b, wsub, threads);
+  for (int k1 = 0; k1 < 7; k1++)
+    for (size_t k2 = 0; k2 < M; k2++) x[k1 + 7 * k2] = y[k1][k2];
+}
+
+template <class P>
+static void domain_transform_general(Fp<P>* v, const DomainShape& d, int inverse, int coset, int threads) {
+  typedef Fp<P> F;
+  if (d.a == 0) {
+    domain_transform<P>(v, d.b, inverse, coset, threads);
+    return;
+  }
+  size_t n = d.n;
+  F omega = omega_general<P>(d);
+  F g = F::generator();
+  std::vector<F> x(v, v + n);
+  if (!inverse) {
+    if (coset) {
+      F pw = F::one();
+      for (size_t i = 0; i < n; i++) { x[i] = x[i] * pw; pw = pw * g; }
+    }
+    mixed_fft<P>(x, d.a, d.b, omega, threads);
+  } else {
+    mixed_fft<P>(x, d.a, d.b, omega.inverse(), threads);
+    F pw = F::from_u64((u64)n).inverse();
+    F gi = coset ? g.inverse() : F::one();
+    for (size_t i = 0; i < n; i++) { x[i] = x[i] * pw; pw = pw * gi; }
+  }
+  memcpy((void*)v, (const void*)x.data(), n * sizeof(F));
+}
+
+// ------------------------------------------------------------------------------------------
 // R1CS in CSR form and the QAP witness map
 // ------------------------------------------------------------------------------------------
 struct Csr {
@@ -565,11 +688,9 @@ template <class P>
 static int witness_map(const Csr& A, const Csr& B, const Csr& Cm, size_t m, size_t num_inputs, const Fp<P>* z,
                        Fp<P>* h, int threads) {
   typedef Fp<P> F;
-  size_t need = m + num_inputs;
-  int log_n = 0;
-  while (((size_t)1 << log_n) < need) log_n++;
-  if (log_n > P::C().two_adicity) return -1;
-  size_t n = (size_t)1 << log_n;
+  DomainShape dom;
+  if (!domain_shape<P>(m + num_inputs, &dom)) return -1;
+  size_t n = dom.n;
   std::vector<F> a(n, F::zero()), b(n, F::zero()), c(n, F::zero());
   parallel_for(m, threads, [&](size_t lo, size_t hi, int) {
     for (size_t i = lo; i < hi; i++) {
@@ -579,20 +700,20 @@ static int witness_map(const Csr& A, const Csr& B, const Csr& Cm, size_t m, size
     }
   });
   for (size_t j = 0; j < num_inputs; j++) a[m + j] = z[j];
-  domain_transform<P>(a.data(), log_n, 1, 0, threads);
-  domain_transform<P>(a.data(), log_n, 0, 1, threads);
-  domain_transform<P>(b.data(), log_n, 1, 0, threads);
-  domain_transform<P>(b.data(), log_n, 0, 1, threads);
-  domain_transform<P>(c.data(), log_n, 1, 0, threads);
-  domain_transform<P>(c.data(), log_n, 0, 1, threads);
+  domain_transform_general<P>(a.data(), dom, 1, 0, threads);
+  domain_transform_general<P>(a.data(), dom, 0, 1, threads);
+  domain_transform_general<P>(b.data(), dom, 1, 0, threads);
+  domain_transform_general<P>(b.data(), dom, 0, 1, threads);
+  domain_transform_general<P>(c.data(), dom, 1, 0, threads);
+  domain_transform_general<P>(c.data(), dom, 0, 1, threads);
   // (g^n - 1)^-1
   F gn = F::generator().pow_u64((u64)n);
   F zinv = (gn - F::one()).inverse();
   parallel_for(n, threads, [&](size_t lo, size_t hi, int) {
     for (size_t i = lo; i < hi; i++) h[i] = (a[i] * b[i] - c[i]) * zinv;
   });
-  domain_transform<P>(h, log_n, 1, 1, threads);
-  return log_n;
+  domain_transform_general<P>(h, dom, 1, 1, threads);
+  return (int)n;
 }
 
 // ------------------------------------------------------------------------------------------
@@ -613,10 +734,9 @@ static int groth16_prove(const Groth16PkView& pk, const Csr& A, const Csr& B, co
                          void* out, int threads) {
   typedef Fp<P> F;
   size_t nv = num_inputs + num_witness;
-  size_t need = m + num_inputs;
-  int log_n = 0;
-  while (((size_t)1 << log_n) < need) log_n++;
-  size_t n = (size_t)1 << log_n;
+  DomainShape dom;
+  if (!domain_shape<P>(m + num_inputs, &dom)) return -1;
+  size_t n = dom.n;
   std::vector<F> h(n);
   if (witness_map<P>(A, B, Cm, m, num_inputs, z, h.data(), threads) < 0) return -1;
   // scalars leave Montgomery form (into_repr)
@@ -760,6 +880,21 @@ void orc_field_op(int field, int op, const void* a, const void* b, void* out) {
 void orc_ntt(int field, void* data, int log_n, int inverse, int coset, int threads) {
   if (field == 0) domain_transform<PR4>((FpR4*)data, log_n, inverse, coset, threads);
   else domain_transform<PQ4>((FpQ4*)data, log_n, inverse, coset, threads);
+}
+// GeneralEvaluationDomain::new(min_size): size chosen (0 if none), with its 7-adic and 2-adic exponents
+size_t orc_domain_size(int field, size_t min_size, int* a, int* b) {
+  DomainShape d;
+  bool ok = field == 0 ? domain_shape<PR4>(min_size, &d) : domain_shape<PQ4>(min_size, &d);
+  if (!ok) return 0;
+  *a = d.a;
+  *b = d.b;
+  return d.n;
+}
+// transform on an explicit domain 7^a 2^b (a > 0 only on q4)
+void orc_ntt_general(int field, void* data, int a, int b, int inverse, int coset, int threads) {
+  DomainShape d{(size_t)(a == 0 ? 1 : (a == 1 ? 7 : 49)) << b, a, b};
+  if (field == 0) domain_transform_general<PR4>((FpR4*)data, d, inverse, coset, threads);
+  else domain_transform_general<PQ4>((FpQ4*)data, d, inverse, coset, threads);
 }
 // curve: 0 = MNT4 G1, 1 = MNT4 G2, 2 = MNT6 G1, 3 = MNT6 G2.  c = 0 -> arkworks window rule
 void orc_msm(int curve, const void* bases, const void* scalars, size_t n, void* out_affine, int threads, int c) {

@@ -72,6 +72,21 @@ def ntt(field: int, data: np.ndarray, inverse: bool, coset: bool, threads: int =
     return d
 
 
+def domain_size(field: int, min_size: int):
+    """GeneralEvaluationDomain::new(min_size) -> (n, a, b) with n = 7^a 2^b, or None."""
+    a, b = ctypes.c_int(), ctypes.c_int()
+    lib().orc_domain_size.restype = ctypes.c_size_t
+    n = lib().orc_domain_size(field, ctypes.c_size_t(min_size), ctypes.byref(a), ctypes.byref(b))
+    return (n, a.value, b.value) if n else None
+
+
+def ntt_general(field: int, data: np.ndarray, a: int, b: int, inverse: bool, coset: bool, threads: int = 1) -> np.ndarray:
+    d = np.array(data, dtype=np.uint64, copy=True).reshape(-1, 5)
+    assert d.shape[0] == (7 ** a) << b
+    lib().orc_ntt_general(field, _p(d), a, b, int(inverse), int(coset), threads)
+    return d
+
+
 def msm(curve: int, bases: np.ndarray, scalars: np.ndarray, threads: int = 1, c: int = 0) -> np.ndarray:
     bases = np.ascontiguousarray(bases, dtype=np.uint64).reshape(-1, POINT_LIMBS[curve])
     scalars = np.ascontiguousarray(scalars, dtype=np.uint64).reshape(-1, 5)
@@ -132,9 +147,10 @@ def witness_map(pairing: int, A, B, C, m: int, num_inputs: int, z: np.ndarray, t
         keep.append(k)
         args += a
     z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
-    n = 1
-    while n < m + num_inputs:
-        n <<= 1
+    dom = domain_size(pairing, m + num_inputs)
+    if dom is None:
+        raise ValueError("domain too large for the field")
+    n = dom[0]
     h = np.zeros((n, 5), dtype=np.uint64)
     rc = lib().orc_witness_map(pairing, *args, ctypes.c_size_t(m), ctypes.c_size_t(num_inputs), _p(z), _p(h), threads)
     if rc < 0:

@@ -685,6 +685,17 @@ def domain_new(fp: PrimeFieldParams, min_size: int) -> Domain:
     return Domain(fp, s, None, omega, "mixed")
 
 
+def domain_mixed(fp: PrimeFieldParams, a: int, b: int) -> Domain:
+    """The mixed-radix domain of size q^a 2^b explicitly (tests: small sizes that domain_new would
+    serve with radix 2)."""
+    q = fp.small_subgroup_base
+    assert q is not None and 0 <= a <= fp.small_subgroup_adicity and 0 <= b <= fp.two_adicity
+    s = (q ** a) << b
+    full = (q ** fp.small_subgroup_adicity) << fp.two_adicity
+    large_root = pow(fp.generator, (fp.p - 1) // full, fp.p)
+    return Domain(fp, s, None if a else b, pow(large_root, full // s, fp.p), "mixed" if a else "radix2")
+
+
 def dft_naive(vals: Sequence[int], omega: int, p: int) -> List[int]:
     """out[i] = sum_j in[j] * omega^(i*j): the definition every NTT is checked against."""
     n = len(vals)

@@ -161,6 +161,36 @@ int pcdgpu_ntt_dev(pcdgpu_ctx* ctx, int field, void* d_data, uint32_t log_n, int
   return ntt_run(ctx, field, d_data, (int)log_n, inverse != 0, coset != 0);
 }
 
+size_t pcdgpu_domain_size(int field, size_t min_size, int* pow7, int* pow2) {
+  size_t n;
+  int a, b;
+  if ((field != PCDGPU_FIELD_R4 && field != PCDGPU_FIELD_Q4) || ntt_domain_shape(field, min_size, &n, &a, &b) != 0) return 0;
+  if (pow7) *pow7 = a;
+  if (pow2) *pow2 = b;
+  return n;
+}
+
+int pcdgpu_ntt_general(pcdgpu_ctx* ctx, int field, void* data, int pow7, int pow2, int inverse, int coset) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, data, "null data pointer");
+  CHECK_ARG(ctx, field == PCDGPU_FIELD_R4 || field == PCDGPU_FIELD_Q4, "unknown field id");
+  CHECK_ARG(ctx, pow7 >= 0 && pow7 <= 2 && pow2 >= 0 && pow2 < 40, "domain exponents out of range");
+  if (pow7 == 0) return pcdgpu_ntt(ctx, field, data, (uint32_t)pow2, inverse, coset);
+  if (field != PCDGPU_FIELD_Q4 || pow2 > 17) {
+    ctx->set_error("no evaluation domain of size 7^%d 2^%d on this field", pow7, pow2);
+    return PCDGPU_E_DOMAIN;
+  }
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t bytes = ((size_t)(pow7 == 1 ? 7 : 49) << pow2) * 40;
+  void* d;
+  PCD_TRY(ctx->scratch(SLOT_IO, bytes, &d));
+  PCD_CUDA(ctx, cudaMemcpyAsync(d, data, bytes, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(ntt_run_general(ctx, field, d, pow7, pow2, inverse != 0, coset != 0));
+  PCD_CUDA(ctx, cudaMemcpyAsync(data, d, bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int pcdgpu_ntt(pcdgpu_ctx* ctx, int field, void* data, uint32_t log_n, int inverse, int coset) {
   if (!ctx) return PCDGPU_E_ARG;
   CHECK_ARG(ctx, data, "null data pointer");
@@ -408,8 +438,14 @@ int pcdgpu_r1cs_upload(pcdgpu_ctx* ctx, int pairing, size_t m, size_t num_inputs
   r->m = m;
   r->num_inputs = num_inputs;
   r->num_witness = num_witness;
-  r->log_n = ilog2_ceil(m + num_inputs);
-  r->n = (size_t)1 << r->log_n;
+  {
+    int field = pairing == PCDGPU_MNT4_298 ? PCDGPU_FIELD_R4 : PCDGPU_FIELD_Q4;
+    if (ntt_domain_shape(field, m + num_inputs, &r->n, &r->dom_a, &r->dom_b) != 0) {
+      r->dom_a = -1;  // no domain: the witness map reports PCDGPU_E_DOMAIN (the host still needs a size for h)
+      r->dom_b = ilog2_ceil(m + num_inputs);
+      r->n = (size_t)1 << r->dom_b;
+    }
+  }
   cudaError_t e = cudaMalloc(&r->storage, total ? total : 16);
   if (e != cudaSuccess) {
     ctx->set_error("cudaMalloc(%zu) for R1CS matrices: %s", total, cudaGetErrorString(e));

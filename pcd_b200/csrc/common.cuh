@@ -67,7 +67,7 @@ struct pcdgpu_ctx {
   // scratch and their latency-bound phases (bucket reduction, window combination) overlap the
   // other lanes' accumulation.  Lane 0 is the context's (or the caller's) stream.
   static const int NLANE = 5;
-  static const int SLOTS_PER_LANE = 16;
+  static const int SLOTS_PER_LANE = 24;
   int lane = 0;
   bool concurrent = true;
   cudaStream_t lane_stream[NLANE] = {nullptr};
@@ -152,7 +152,8 @@ enum {
   SLOT_MISC = 12,
   SLOT_CUB = 13,
   SLOT_MSM_HP = 14,  // heavy-bucket partial sums
-  SLOT_CUB2 = 15
+  SLOT_CUB2 = 15,
+  SLOT_NTT_MIXED = 16  // ping-pong buffer of a mixed-radix transform
 };
 
 template <class T>

@@ -70,9 +70,8 @@ template <class F>
 static int witness_map_t(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h) {
   int field = r->pairing == PCDGPU_MNT4_298 ? PCDGPU_FIELD_R4 : PCDGPU_FIELD_Q4;
   size_t n = r->n;
-  int log_n = r->log_n;
-  if (log_n > F::Params::TWO_ADICITY) {
-    ctx->set_error("witness map needs a 2^%d domain; the field's 2-adicity is %d", log_n, F::Params::TWO_ADICITY);
+  if (r->dom_a < 0) {
+    ctx->set_error("witness map needs a domain of %zu elements; the field has none that large", r->m + r->num_inputs);
     return PCDGPU_E_DOMAIN;
   }
   void *a, *b, *c;
@@ -88,15 +87,15 @@ static int witness_map_t(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z,
   ctx->prof_end(ps);
   void* v[3] = {a, b, c};
   for (int i = 0; i < 3; i++) {
-    PCD_TRY(ntt_run(ctx, field, v[i], log_n, 1, 0));
-    PCD_TRY(ntt_run(ctx, field, v[i], log_n, 0, 1));
+    PCD_TRY(ntt_run_general(ctx, field, v[i], r->dom_a, r->dom_b, 1, 0));
+    PCD_TRY(ntt_run_general(ctx, field, v[i], r->dom_a, r->dom_b, 0, 1));
   }
-  NttTablesDev t;
-  PCD_TRY(ntt_tables(ctx, field, log_n, &t));
+  const u32* zinv;
+  PCD_TRY(ntt_zinv_general(ctx, field, n, &zinv));
   qap_combine_kernel<F><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((u32*)a, (const u32*)b, (const u32*)c,
-                                                                              t.zinv, n);
+                                                                              zinv, n);
   PCD_CUDA(ctx, cudaGetLastError());
-  PCD_TRY(ntt_run(ctx, field, a, log_n, 1, 1));
+  PCD_TRY(ntt_run_general(ctx, field, a, r->dom_a, r->dom_b, 1, 1));
   *d_h = a;
   return 0;
 }

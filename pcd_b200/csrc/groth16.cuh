@@ -13,8 +13,8 @@ struct CsrDev {
 struct pcdgpu_r1cs {
   pcdgpu_ctx* ctx;
   int pairing;
-  size_t m, num_inputs, num_witness, n;
-  int log_n;
+  size_t m, num_inputs, num_witness, n;  // n = domain size = 7^dom_a 2^dom_b (GeneralEvaluationDomain::new)
+  int dom_a, dom_b;
   CsrDev A, B, C;
   void* storage;  // one allocation holding all nine arrays
 };

@@ -28,7 +28,7 @@ TWO_ADICITY = {FIELD_R4: 34, FIELD_Q4: 17}
 
 EXPORTS = [
     "pcdgpu_strerror", "pcdgpu_last_error", "pcdgpu_affine_bytes", "pcdgpu_ctx_create", "pcdgpu_ctx_destroy",
-    "pcdgpu_sync", "pcdgpu_set_stream", "pcdgpu_set_concurrency", "pcdgpu_set_msm_window", "pcdgpu_ntt", "pcdgpu_ntt_dev", "pcdgpu_msm",
+    "pcdgpu_sync", "pcdgpu_set_stream", "pcdgpu_set_concurrency", "pcdgpu_set_msm_window", "pcdgpu_ntt", "pcdgpu_ntt_dev", "pcdgpu_domain_size", "pcdgpu_ntt_general", "pcdgpu_msm",
     "pcdgpu_msm_dev", "pcdgpu_bases_upload", "pcdgpu_bases_free", "pcdgpu_msm_bases", "pcdgpu_msm_bases_dev",
     "pcdgpu_xyzz_sum", "pcdgpu_xyzz_download", "pcdgpu_fixed_base_mul", "pcdgpu_fixed_base_mul_dev",
     "pcdgpu_r1cs_upload", "pcdgpu_r1cs_free", "pcdgpu_r1cs_domain_size", "pcdgpu_witness_map", "pcdgpu_pk_upload",
@@ -71,6 +71,9 @@ def load():
     lib.pcdgpu_set_concurrency.argtypes = [vp, ci]
     lib.pcdgpu_ntt.argtypes = [vp, ci, vp, ctypes.c_uint32, ci, ci]
     lib.pcdgpu_ntt_dev.argtypes = [vp, ci, vp, ctypes.c_uint32, ci, ci]
+    lib.pcdgpu_domain_size.restype = sz
+    lib.pcdgpu_domain_size.argtypes = [ci, sz, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.pcdgpu_ntt_general.argtypes = [vp, ci, vp, ci, ci, ci, ci]
     lib.pcdgpu_msm.argtypes = [vp, ci, vp, vp, sz, vp]
     lib.pcdgpu_msm_dev.argtypes = [vp, ci, vp, vp, ci, sz, vp]
     lib.pcdgpu_bases_upload.argtypes = [vp, ci, vp, sz, ci, ctypes.POINTER(vp)]
@@ -102,6 +105,13 @@ def load():
     lib.pcdgpu_bench_imad.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
     _lib = lib
     return lib
+
+
+def domain_size(field: int, min_size: int):
+    """GeneralEvaluationDomain::new(min_size) -> (n, pow7, pow2) or None"""
+    a, b = ctypes.c_int(), ctypes.c_int()
+    n = load().pcdgpu_domain_size(field, min_size, ctypes.byref(a), ctypes.byref(b))
+    return (n, a.value, b.value) if n else None
 
 
 def _u64(a, width=None):
@@ -163,6 +173,15 @@ class Context:
         if n == 0 or (1 << log_n) != n:
             raise ValueError("NTT length must be a power of two")
         self._check(self.lib.pcdgpu_ntt(self.h, field, _p(d), log_n, int(inverse), int(coset)))
+        return d
+
+    def ntt_general(self, field: int, data: np.ndarray, pow7: int, pow2: int, inverse: bool = False,
+                    coset: bool = False) -> np.ndarray:
+        """transform on the domain 7^pow7 * 2^pow2 (ark-poly GeneralEvaluationDomain)"""
+        d = np.array(data, dtype=np.uint64, copy=True).reshape(-1, 5)
+        if d.shape[0] != (7 ** pow7) << pow2:
+            raise ValueError("data length does not match the domain")
+        self._check(self.lib.pcdgpu_ntt_general(self.h, field, _p(d), pow7, pow2, int(inverse), int(coset)))
         return d
 
     def ntt_dev(self, field: int, d_ptr: int, log_n: int, inverse: bool = False, coset: bool = False):

@@ -83,14 +83,16 @@ def _limbs_from_ints(vals) -> np.ndarray:
     return np.frombuffer(b, dtype="<u8").copy().reshape(-1, 5)
 
 
-def _omega(field: int, log_n: int) -> int:
+def _omega(field: int, n: int) -> int:
+    """generator of the evaluation domain of size n = 7^a 2^b: GENERATOR^((p-1)/n)"""
     p = FIELD_P[field]
-    gen, s = (10, 34) if field == L.FIELD_R4 else (17, 17)
-    return pow(pow(gen, (p - 1) >> s, p), 1 << (s - log_n), p)
+    gen = 10 if field == L.FIELD_R4 else 17
+    assert (p - 1) % n == 0
+    return pow(gen, (p - 1) // n, p)
 
 
 def make_groth16_instance(ctx: L.Context, pairing: int, log_n: int, seed: int = 20261017, bitlike: float = 0.4,
-                          verbose=None):
+                          verbose=None, num_constraints: int = None):
     """Satisfiable synthetic R1CS with 2^log_n - 2 constraints and 2 instance variables (domain size
     exactly 2^log_n), its assignment, and a Groth16 proving key with a KNOWN trapdoor.
 
@@ -104,9 +106,16 @@ def make_groth16_instance(ctx: L.Context, pairing: int, log_n: int, seed: int = 
     t0 = time.time()
     field = L.SCALAR_FIELD_OF[pairing]
     p = FIELD_P[field]
-    n = 1 << log_n
-    m = n - 2
     ni = 2
+    if num_constraints is None:
+        n = 1 << log_n
+        m = n - 2
+    else:  # any size: the domain is GeneralEvaluationDomain::new(m + ni), possibly mixed radix on q4
+        m = num_constraints
+        dom = L.domain_size(field, m + ni)
+        if dom is None:
+            raise ValueError("no evaluation domain for %d constraints on this field" % m)
+        n = dom[0]
     rnd = random.Random(seed)
     z = [1, rnd.randrange(p)]
     rows_a, rows_b, rows_c = [], [], []
@@ -149,7 +158,7 @@ def make_groth16_instance(ctx: L.Context, pairing: int, log_n: int, seed: int = 
     z_mont = _limbs_from_ints([v * R % p for v in z])
     # ---- trapdoor scalars -------------------------------------------------------------------------
     alpha, beta, delta, tau = (rnd.randrange(1, p) for _ in range(4))
-    omega = _omega(field, log_n)
+    omega = _omega(field, n)
     zt = (pow(tau, n, p) - 1) % p
     ninv = pow(n, -1, p)
     ws, dens = [1] * n, [0] * n

@@ -47,3 +47,17 @@ def test_product_never_imports_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h", ".cpp")):
                 text = open(os.path.join(dirpath, f)).read()
                 assert "c_oracle" not in text and "pcd_oracle" not in text and "liboracle" not in text, f
+
+
+def test_domain_size_rule_matches_oracle():
+    """GeneralEvaluationDomain::new: host-only entry point, no GPU needed"""
+    import pcd_b200.lib as L
+    if not os.path.exists(L.LIB_PATH):
+        pytest.skip("libpcdgpu.so not built yet")
+    import sys
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import c_oracle as co
+    for field in (0, 1):
+        for m in (1, 2, 3, 1000, 1 << 16, (1 << 17) - 1, 1 << 17, (1 << 17) + 1, 200704, 200705, 7 << 17, (7 << 17) + 1,
+                  49 << 17, (49 << 17) + 1, 1 << 20, (1 << 34) + 1):
+            assert L.domain_size(field, m) == co.domain_size(field, m), (field, m)

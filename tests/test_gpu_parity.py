@@ -225,9 +225,10 @@ def test_groth16_vs_oracle_and_trapdoor(ctx, pairing, m):
 
 
 def test_groth16_domain_limit(ctx):
-    # helper-side field q4 has 2-adicity 17: a 2^18 domain must be refused, not mis-computed
+    # helper-side field q4: radix 2 up to 2^17, mixed radix up to 49 * 2^17; anything larger must be refused,
+    # not mis-computed
     import pcd_b200
-    m = (1 << 17) + 1
+    m = (49 << 17) + 1
     ptr = np.zeros(m + 1, dtype=np.uint32)
     empty = (ptr, np.zeros(0, np.uint32), np.zeros((0, 5), np.uint64))
     cm = pcd_b200.ConstraintMatrices(1, 1, 0, empty, empty, empty)
@@ -238,7 +239,50 @@ def test_groth16_domain_limit(ctx):
         args += [p_.ctypes.data, c_.ctypes.data, v_.ctypes.data]
     ctx._check(ctx.lib.pcdgpu_r1cs_upload(ctx.h, 1, m, 1, 0, *args, ctypes.byref(h)))
     z = np.zeros((1, 5), dtype=np.uint64)
-    out = np.zeros((1 << 18, 5), dtype=np.uint64)
+    out = np.zeros((ctx.lib.pcdgpu_r1cs_domain_size(h), 5), dtype=np.uint64)
     rc = ctx.lib.pcdgpu_witness_map(ctx.h, h, z.ctypes.data, out.ctypes.data)
     assert rc == -4
     ctx.lib.pcdgpu_r1cs_free(h)
+
+
+# ---- mixed-radix domains (q4 = MNT6-298 Fr beyond 2^17) ------------------------------------------------
+@pytest.mark.parametrize("a,b", [(1, 0), (2, 0), (1, 3), (2, 2), (1, 10), (2, 9), (1, 13), (2, 12)])
+def test_ntt_mixed_radix_vs_oracle(ctx, a, b):
+    n = (7 ** a) << b
+    x = codec.random_field_elems(n, 1, 300 + 10 * a + b)
+    for name, inv, cos in FLAVOURS:
+        got = ctx.ntt_general(1, x, a, b, inv, cos)
+        ref = co.ntt_general(1, x, a, b, inv, cos, threads=8)
+        assert np.array_equal(got, ref), (a, b, name)
+    # round trip on the coset
+    assert np.array_equal(ctx.ntt_general(1, ctx.ntt_general(1, x, a, b, False, True), a, b, True, True), x)
+
+
+def test_mixed_radix_refused_on_r4(ctx):
+    import pcd_b200
+    x = np.zeros((7, 5), dtype=np.uint64)
+    with pytest.raises(pcd_b200.PcdGpuError) as e:
+        ctx.ntt_general(0, x, 1, 0)
+    assert e.value.code == -4
+
+
+def test_groth16_mixed_radix_domain(ctx):
+    """helper side (MNT6-298, Fr = q4): 2^17 + 1 constraints need the domain 49 * 2^12 = 200704"""
+    import pcd_b200
+    from pcd_b200 import synthetic
+    m = (1 << 17) + 1
+    inst = synthetic.make_groth16_instance(ctx, 1, 0, seed=5, num_constraints=m)
+    assert pcd_b200.lib.domain_size(1, m + 2) == (200704, 2, 12)
+    g = pcd_b200.Groth16(ctx, 1)
+    idx = g.index(pcd_b200.ProvingKey(pairing=1, **inst["pk"]),
+                  pcd_b200.ConstraintMatrices(1, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"]),
+                  precompute=True)
+    assert idx.domain_size == 200704
+    p = inst["p"]
+    r, s = pow(3, 99, p), pow(5, 77, p)
+    proof = g.create_proof_with_reduction(idx, inst["z"], codec.int_to_limbs(r), codec.int_to_limbs(s))
+    assert np.array_equal(proof.affine_limbs(), synthetic.expected_proof(ctx, inst, r, s))
+    h = g.witness_map(idx, inst["z"])
+    ref_h = co.witness_map(1, inst["A"], inst["B"], inst["C"], m, inst["num_inputs"], inst["z"], threads=16)
+    assert np.array_equal(h, ref_h)
+    idx.close()
