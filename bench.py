@@ -187,7 +187,9 @@ def run_gpu(args, rank, local_rank, world):
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         return float(t.item())
 
-    imad_peak, _ = ctx.bench_imad(0, 4000)   # independent IMAD.WIDE.U32 chains: the integer roof
+    # the integer roof: independent accumulate-form IMAD.WIDE.U32 (fmaheavy pipe, 32 lanes/clk/SM on B200 -- the
+    # first version of this microbenchmark let ptxas hoist the products and measured 64-bit ADDS instead)
+    imad_peak, _ = ctx.bench_imad(0, 4000)
     imad_chain, _ = ctx.bench_imad(3, 4000)  # the same multiply-adds as carry chains (.X form)
 
     # ---- workload -----------------------------------------------------------------------------------
@@ -366,7 +368,7 @@ def run_gpu(args, rank, local_rank, world):
         "frac": achieved / (imad_peak / 1e12), "traffic": traffic,
         "traffic_note": "DRAM bytes of one launch from the committed ncu capture (2^20 points, uniform scalars); "
                         "algorithmic: 80 B per gathered point + 4 B per entry",
-        "peak_source": "measured live: independent IMAD.WIDE.U32 chains (carry-chain form: %.2f TIMAD/s)" % (imad_chain / 1e12),
+        "peak_source": "measured live: independent accumulate-form IMAD.WIDE.U32 on the fmaheavy pipe (carry-chain form: %.2f TIMAD/s)" % (imad_chain / 1e12),
         "launch_ms_avg": prof["ms"][dom] / max(prof["spans"][dom], 1),
         "work": "bucket entries x %d Montgomery products (XYZZ mixed add 8M+2S) x %d IMAD" % (MADD_MODMULS[deg], MODMUL_IMADS),
     }

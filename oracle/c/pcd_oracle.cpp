@@ -790,6 +790,132 @@ static int groth16_prove(const Groth16PkView& pk, const Csr& A, const Csr& B, co
 }
 
 // ------------------------------------------------------------------------------------------
+// GM17 prover (ark-gm17 r1cs_to_sap.rs / prover.rs).  Mirrors oracle/pcd_oracle.py
+// sap_witness_map / gm17_prove; the reference binds it at /root/reference/tests/mnt4_gm17.rs:27-28.
+// ------------------------------------------------------------------------------------------
+// full: num_inputs + num_witness + m + (num_inputs - 1) elements (the SAP assignment), h: n + 1 coefficients
+template <class P>
+static int sap_witness_map(const Csr& A, const Csr& B, const Csr& Cm, size_t m, size_t num_inputs, size_t num_witness,
+                           const Fp<P>* z, const Fp<P>& d1, const Fp<P>& d2, Fp<P>* full, Fp<P>* h, int threads) {
+  typedef Fp<P> F;
+  DomainShape dom;
+  if (!domain_shape<P>(2 * m + 2 * (num_inputs - 1) + 1, &dom)) return -1;
+  const size_t n = dom.n, nv = num_inputs + num_witness;
+  const size_t ev1 = nv, ev2 = nv + m - 1, off = 2 * m;
+  const F one = F::one();
+  std::vector<F> a(n, F::zero()), c(n, F::zero());
+  for (size_t i = 0; i < nv; i++) full[i] = z[i];
+  parallel_for(m, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; i++) {
+      F az = row_dot<P>(A, i, z), bz = row_dot<P>(B, i, z), cz = row_dot<P>(Cm, i, z);
+      F e = (az - bz) * (az - bz);
+      full[ev1 + i] = e;
+      a[2 * i] = az + bz;
+      a[2 * i + 1] = az - bz;
+      F c4 = cz + cz;
+      c4 = c4 + c4;
+      c[2 * i] = c4 + e;
+      c[2 * i + 1] = e;
+    }
+  });
+  a[off] = one;
+  c[off] = one;
+  for (size_t i = 1; i < num_inputs; i++) {
+    F e = (z[i] - one) * (z[i] - one);
+    full[ev2 + i] = e;
+    a[off + 2 * i - 1] = z[i] + one;
+    a[off + 2 * i] = z[i] - one;
+    F x4 = z[i] + z[i];
+    x4 = x4 + x4;
+    c[off + 2 * i - 1] = x4 + e;
+    c[off + 2 * i] = e;
+  }
+  domain_transform_general<P>(a.data(), dom, 1, 0, threads);
+  F d1d = d1 + d1, d1sq = d1 * d1;
+  parallel_for(n, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; i++) h[i] = d1d * a[i];
+  });
+  h[0] = h[0] - d2 - d1sq;
+  h[n] = d1sq;
+  domain_transform_general<P>(a.data(), dom, 0, 1, threads);
+  domain_transform_general<P>(c.data(), dom, 1, 0, threads);
+  domain_transform_general<P>(c.data(), dom, 0, 1, threads);
+  F zinv = (F::generator().pow_u64((u64)n) - one).inverse();
+  parallel_for(n, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; i++) a[i] = (a[i] * a[i] - c[i]) * zinv;
+  });
+  domain_transform_general<P>(a.data(), dom, 1, 1, threads);
+  parallel_for(n - 1, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; i++) h[i] = h[i] + a[i];
+  });
+  return (int)n;
+}
+
+struct Gm17PkView {
+  const void *a_query, *b_query, *c_query_1, *c_query_2, *g_gamma2_z_t;  // nsap G1, nsap G2, nsap - ni G1, nsap G1, n + 1 G1
+  const void *g_gamma_z, *h_gamma_z, *g_ab_gamma_z, *g_gamma2_z2;         // G1, G2, G1, G1
+};
+
+template <class G1, class G2, class P>
+static int gm17_prove(const Gm17PkView& pk, const Csr& A, const Csr& B, const Csr& Cm, size_t m, size_t num_inputs,
+                      size_t num_witness, const Fp<P>* z, const u64* d1p, const u64* d2p, const u64* rp, void* out,
+                      int threads) {
+  typedef Fp<P> F;
+  DomainShape dom;
+  if (!domain_shape<P>(2 * m + 2 * (num_inputs - 1) + 1, &dom)) return -1;
+  const size_t n = dom.n, nsap = num_inputs + num_witness + m + num_inputs - 1;
+  F d1, d2, r;
+  memcpy(d1.l, d1p, 40);
+  memcpy(d2.l, d2p, 40);
+  memcpy(r.l, rp, 40);
+  F d1m = d1.to_mont(), d2m = d2.to_mont(), rm = r.to_mont();
+  std::vector<F> full(nsap), h(n + 1);
+  if (sap_witness_map<P>(A, B, Cm, m, num_inputs, num_witness, z, d1m, d2m, full.data(), h.data(), threads) < 0) return -1;
+  std::vector<u64> hs(5 * (n + 1)), fs(5 * nsap);
+  parallel_for(n + 1, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; i++) { F v = h[i].from_mont(); memcpy(&hs[5 * i], v.l, 40); }
+  });
+  parallel_for(nsap, threads, [&](size_t lo, size_t hi, int) {
+    for (size_t i = lo; i < hi; i++) { F v = full[i].from_mont(); memcpy(&fs[5 * i], v.l, 40); }
+  });
+  const Aff<G1>* aq = (const Aff<G1>*)pk.a_query;
+  const Aff<G2>* bq = (const Aff<G2>*)pk.b_query;
+  const Aff<G1>* c2q = (const Aff<G1>*)pk.c_query_2;
+  const Aff<G1>* gzt = (const Aff<G1>*)pk.g_gamma2_z_t;
+  Jac<G1> ggz = Jac<G1>::from_affine(*(const Aff<G1>*)pk.g_gamma_z);
+  Jac<G2> hgz = Jac<G2>::from_affine(*(const Aff<G2>*)pk.h_gamma_z);
+  Jac<G1> gabz = Jac<G1>::from_affine(*(const Aff<G1>*)pk.g_ab_gamma_z);
+  Jac<G1> gz2 = Jac<G1>::from_affine(*(const Aff<G1>*)pk.g_gamma2_z2);
+  F rd1 = (rm + d1m).from_mont();
+  // A = (r + d1) g_gamma_z + a_query[0] + MSM(a_query[1..], full[1..]);  B likewise in G2
+  Jac<G1> g_a = Jac<G1>::mul(ggz, rd1.l, 5);
+  g_a.add_mixed(aq[0]);
+  g_a.add(msm_pippenger<G1>(aq + 1, fs.data() + 5, nsap - 1, threads, 0));
+  Jac<G2> g_b = Jac<G2>::mul(hgz, rd1.l, 5);
+  g_b.add_mixed(bq[0]);
+  g_b.add(msm_pippenger<G2>(bq + 1, fs.data() + 5, nsap - 1, threads, 0));
+  // C = MSM(c_query_1, aux) + (r^2 + 2 r d1) g_gamma2_z2 + (r + d1) g_ab_gamma_z + r (c_query_2[0] + MSM(c_query_2[1..]))
+  //     + d2 g_gamma2_z_t[0] + MSM(g_gamma2_z_t, h)
+  Jac<G1> g_c = msm_pippenger<G1>((const Aff<G1>*)pk.c_query_1, fs.data() + 5 * num_inputs, nsap - num_inputs, threads, 0);
+  F k = (rm * rm + (rm + rm) * d1m).from_mont();
+  g_c.add(Jac<G1>::mul(gz2, k.l, 5));
+  g_c.add(Jac<G1>::mul(gabz, rd1.l, 5));
+  Jac<G1> c2 = msm_pippenger<G1>(c2q + 1, fs.data() + 5, nsap - 1, threads, 0);
+  c2.add_mixed(c2q[0]);
+  g_c.add(Jac<G1>::mul(c2, r.l, 5));
+  g_c.add(Jac<G1>::mul(Jac<G1>::from_affine(gzt[0]), d2.l, 5));
+  g_c.add(msm_pippenger<G1>(gzt, hs.data(), n + 1, threads, 0));
+  char* o = (char*)out;
+  Aff<G1> A_ = g_a.to_affine();
+  Aff<G2> B_ = g_b.to_affine();
+  Aff<G1> C_ = g_c.to_affine();
+  memcpy(o, &A_, sizeof(A_));
+  memcpy(o + sizeof(A_), &B_, sizeof(B_));
+  memcpy(o + sizeof(A_) + sizeof(B_), &C_, sizeof(C_));
+  return 0;
+}
+
+// ------------------------------------------------------------------------------------------
 // ark-serialize compressed encodings
 // ------------------------------------------------------------------------------------------
 template <class P>
@@ -964,6 +1090,33 @@ int orc_groth16_prove(int pairing, const void* const* pk, const uint32_t* a_ptr,
                                           (const u64*)s, out, threads);
   return groth16_prove<C6G1, C6G2, PQ4>(v, A, B, C, m, num_inputs, num_witness, (const FpQ4*)z, (const u64*)r,
                                         (const u64*)s, out, threads);
+}
+// GM17.  full: the SAP assignment (num_inputs + num_witness + m + num_inputs - 1), h: n + 1 coefficients;
+// d1, d2 in Montgomery form here.  Returns the SAP domain size n (or -1).
+int orc_sap_witness_map(int pairing, const uint32_t* a_ptr, const uint32_t* a_col, const void* a_val,
+                        const uint32_t* b_ptr, const uint32_t* b_col, const void* b_val, const uint32_t* c_ptr,
+                        const uint32_t* c_col, const void* c_val, size_t m, size_t num_inputs, size_t num_witness,
+                        const void* z, const void* d1, const void* d2, void* full, void* h, int threads) {
+  Csr A{a_ptr, a_col, (const u64*)a_val}, B{b_ptr, b_col, (const u64*)b_val}, C{c_ptr, c_col, (const u64*)c_val};
+  if (pairing == 0)
+    return sap_witness_map<PR4>(A, B, C, m, num_inputs, num_witness, (const FpR4*)z, ldf<FpR4>(d1), ldf<FpR4>(d2),
+                                (FpR4*)full, (FpR4*)h, threads);
+  return sap_witness_map<PQ4>(A, B, C, m, num_inputs, num_witness, (const FpQ4*)z, ldf<FpQ4>(d1), ldf<FpQ4>(d2),
+                              (FpQ4*)full, (FpQ4*)h, threads);
+}
+// pk: 9 pointers in Gm17PkView order; d1, d2, r plain integers (like r, s of orc_groth16_prove).
+// out: A (G1 affine) || B (G2 affine) || C (G1 affine).
+int orc_gm17_prove(int pairing, const void* const* pk, const uint32_t* a_ptr, const uint32_t* a_col, const void* a_val,
+                   const uint32_t* b_ptr, const uint32_t* b_col, const void* b_val, const uint32_t* c_ptr,
+                   const uint32_t* c_col, const void* c_val, size_t m, size_t num_inputs, size_t num_witness,
+                   const void* z, const void* d1, const void* d2, const void* r, void* out, int threads) {
+  Gm17PkView v{pk[0], pk[1], pk[2], pk[3], pk[4], pk[5], pk[6], pk[7], pk[8]};
+  Csr A{a_ptr, a_col, (const u64*)a_val}, B{b_ptr, b_col, (const u64*)b_val}, C{c_ptr, c_col, (const u64*)c_val};
+  if (pairing == 0)
+    return gm17_prove<C4G1, C4G2, PR4>(v, A, B, C, m, num_inputs, num_witness, (const FpR4*)z, (const u64*)d1,
+                                       (const u64*)d2, (const u64*)r, out, threads);
+  return gm17_prove<C6G1, C6G2, PQ4>(v, A, B, C, m, num_inputs, num_witness, (const FpQ4*)z, (const u64*)d1,
+                                     (const u64*)d2, (const u64*)r, out, threads);
 }
 // proof affine bytes (as written by orc_groth16_prove / pcdgpu_groth16_prove) -> canonical
 // compressed bytes; returns the length (152 MNT4, 190 MNT6)

@@ -1101,6 +1101,216 @@ def serialize_proof(pairing: Pairing, proof) -> bytes:
 
 
 # ----------------------------------------------------------------------------------------------
+# GM17 (ark-gm17 r1cs_to_sap.rs / generator.rs / prover.rs), the second SNARK the
+# reference plugs into ECCyclePCD (/root/reference/tests/mnt4_gm17.rs:27-28, mnt4_mix_*.rs).  Restated
+# from the published construction (Groth-Maller 2017 over square arithmetic programs, in the shape of
+# libsnark's r1cs_se_ppzksnark that ark-gm17 follows); PARITY UNPINNED like everything else here.  The
+# key is generated with a KNOWN trapdoor so a proof can be checked through its discrete logarithms.
+# ----------------------------------------------------------------------------------------------
+def _row_eval(row, z, p):
+    return sum(co * z[j] for co, j in row) % p
+
+
+def sap_extend_assignment(r1cs: R1CS, z: Sequence[int]) -> List[int]:
+    """``R1CStoSAP::witness_map``, first half: the SAP assignment = z || (<A_i,z> - <B_i,z>)^2 for every
+    constraint || (z_i - 1)^2 for every public input i >= 1."""
+    p = r1cs.fp.p
+    full = list(z)
+    for ra, rb in zip(r1cs.A, r1cs.B):
+        full.append(pow((_row_eval(ra, z, p) - _row_eval(rb, z, p)) % p, 2, p))
+    for i in range(1, r1cs.num_inputs):
+        full.append(pow((z[i] - 1) % p, 2, p))
+    return full
+
+
+def sap_domain(r1cs: R1CS) -> Domain:
+    return domain_new(r1cs.fp, 2 * r1cs.num_constraints + 2 * (r1cs.num_inputs - 1) + 1)
+
+
+def sap_witness_map(r1cs: R1CS, z: Sequence[int], d1: int, d2: int):
+    """``R1CStoSAP::witness_map``: returns (full SAP assignment, the n + 1 coefficients of
+    H = ((u + d1 Z)^2 - (c + d2 Z)) / Z, domain).  SAP rows: constraint i gives rows 2i: (A_i + B_i)^2 =
+    4 C_i + e_i and 2i + 1: (A_i - B_i)^2 = e_i; then 1^2 = 1; then for each input (x + 1)^2 = 4 x + e', (x - 1)^2 = e'."""
+    fp = r1cs.fp
+    p = fp.p
+    m, ni = r1cs.num_constraints, r1cs.num_inputs
+    full = sap_extend_assignment(r1cs, z)
+    d = sap_domain(r1cs)
+    n = d.size
+    off = 2 * m
+    ev1 = ni + r1cs.num_witness          # first per-constraint extra variable
+    ev2 = ev1 + m - 1                    # extra variable of input i is at ev2 + i
+    a = [0] * n
+    c = [0] * n
+    for i in range(m):
+        az, bz, cz = (_row_eval(r, z, p) for r in (r1cs.A[i], r1cs.B[i], r1cs.C[i]))
+        a[2 * i] = (az + bz) % p
+        a[2 * i + 1] = (az - bz) % p
+        c[2 * i] = (4 * cz + full[ev1 + i]) % p
+        c[2 * i + 1] = full[ev1 + i]
+    a[off] = 1
+    c[off] = 1
+    for i in range(1, ni):
+        a[off + 2 * i - 1] = (z[i] + 1) % p
+        a[off + 2 * i] = (z[i] - 1) % p
+        c[off + 2 * i - 1] = (4 * z[i] + full[ev2 + i]) % p
+        c[off + 2 * i] = full[ev2 + i]
+    a = domain_ifft(d, a)
+    h = [(2 * d1 * x) % p for x in a]
+    h[0] = (h[0] - d2 - d1 * d1) % p
+    h.append(d1 * d1 % p)
+    a = domain_coset_fft(d, a)
+    c = domain_coset_fft(d, domain_ifft(d, c))
+    zinv = pow((pow(d.coset_gen, n, p) - 1) % p, -1, p)
+    aa = domain_coset_ifft(d, [((a[i] * a[i] - c[i]) * zinv) % p for i in range(n)])
+    for i in range(n - 1):
+        h[i] = (h[i] + aa[i]) % p
+    assert aa[n - 1] == 0, "SAP not satisfied: quotient degree too high"
+    return full, h, d
+
+
+@dataclass
+class GM17PK:
+    pairing: Pairing
+    # vk
+    h_g2: tuple
+    g_alpha_g1: tuple
+    h_beta_g2: tuple
+    g_gamma_g1: tuple
+    h_gamma_g2: tuple
+    vk_query: list          # G1, one per public input (incl. the constant)
+    # pk
+    a_query: list           # G1, one per SAP variable: gamma At_i
+    b_query: list           # G2, one per SAP variable: gamma At_i
+    c_query_1: list         # G1, non-input SAP variables: gamma^2 Ct_i + (alpha + beta) gamma At_i
+    c_query_2: list         # G1, one per SAP variable: 2 gamma^2 Z At_i
+    g_gamma_z: tuple
+    h_gamma_z: tuple
+    g_ab_gamma_z: tuple
+    g_gamma2_z2: tuple
+    g_gamma2_z_t: list      # G1, n + 1 powers: gamma^2 Z t^i
+    trapdoor: dict = dc_field(default_factory=dict)
+
+
+def gm17_setup_scalars(pairing: Pairing, r1cs: R1CS, seed: int = 11) -> dict:
+    """``R1CStoSAP::instance_map_with_evaluation`` + the exponents of ``generate_parameters`` for a known
+    trapdoor (t, alpha, beta, gamma); generators are the fixed group generators (upstream draws random ones)."""
+    fp = pairing.fr
+    assert fp is r1cs.fp
+    p = fp.p
+    rng = SplitMix64(seed)
+    alpha, beta, gamma, t = (rng.field(p) or 1 for _ in range(4))
+    m, ni = r1cs.num_constraints, r1cs.num_inputs
+    d = sap_domain(r1cs)
+    n = d.size
+    u = _lagrange_at(d, t)
+    nsap = ni + r1cs.num_witness + m + (ni - 1)
+    ev1 = ni + r1cs.num_witness
+    ev2 = ev1 + m - 1
+    off = 2 * m
+    At = [0] * nsap
+    Ct = [0] * nsap
+    for i in range(m):
+        uadd, usub = (u[2 * i] + u[2 * i + 1]) % p, (u[2 * i] - u[2 * i + 1]) % p
+        for co, j in r1cs.A[i]:
+            At[j] = (At[j] + uadd * co) % p
+        for co, j in r1cs.B[i]:
+            At[j] = (At[j] + usub * co) % p
+        for co, j in r1cs.C[i]:
+            Ct[j] = (Ct[j] + 4 * u[2 * i] * co) % p
+        Ct[ev1 + i] = (Ct[ev1 + i] + uadd) % p
+    At[0] = (At[0] + u[off]) % p
+    Ct[0] = (Ct[0] + u[off]) % p
+    for i in range(1, ni):
+        u1, u2 = u[off + 2 * i - 1], u[off + 2 * i]
+        At[i] = (At[i] + u1 + u2) % p
+        At[0] = (At[0] + u1 - u2) % p
+        Ct[i] = (Ct[i] + 4 * u1) % p
+        Ct[ev2 + i] = (Ct[ev2 + i] + u1 + u2) % p
+    zt = (pow(t, n, p) - 1) % p
+    ab = (alpha + beta) % p
+    g2 = gamma * gamma % p
+    return dict(
+        alpha=alpha, beta=beta, gamma=gamma, t=t, zt=zt, At=At, Ct=Ct, n=n,
+        a_sc=[gamma * x % p for x in At],
+        c1_sc=[(g2 * Ct[j] + ab * gamma % p * At[j]) % p for j in range(ni, nsap)],
+        c2_sc=[2 * g2 % p * zt % p * x % p for x in At],
+        vk_sc=[(gamma * Ct[j] + ab * At[j]) % p for j in range(ni)],
+        gzt_sc=[g2 * zt % p * pow(t, i, p) % p for i in range(n + 1)],
+    )
+
+
+def gm17_setup(pairing: Pairing, r1cs: R1CS, seed: int = 11) -> GM17PK:
+    t = gm17_setup_scalars(pairing, r1cs, seed)
+    p = pairing.fr.p
+    G1, G2 = pairing.g1, pairing.g2
+    g, h = generator(G1), generator(G2)
+    gam, zt, ab = t["gamma"], t["zt"], (t["alpha"] + t["beta"]) % p
+    return GM17PK(
+        pairing, h, G1.mul(g, t["alpha"]), G2.mul(h, t["beta"]), G1.mul(g, gam), G2.mul(h, gam),
+        [G1.mul(g, x) for x in t["vk_sc"]],
+        [G1.mul(g, x) for x in t["a_sc"]],
+        [G2.mul(h, x) for x in t["a_sc"]],
+        [G1.mul(g, x) for x in t["c1_sc"]],
+        [G1.mul(g, x) for x in t["c2_sc"]],
+        G1.mul(g, gam * zt % p), G2.mul(h, gam * zt % p), G1.mul(g, ab * gam % p * zt % p),
+        G1.mul(g, gam * gam % p * zt % p * zt % p),
+        [G1.mul(g, x) for x in t["gzt_sc"]],
+        t,
+    )
+
+
+def gm17_prove(pk: GM17PK, r1cs: R1CS, z: Sequence[int], d1: int, d2: int, r: int, msm=msm_pippenger):
+    """``create_proof`` of ark-gm17 (d1, d2, r supplied by the caller, drawn in this order upstream).  The
+    input / aux splits of upstream's MSMs are not reproduced: a sum of MSMs over a partition of the
+    index set is the MSM over the whole set, and proofs are compared after into_affine()."""
+    pairing = pk.pairing
+    G1, G2 = pairing.g1, pairing.g2
+    p = pairing.fr.p
+    ni = r1cs.num_inputs
+    full, h, _ = sap_witness_map(r1cs, z, d1, d2)
+    rest = full[1:]
+    aux = full[ni:]
+    g_a = G1.sum([G1.mul(pk.g_gamma_z, r), pk.a_query[0], G1.mul(pk.g_gamma_z, d1), msm(G1, pk.a_query[1:], rest)])
+    g_b = G2.sum([G2.mul(pk.h_gamma_z, r), pk.b_query[0], G2.mul(pk.h_gamma_z, d1), msm(G2, pk.b_query[1:], rest)])
+    c1_acc = msm(G1, pk.c_query_1, aux)
+    c2_acc = msm(G1, pk.c_query_2[1:], rest)
+    g_acc = msm(G1, pk.g_gamma2_z_t, h)
+    g_c = G1.sum([
+        c1_acc,
+        G1.mul(pk.g_gamma2_z2, r * r % p),
+        G1.mul(pk.g_ab_gamma_z, r),
+        G1.mul(pk.g_ab_gamma_z, d1),
+        G1.mul(pk.c_query_2[0], r),
+        G1.mul(pk.g_gamma2_z2, 2 * r * d1 % p),
+        G1.mul(c2_acc, r),
+        G1.mul(pk.g_gamma2_z_t[0], d2),
+        g_acc,
+    ])
+    return g_a, g_b, g_c
+
+
+def gm17_trapdoor_check(pk: GM17PK, r1cs: R1CS, z: Sequence[int], d1: int, d2: int, r: int, proof) -> bool:
+    """Trapdoor check of a GM17 proof produced with known (d1, d2, r): a = gamma (u + (r + d1) Z) with
+    u = sum full_i At_i(t); b = a (in G2); c from the verification equation
+    (a + alpha)(a + beta) = alpha beta + gamma psi + c.  Checks A == [a]G, B == [a]H, C == [c]G -- i.e. that
+    the proof satisfies both of GM17's pairing equations AND is the honest prover's output for this randomness.
+    The SAP quotient is never formed here, so witness map, NTTs and all MSMs are validated end to end."""
+    t = pk.trapdoor
+    pairing = pk.pairing
+    p = pairing.fr.p
+    G1, G2 = pairing.g1, pairing.g2
+    full = sap_extend_assignment(r1cs, z)
+    u = sum(x * y for x, y in zip(full, t["At"])) % p
+    a_log = t["gamma"] * ((u + (r + d1) * t["zt"]) % p) % p
+    psi = sum(z[i] * t["vk_sc"][i] for i in range(r1cs.num_inputs)) % p
+    c_log = ((a_log + t["alpha"]) * (a_log + t["beta"]) - t["alpha"] * t["beta"] - t["gamma"] * psi) % p
+    A, B, C = proof
+    return (A == G1.mul(generator(G1), a_log) and B == G2.mul(generator(G2), a_log)
+            and C == G1.mul(generator(G1), c_log))
+
+
+# ----------------------------------------------------------------------------------------------
 # Self-check of every constant (SURVEY.md A; "verify every recalled constant arithmetically").
 # ----------------------------------------------------------------------------------------------
 def _is_probable_prime(n: int) -> bool:

@@ -19,6 +19,7 @@
 #include <cstdint>
 
 #include "constants30.cuh"
+#include "prims.cuh"
 
 #if defined(__CUDACC__)
 #define F30_HD __host__ __device__ __forceinline__
@@ -149,35 +150,56 @@ struct Fp30 {
   F30_HD Fp30 dbl() const { return *this + *this; }
 
   // ---- Montgomery product, R' = 2^300 ---------------------------------------------------------------
-  // Operand scanning with 64-bit column accumulators.  Row i adds a[j] * b[i] and m * p[j] to the ten
-  // columns (20 independent IMAD.WIDE.U32), where m makes column 0 divisible by 2^30; the columns
-  // then shift down by one limb.  A column sees at most 2 * 5 products of < 2^60 between the two
-  // carry sweeps (after rows 4 and 9), so it stays below 2^64.
+  // Operand scanning with 64-bit column accumulators held as register PAIRS (lo[j], hi[j]).  Row i adds
+  // a[j] * b[i] and m * p[j] to the ten columns (20 independent multiply-adds), where m makes column 0
+  // divisible by 2^30; the columns then shift down by one limb.  A column sees at most 2 * 5 products of
+  // < 2^60 between the two carry sweeps (after rows 4 and 9), so it stays below 2^64.
+  //
+  // The multiply-add is written as mad.lo.cc / madc.hi on the 32-bit halves (prims::mac), NOT as
+  // mad.wide.u32 on a 64-bit register: ptxas 12.9 rewrites chains of the latter into IMAD.WIDE + 3-input
+  // IADD3 pairs (646 alu instructions per two products, 36.6 G products/s on B200), while the former
+  // becomes one plain accumulate-form IMAD.WIDE.U32 each -- no carry predicate, so it issues at full rate
+  // (a carry-in OR carry-out predicate on IMAD.WIDE halves its issue rate: tools/probe_modmul.py).
   F30_HD friend Fp30 operator*(const Fp30& a, const Fp30& b) {
-    u64 t[11];
-#pragma unroll
-    for (int j = 0; j < 11; j++) t[j] = 0;
+    u32 lo[10], hi[10];
 #pragma unroll
     for (int i = 0; i < 10; i++) {
       const u32 bi = b.l[i];
+      if (i == 0) {
 #pragma unroll
-      for (int j = 0; j < 10; j++) mad_wide(t[j], a.l[j], bi);
-      const u32 m = ((u32)t[0] * P::PINV30) & MASK30;
+        for (int j = 0; j < 10; j++) prims::mul_wide(lo[j], hi[j], a.l[j], bi);
+      } else {
 #pragma unroll
-      for (int j = 0; j < 10; j++) mad_wide(t[j], m, P::mod(j));
-      t[1] += t[0] >> 30;
+        for (int j = 0; j < 10; j++) prims::mac(lo[j], hi[j], a.l[j], bi);
+      }
+      const u32 m = (lo[0] * P::PINV30) & MASK30;
 #pragma unroll
-      for (int j = 0; j < 10; j++) t[j] = t[j + 1];
-      t[10] = 0;
+      for (int j = 0; j < 10; j++) prims::mac(lo[j], hi[j], m, P::mod(j));
+      prims::add_shr30(lo[1], hi[1], lo[0], hi[0]);
+#pragma unroll
+      for (int j = 0; j < 9; j++) {
+        lo[j] = lo[j + 1];
+        hi[j] = hi[j + 1];
+      }
+      lo[9] = 0;
+      hi[9] = 0;
       if (i == 4) {
 #pragma unroll
-        for (int j = 0; j < 9; j++) {
-          t[j + 1] += t[j] >> 30;
-          t[j] &= MASK30;
+        for (int j = 0; j < 8; j++) {
+          prims::add_shr30(lo[j + 1], hi[j + 1], lo[j], hi[j]);
+          lo[j] &= MASK30;
+          hi[j] = 0;
         }
       }
     }
-    return normalize(t);
+    Fp30 r;
+#pragma unroll
+    for (int j = 0; j < 9; j++) {
+      prims::add_shr30(lo[j + 1], hi[j + 1], lo[j], hi[j]);
+      r.l[j] = lo[j] & MASK30;
+    }
+    r.l[9] = lo[9];
+    return r;
   }
   F30_HD Fp30 sqr() const { return (*this) * (*this); }
   F30_NOINLINE static Fp30 mul_ni(Fp30 a, Fp30 b) { return a * b; }

@@ -246,25 +246,32 @@ int groth16_serialize(pcdgpu_ctx* ctx, int pairing, const void* d_proof, unsigne
 }
 
 // ---- integer-pipe microbenchmarks -----------------------------------------------------------------
-// 8 independent 32x32+64 multiply-add chains per thread (IMAD.WIDE.U32): the IMAD roof of SURVEY.md 8d.
+// 8 independent 32x32+64 multiply-add chains per thread (IMAD.WIDE.U32 R, a, b, R): the IMAD roof of
+// SURVEY.md 8d.  The multiplier changes with the data every round: with loop-invariant operands ptxas hoists
+// the products out of the loop and leaves 64-bit ADDS (the first version of this kernel did exactly that --
+// ncu showed the alu pipe 96 % busy and the fma pipe 3 % -- and reported a "17.9 T IMAD/s" roof that does not
+// exist).  IMAD.WIDE issues on the fmaheavy pipe only: 32 lanes/clk/SM, with or without a carry predicate.
 __global__ void __launch_bounds__(256) bench_imad_kernel(unsigned long long* out, int iters, u32 seed) {
-  unsigned long long acc[8];
-  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+  u32 lo[8], hi[8], a[8];
+  u32 b = seed * 3 + blockIdx.x;
 #pragma unroll
-  for (int j = 0; j < 8; j++) acc[j] = j + threadIdx.x;
+  for (int j = 0; j < 8; j++) {
+    lo[j] = j + threadIdx.x;
+    hi[j] = j * 5 + blockIdx.x;
+    a[j] = (seed + threadIdx.x) * (2 * j + 1);
+  }
   for (int i = 0; i < iters; i++) {
 #pragma unroll
     for (int rep = 0; rep < 8; rep++) {
 #pragma unroll
-      for (int j = 0; j < 8; j++) {
-        asm volatile("mad.wide.u32 %0, %1, %2, %0;" : "+l"(acc[j]) : "r"(a + j), "r"(b));
-      }
+      for (int j = 0; j < 8; j++) prims::mac(lo[j], hi[j], a[j], b);
+      b = hi[rep];
     }
   }
-  unsigned long long s = 0;
+  u32 s = 0;
 #pragma unroll
-  for (int j = 0; j < 8; j++) s ^= acc[j];
-  if (s == 0x1234567ull) out[0] = s;
+  for (int j = 0; j < 8; j++) s ^= lo[j] ^ hi[j];
+  if (s == 0x1234567u) out[0] = s;
 }
 // the same multiply-adds written as carry chains (mad.lo.cc / madc.hi.cc -> IMAD.WIDE.U32.X): this is
 // the form a multi-limb product needs, and what fp.cuh's operator* is made of.
@@ -310,6 +317,52 @@ __global__ void __launch_bounds__(256) bench_modmul_kernel(u32* out, int iters, 
   if (x.l[0] == 0x12345u && y.l[3] == 7u) out[0] = x.l[1];
 }
 
+// the same with an explicit choice of product: SC = 1 separated carries (Fp::mul_sc), 0 carry chains (Fp::mul_cc)
+template <class F, int SC>
+__global__ void __launch_bounds__(256) bench_modmul_sel_kernel(u32* out, int iters, u32 seed) {
+  F x, y;
+  const u32* in = out + 64 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 20;
+#pragma unroll
+  for (int i = 0; i < 10; i++) {
+    x.l[i] = in[i];
+    y.l[i] = in[10 + i] ^ seed;
+  }
+  x.l[9] &= 0xff;
+  y.l[9] &= 0xff;
+  for (int i = 0; i < iters; i++) {
+    if (SC) {
+      x = F::mul_sc(x, y);
+      y = F::mul_sc(y, x);
+    } else {
+      x = F::mul_cc(x, y);
+      y = F::mul_cc(y, x);
+    }
+  }
+  if (x.l[0] == 0x12345u && y.l[3] == 7u) out[0] = x.l[1];
+}
+// independent multiply-adds with a carry OUT only, counted on the alu pipe (the building block of mul_sc)
+__global__ void __launch_bounds__(256) bench_imad_cout_kernel(u32* out, int iters, u32 seed) {
+  u32 lo[8], hi[8], c[8];
+  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
+#pragma unroll
+  for (int j = 0; j < 8; j++) {
+    lo[j] = j + threadIdx.x;
+    hi[j] = j * 3 + threadIdx.x;
+    c[j] = 0;
+  }
+  for (int i = 0; i < iters; i++) {
+#pragma unroll
+    for (int rep = 0; rep < 8; rep++) {
+#pragma unroll
+      for (int j = 0; j < 8; j++) prims::mac_carry(lo[j], hi[j], c[j], a + j, b);
+    }
+  }
+  u32 s = 0;
+#pragma unroll
+  for (int j = 0; j < 8; j++) s ^= lo[j] ^ hi[j] ^ c[j];
+  if (s == 0x1234567u) out[0] = s;
+}
+
 // the radix-2^30 carry-free product (fp30.cuh), same shape of benchmark
 template <class F, int CHAINS>
 __global__ void __launch_bounds__(256) bench_modmul30_kernel(u32* out, int iters, u32 seed) {
@@ -349,7 +402,9 @@ int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double
   if (modmul == 9) blocks = ctx->sm_count;
   double per_thread = modmul == 3 ? 64.0 * iters : (modmul ? 2.0 * iters : 64.0 * iters);
   if (modmul == 6) per_thread = 4.0 * iters;
-  if (modmul >= 7) blocks = ctx->sm_count * (modmul == 7 ? 2 : 1);  // low occupancy: 16 / 8 warps per SM
+  if (modmul >= 7 && modmul <= 9) blocks = ctx->sm_count * (modmul == 7 ? 2 : 1);  // low occupancy: 16 / 8 warps per SM
+  if (modmul == 12 || modmul == 15) blocks = ctx->sm_count;                         // 8 warps per SM
+  if (modmul == 16) per_thread = 64.0 * iters;
   for (int rep = 0; rep < 2; rep++) {  // first round warms up
     PCD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     if (modmul == 1) bench_modmul_kernel<FpR4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
@@ -360,6 +415,11 @@ int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double
     else if (modmul == 6) bench_modmul30_kernel<Fp30Q4, 2><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else if (modmul == 7 || modmul == 8) bench_modmul30_kernel<Fp30Q4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else if (modmul == 9) bench_modmul_kernel<FpQ4><<<ctx->sm_count, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 10) bench_modmul_sel_kernel<FpR4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 11 || modmul == 12) bench_modmul_sel_kernel<FpQ4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 13) bench_modmul_sel_kernel<FpR4, 0><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 14 || modmul == 15) bench_modmul_sel_kernel<FpQ4, 0><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 16) bench_imad_cout_kernel<<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else bench_imad_kernel<<<blocks, 256, 0, ctx->stream>>>((unsigned long long*)d, iters, 7u);
     PCD_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     PCD_CUDA(ctx, cudaEventSynchronize(e1));

@@ -134,7 +134,15 @@ static __global__ void msm_sizekey_kernel(const u32* __restrict__ counts, size_t
 // Persistent warps pull 32 buckets at a time from a global queue (dynamic scheduling): with one thread per
 // bucket and a plain grid the kernel ran in a few "waves" of equally long threads, and its time was
 // the wave count rounded up (c = 18 at 2^20: 2.3 waves cost 3).
-template <class C>
+// PRE: the bases are a precomputed window table, stored in the radix-2^30 form already (precompute_kernel);
+// otherwise they are ABI points and are converted as they are loaded (two extra products per addition).
+template <class C, bool PRE>
+__device__ __forceinline__ AffinePoint<typename C::Fast::F> ld_base(const void* bases, size_t idx) {
+  if constexpr (PRE) return ld_vec<AffinePoint<typename C::Fast::F>>(bases, idx);
+  else return fast_affine<C>(ld_vec<AffinePoint<typename C::F>>(bases, idx));
+}
+
+template <class C, bool PRE>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ bases,
                                                              const u32* __restrict__ offsets,
                                                              const u32* __restrict__ entries,
@@ -142,6 +150,8 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
                                                              void* __restrict__ buckets, u32* __restrict__ heavy,
                                                              u32* __restrict__ queue, u32 heavy_thr) {
   typedef typename C::F F;
+  typedef typename C::Fast CF;    // the radix-2^30 twin of a G1 curve (ec.cuh); C itself for G2
+  typedef typename CF::F FF;
   const unsigned lane = threadIdx.x & 31;
   for (;;) {
     u32 first = 0;
@@ -152,7 +162,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
     if (t >= nbuckets) continue;
     size_t g = perm[t];
     u32 lo = offsets[g], hi = offsets[g + 1];
-    XYZZ<C> acc = XYZZ<C>::inf();
+    XYZZ<CF> acc = XYZZ<CF>::inf();
     if (hi - lo > heavy_thr) {
       u32 slot = atomicAdd(&heavy[0], 1u);
       if (slot < (u32)MSM_MAX_HEAVY) {
@@ -163,11 +173,11 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
     }
     for (u32 e = lo; e < hi; e++) {
       u32 ent = entries[e];
-      AffinePoint<F> p = ld_vec<AffinePoint<F>>(bases, ent & 0x7fffffffu);
+      AffinePoint<FF> p = ld_base<C, PRE>(bases, ent & 0x7fffffffu);
       if (ent >> 31) p.y = p.y.neg();
       acc.madd(p);
     }
-    st_vec(buckets, g, acc);
+    st_vec(buckets, g, slow_xyzz<C>(acc));
   }
 }
 
@@ -189,7 +199,7 @@ __device__ __forceinline__ void cta_tree_sum(XYZZ<C>* sm, const XYZZ<C>& mine) {
 // Heavy buckets (more than MSM_HEAVY entries: the "scalar == 1" bucket of a real witness holds a
 // fifth of all points) are cut into chunks of MSM_HEAVY_CHUNK entries; every CTA of the grid takes
 // chunks round-robin, sums one with a tree and appends (bucket, partial sum) to a list ...
-template <class C>
+template <class C, bool PRE>
 __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_accumulate_heavy_kernel(
     const void* __restrict__ bases, const u32* __restrict__ offsets, const u32* __restrict__ entries,
     const u32* __restrict__ heavy, u32* __restrict__ hp_count, u32* __restrict__ hp_id, void* __restrict__ hp_sum) {
@@ -206,14 +216,14 @@ __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_accumulate_heavy_kernel
       if (job % gridDim.x != blockIdx.x) continue;
       u32 e0 = lo + ch * MSM_HEAVY_CHUNK;
       u32 e1 = e0 + MSM_HEAVY_CHUNK < hi ? e0 + MSM_HEAVY_CHUNK : hi;
-      XYZZ<C> acc = XYZZ<C>::inf();
+      XYZZ<typename C::Fast> acc = XYZZ<typename C::Fast>::inf();
       for (u32 e = e0 + threadIdx.x; e < e1; e += MSM_HEAVY_THREADS) {
         u32 ent = entries[e];
-        AffinePoint<F> p = ld_vec<AffinePoint<F>>(bases, ent & 0x7fffffffu);
+        AffinePoint<typename C::Fast::F> p = ld_base<C, PRE>(bases, ent & 0x7fffffffu);
         if (ent >> 31) p.y = p.y.neg();
         acc.madd(p);
       }
-      cta_tree_sum<C>(sm, acc);
+      cta_tree_sum<C>(sm, slow_xyzz<C>(acc));
       if (threadIdx.x == 0) {
         u32 slot = atomicAdd(hp_count, 1u);
         hp_id[slot] = h;
@@ -358,21 +368,23 @@ __global__ void __launch_bounds__(128) fixed_mul_kernel(const void* __restrict__
   st_vec(out, i, acc.to_affine());
 }
 
-// pre[j * n + i] = 2^(start_j) * bases[i]  (affine), j < nwin, start_j = msm_win_start(j, c, nwin, balanced)
+// pre[j * n + i] = 2^(start_j) * bases[i]  (affine), j < nwin, start_j = msm_win_start(j, c, nwin, balanced).
+// For the G1 curves the table is written in the radix-2^30 form the accumulate kernels compute in (same 40
+// bytes per coordinate): it is read by msm_accumulate*<C, true> only.
 template <class C>
 __global__ void __launch_bounds__(128) precompute_kernel(const void* __restrict__ bases, size_t n, int c, int nwin,
                                                          void* __restrict__ pre) {
   typedef typename C::F F;
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  AffinePoint<F> a = ld_vec<AffinePoint<F>>(bases, i);
-  st_vec(pre, i, a);
+  AffinePoint<F> a = ld_vec_rw<AffinePoint<F>>(bases, i);  // pre may alias bases (row 0 in place)
+  st_vec(pre, i, fast_affine<C>(a));
   XYZZ<C> p = XYZZ<C>::from_affine(a);
   for (int j = 1; j < nwin; j++) {
     int nd = msm_win_start(j, c, nwin, 1) - msm_win_start(j - 1, c, nwin, 1);
     for (int b = 0; b < nd; b++) p = p.dbl();
     a = p.to_affine();
-    st_vec(pre, (size_t)j * n + i, a);
+    st_vec(pre, (size_t)j * n + i, fast_affine<C>(a));
     p = XYZZ<C>::from_affine(a);
   }
 }
@@ -456,7 +468,8 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     cudaMemcpyAsync(ctx->prof_pinned + ps, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st);
   }
   int acc_ctas = 0;
-  PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C>, 128, 0));
+  if (shared) PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, true>, 128, 0));
+  else PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, false>, 128, 0));
   if (acc_ctas < 1) acc_ctas = 1;
   // two CTAs (8 warps) per SM already saturate the multiply pipe (tools/probe_modmul.py); the registers left
   // free let the other lanes' latency-bound kernels (reduction, sorting, assembly) run beside this one
@@ -468,8 +481,12 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   // one thread (7 ms) would set the kernel's duration; such buckets go to the CTA-parallel heavy path.
   size_t avg_entries = total / nbuckets;
   u32 heavy_thr = (u32)(4 * avg_entries < 64 ? 64 : (4 * avg_entries > (size_t)MSM_HEAVY ? (size_t)MSM_HEAVY : 4 * avg_entries));
-  msm_accumulate_kernel<C><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets, bkt,
-                                                             heavy, queue, heavy_thr);
+  if (shared)
+    msm_accumulate_kernel<C, true><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
+                                                                     bkt, heavy, queue, heavy_thr);
+  else
+    msm_accumulate_kernel<C, false><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
+                                                                      bkt, heavy, queue, heavy_thr);
   PCD_CUDA(ctx, cudaGetLastError());
   size_t heavy_smem = MSM_HEAVY_THREADS * sizeof(XYZZ<C>);
   // heavy-bucket partial list: at most one partial per MSM_HEAVY_CHUNK entries plus one per bucket
@@ -480,13 +497,19 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   u32* hp_id = hp_count + 4;
   void* hp_sum = (char*)hp + 64 + ((hp_cap * 4 + 63) & ~(size_t)63);
   PCD_CUDA(ctx, cudaMemsetAsync(hp_count, 0, 4, st));
-  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                     (int)heavy_smem));
+  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)heavy_smem));
   PCD_CUDA(ctx, cudaFuncSetAttribute(msm_heavy_finish_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)heavy_smem));
   PCD_CUDA(ctx, cudaFuncSetAttribute(msm_sum_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem));
-  msm_accumulate_heavy_kernel<C><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
-      d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
+  if (shared)
+    msm_accumulate_heavy_kernel<C, true><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
+        d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
+  else
+    msm_accumulate_heavy_kernel<C, false><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
+        d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
   PCD_CUDA(ctx, cudaGetLastError());
   msm_heavy_finish_kernel<C><<<64, MSM_HEAVY_THREADS, heavy_smem, st>>>(heavy, hp_count, hp_id, hp_sum, bkt);
   PCD_CUDA(ctx, cudaGetLastError());

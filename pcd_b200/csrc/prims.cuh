@@ -41,6 +41,33 @@ PCD_D u32 addc(u32 a, u32 b) { u32 r; asm volatile("addc.u32 %0,%1,%2;" : "=r"(r
 PCD_D u32 sub_cc(u32 a, u32 b) { u32 r; asm volatile("sub.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PCD_D u32 subc_cc(u32 a, u32 b) { u32 r; asm volatile("subc.cc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
 PCD_D u32 subc(u32 a, u32 b) { u32 r; asm volatile("subc.u32 %0,%1,%2;" : "=r"(r) : "r"(a), "r"(b)); return r; }
+// (t1:t0) += a * b, the carry out of the 64-bit addition counted into c2.  One asm statement, carry flag
+// internal and not volatile: ptxas emits IMAD.WIDE.U32 (no .X, full rate) + IADD3.X and may schedule
+// independent instances freely.
+PCD_D void mac_carry(u32& t0, u32& t1, u32& c2, u32 a, u32 b) {
+  asm("mad.lo.cc.u32 %0,%3,%4,%0;\n\tmadc.hi.cc.u32 %1,%3,%4,%1;\n\taddc.u32 %2,%2,0;"
+      : "+r"(t0), "+r"(t1), "+r"(c2)
+      : "r"(a), "r"(b));
+}
+// (t1:t0) += a * b without a carry out (the caller knows it cannot overflow)
+PCD_D void mac(u32& t0, u32& t1, u32 a, u32 b) {
+  asm("mad.lo.cc.u32 %0,%2,%3,%0;\n\tmadc.hi.u32 %1,%2,%3,%1;" : "+r"(t0), "+r"(t1) : "r"(a), "r"(b));
+}
+// (t1:t0) = a * b
+PCD_D void mul_wide(u32& t0, u32& t1, u32 a, u32 b) {
+  asm("mul.lo.u32 %0,%2,%3;\n\tmul.hi.u32 %1,%2,%3;" : "=&r"(t0), "=r"(t1) : "r"(a), "r"(b));
+}
+// (t1:t0) += (x1:x0), the carry out counted into c2
+PCD_D void add64_carry(u32& t0, u32& t1, u32& c2, u32 x0, u32 x1) {
+  asm("add.cc.u32 %0,%0,%3;\n\taddc.cc.u32 %1,%1,%4;\n\taddc.u32 %2,%2,0;"
+      : "+r"(t0), "+r"(t1), "+r"(c2)
+      : "r"(x0), "r"(x1));
+}
+// (t1:t0) += (x1:x0) >> 30  (radix-2^30 column carry; the sum is known not to overflow 64 bits)
+PCD_D void add_shr30(u32& t0, u32& t1, u32 x0, u32 x1) {
+  const u32 s0 = __funnelshift_r(x0, x1, 30), s1 = x1 >> 30;
+  asm("add.cc.u32 %0,%0,%2;\n\taddc.u32 %1,%1,%3;" : "+r"(t0), "+r"(t1) : "r"(s0), "r"(s1));
+}
 }  // namespace prims
 
 #elif defined(PCDGPU_HOSTEMU)
@@ -55,5 +82,8 @@ u32 madc_lo_cc(u32, u32, u32); u32 madc_hi_cc(u32, u32, u32);
 u32 madc_lo(u32, u32, u32); u32 madc_hi(u32, u32, u32);
 u32 add_cc(u32, u32); u32 addc_cc(u32, u32); u32 addc(u32, u32);
 u32 sub_cc(u32, u32); u32 subc_cc(u32, u32); u32 subc(u32, u32);
+void mac_carry(u32&, u32&, u32&, u32, u32); void mac(u32&, u32&, u32, u32);
+void mul_wide(u32&, u32&, u32, u32); void add64_carry(u32&, u32&, u32&, u32, u32);
+void add_shr30(u32&, u32&, u32, u32);
 }  // namespace prims
 #endif

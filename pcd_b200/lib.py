@@ -12,7 +12,8 @@ import os
 import numpy as np
 
 HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(HERE, "libpcdgpu.so")
+# PCDGPU_LIB selects another build of the SAME library (A/B runs of kernel variants); there is no non-CUDA build
+LIB_PATH = os.environ.get("PCDGPU_LIB") or os.path.join(HERE, "libpcdgpu.so")
 
 # ids (include/pcdgpu.h)
 FIELD_R4, FIELD_Q4 = 0, 1

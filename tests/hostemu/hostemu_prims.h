@@ -21,4 +21,34 @@ inline u32 _bor(u64 t) { CC = (u32)(t >> 63) & 1; return (u32)t; }  // CC = borr
 inline u32 sub_cc(u32 a, u32 b) { return _bor((u64)a - b); }
 inline u32 subc_cc(u32 a, u32 b) { return _bor((u64)a - b - CC); }
 inline u32 subc(u32 a, u32 b) { return (u32)((u64)a - b - CC); }
+inline void mac_carry(u32& t0, u32& t1, u32& c2, u32 a, u32 b) {
+  u64 p = (u64)a * b;
+  u64 lo = (u64)t0 + (u32)p;
+  u64 hi = (u64)t1 + (u32)(p >> 32) + (lo >> 32);
+  t0 = (u32)lo;
+  t1 = (u32)hi;
+  c2 += (u32)(hi >> 32);
+}
+inline void mac(u32& t0, u32& t1, u32 a, u32 b) {
+  u64 v = (((u64)t1 << 32) | t0) + (u64)a * b;
+  t0 = (u32)v;
+  t1 = (u32)(v >> 32);
+}
+inline void mul_wide(u32& t0, u32& t1, u32 a, u32 b) {
+  u64 v = (u64)a * b;
+  t0 = (u32)v;
+  t1 = (u32)(v >> 32);
+}
+inline void add64_carry(u32& t0, u32& t1, u32& c2, u32 x0, u32 x1) {
+  u64 lo = (u64)t0 + x0;
+  u64 hi = (u64)t1 + x1 + (lo >> 32);
+  t0 = (u32)lo;
+  t1 = (u32)hi;
+  c2 += (u32)(hi >> 32);
+}
+inline void add_shr30(u32& t0, u32& t1, u32 x0, u32 x1) {
+  u64 v = (((u64)t1 << 32) | t0) + ((((u64)x1 << 32) | x0) >> 30);
+  t0 = (u32)v;
+  t1 = (u32)(v >> 32);
+}
 }  // namespace prims
