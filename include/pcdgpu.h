@@ -152,6 +152,32 @@ int pcdgpu_groth16_prove(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs
 /* same with z already in device memory (Montgomery elements) */
 int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
                              const void* r, const void* s, void* out_proof);
+/* ---- GM17 (ark-gm17: R1CStoSAP::witness_map + create_proof) --------------------------------------------
+ * Replaces `GM17::<E>::prove` as the reference binds it (/root/reference/tests/mnt4_gm17.rs:27-28,
+ * tests/mnt4_mix_groth16gm17.rs, tests/mnt4_mix_gm17groth16.rs), reached through IC::MainSNARK::prove /
+ * IC::HelpSNARK::prove (/root/reference/src/ec_cycle_pcd/mod.rs:171,179).  The R1CS handle is the one of
+ * pcdgpu_r1cs_upload; the SAP (2m + 2(ni - 1) + 1 rows, m + ni - 1 extra variables) is derived on the GPU.
+ * d1, d2, r: plain-integer scalars drawn by the caller in this order (create_random_proof), like r, s above.
+ * Query vectors are ark-gm17's ProvingKey fields: a_query, b_query (G2), c_query_2 hold one point per SAP
+ * variable (num_sap_vars = num_inputs + num_witness + m + num_inputs - 1), c_query_1 one per non-input SAP
+ * variable, g_gamma2_z_t h_len = n + 1 points (n = pcdgpu_sap_domain_size).  Proof layout = Groth16's. */
+typedef struct pcdgpu_gm17_pk pcdgpu_gm17_pk;
+/* size of GeneralEvaluationDomain::new(2m + 2(num_inputs - 1) + 1) over the pairing's scalar field; 0 if none */
+size_t pcdgpu_sap_domain_size(int pairing, size_t m, size_t num_inputs);
+/* R1CStoSAP::witness_map: full = the SAP assignment (num_sap_vars elements), h = n + 1 coefficients */
+int pcdgpu_sap_witness_map(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* z, const void* d1, const void* d2,
+                           void* full, void* h);
+int pcdgpu_gm17_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_sap_vars, size_t num_inputs, size_t h_len,
+                          const void* a_query, const void* b_query, const void* c_query_1, const void* c_query_2,
+                          const void* g_gamma2_z_t, const void* g_gamma_z, const void* h_gamma_z,
+                          const void* g_ab_gamma_z, const void* g_gamma2_z2, int precompute, pcdgpu_gm17_pk** out);
+void pcdgpu_gm17_pk_free(pcdgpu_gm17_pk* pk);
+int pcdgpu_gm17_prove(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgpu_r1cs* r1cs, const void* z, const void* d1,
+                      const void* d2, const void* r, void* out_proof);
+/* same with z already in device memory (Montgomery elements) */
+int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
+                          const void* d1, const void* d2, const void* r, void* out_proof);
+
 /* ark-serialize CanonicalSerialize of the proof (compressed points: x with flag bits 7 = "y is the
  * larger root", 6 = infinity on the last byte): 152 B (MNT4) / 190 B (MNT6).  out: >= 190 bytes. */
 int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affine, uint8_t* out, size_t* out_len);

@@ -189,3 +189,56 @@ def serialize_proof(pairing: int, proof_affine: np.ndarray) -> bytes:
     out = np.zeros(190, dtype=np.uint8)
     n = lib().orc_serialize_proof(pairing, _p(proof_affine), _p(out))
     return out[:n].tobytes()
+
+
+GM17_PK_FIELDS = ("a_query", "b_query", "c_query_1", "c_query_2", "g_gamma2_z_t", "g_gamma_z", "h_gamma_z",
+                  "g_ab_gamma_z", "g_gamma2_z2")
+
+
+def sap_domain_size(pairing: int, m: int, num_inputs: int):
+    dom = domain_size(pairing, 2 * m + 2 * (num_inputs - 1) + 1)
+    return dom[0] if dom else None
+
+
+def sap_witness_map(pairing: int, A, B, C, m: int, num_inputs: int, num_witness: int, z: np.ndarray, d1: np.ndarray,
+                    d2: np.ndarray, threads: int = 1):
+    """R1CStoSAP::witness_map; d1, d2 plain-integer limbs.  Returns (full SAP assignment, h with n + 1 coefficients)."""
+    keep, args = [], []
+    for M in (A, B, C):
+        k, a = _csr_args(M)
+        keep.append(k)
+        args += a
+    z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
+    n = sap_domain_size(pairing, m, num_inputs)
+    if n is None:
+        raise ValueError("domain too large for the field")
+    d1m = to_mont(pairing, np.ascontiguousarray(d1, dtype=np.uint64).reshape(1, 5))
+    d2m = to_mont(pairing, np.ascontiguousarray(d2, dtype=np.uint64).reshape(1, 5))
+    full = np.zeros((num_inputs + num_witness + m + num_inputs - 1, 5), dtype=np.uint64)
+    h = np.zeros((n + 1, 5), dtype=np.uint64)
+    rc = lib().orc_sap_witness_map(pairing, *args, ctypes.c_size_t(m), ctypes.c_size_t(num_inputs),
+                                   ctypes.c_size_t(num_witness), _p(z), _p(d1m), _p(d2m), _p(full), _p(h), threads)
+    if rc < 0:
+        raise ValueError("domain too large for the field")
+    return full, h
+
+
+def gm17_prove(pairing: int, pk: dict, A, B, C, m: int, num_inputs: int, num_witness: int, z: np.ndarray,
+               d1: np.ndarray, d2: np.ndarray, r: np.ndarray, threads: int = 1) -> np.ndarray:
+    """pk: dict of numpy uint64 arrays keyed by GM17_PK_FIELDS; d1, d2, r plain-integer limbs.  Returns the proof as
+    affine limbs A || B || C."""
+    arrs = [np.ascontiguousarray(pk[k], dtype=np.uint64) for k in GM17_PK_FIELDS]
+    ptrs = (ctypes.c_void_p * 9)(*[a.ctypes.data for a in arrs])
+    keep, args = [], []
+    for M in (A, B, C):
+        k, a = _csr_args(M)
+        keep.append(k)
+        args += a
+    z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
+    d1, d2, r = (np.ascontiguousarray(x, dtype=np.uint64) for x in (d1, d2, r))
+    out = np.zeros(40 if pairing == 0 else 50, dtype=np.uint64)
+    rc = lib().orc_gm17_prove(pairing, ptrs, *args, ctypes.c_size_t(m), ctypes.c_size_t(num_inputs),
+                              ctypes.c_size_t(num_witness), _p(z), _p(d1), _p(d2), _p(r), _p(out), threads)
+    if rc < 0:
+        raise ValueError("gm17_prove failed (domain too large)")
+    return out

@@ -14,8 +14,10 @@ const MsmOps* msm_ops(int curve) {
   }
   return nullptr;
 }
-static int g1_of(int pairing) { return pairing == PCDGPU_MNT4_298 ? PCDGPU_MNT4_G1 : PCDGPU_MNT6_G1; }
-static int g2_of(int pairing) { return pairing == PCDGPU_MNT4_298 ? PCDGPU_MNT4_G2 : PCDGPU_MNT6_G2; }
+int pcd_g1_of(int pairing) { return pairing == PCDGPU_MNT4_298 ? PCDGPU_MNT4_G1 : PCDGPU_MNT6_G1; }
+int pcd_g2_of(int pairing) { return pairing == PCDGPU_MNT4_298 ? PCDGPU_MNT4_G2 : PCDGPU_MNT6_G2; }
+static int g1_of(int pairing) { return pcd_g1_of(pairing); }
+static int g2_of(int pairing) { return pcd_g2_of(pairing); }
 
 static const int MSM_BITS = 298;
 int msm_num_windows_c(int c) { return (MSM_BITS + 1 + c - 1) / c; }
@@ -306,7 +308,8 @@ void pcdgpu_bases_free(pcdgpu_bases* b) {
 
 // MSM over points [offset, offset + n) of a resident vector followed by its last n_extra points
 // (the per-proof constant pairs appended at key upload) with plain scalars d_extra.
-static int bases_msm(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* d_scalars, int scalars_mont,
+}  // extern "C"
+int bases_msm(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* d_scalars, int scalars_mont,
                      size_t n, const void* d_extra, size_t n_extra, void* d_out_xyzz) {
   const MsmOps* ops = msm_ops(b->curve);
   size_t avail = b->n - n_extra;  // ordinary points
@@ -323,6 +326,7 @@ static int bases_msm(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, cons
   return ops->run(ctx, (const char*)b->points + offset * ops->affine_bytes, d_scalars, scalars_mont, n, d_extra,
                   n_extra, plan_plain(ctx, n + n_extra), d_out_xyzz);
 }
+extern "C" {
 
 int pcdgpu_msm_bases_dev(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* d_scalars, int scalars_mont,
                          size_t n, void* d_out_xyzz) {

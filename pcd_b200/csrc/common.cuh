@@ -153,7 +153,8 @@ enum {
   SLOT_CUB = 13,
   SLOT_MSM_HP = 14,  // heavy-bucket partial sums
   SLOT_CUB2 = 15,
-  SLOT_NTT_MIXED = 16  // ping-pong buffer of a mixed-radix transform
+  SLOT_NTT_MIXED = 16,  // ping-pong buffer of a mixed-radix transform
+  SLOT_SAP_FULL = 17    // GM17: the SAP assignment (z and the extra variables)
 };
 
 template <class T>

@@ -10,25 +10,6 @@
 #include "msm_ops.cuh"
 #include "ntt.cuh"
 
-template <class F>
-__device__ __forceinline__ F ld10(const u32* g, size_t idx) {
-  const uint2* p = reinterpret_cast<const uint2*>(g + idx * 10);
-  F r;
-#pragma unroll
-  for (int i = 0; i < 5; i++) {
-    uint2 v = __ldg(p + i);
-    r.l[2 * i] = v.x;
-    r.l[2 * i + 1] = v.y;
-  }
-  return r;
-}
-template <class F>
-__device__ __forceinline__ void st10(u32* g, size_t idx, const F& a) {
-  uint2* p = reinterpret_cast<uint2*>(g + idx * 10);
-#pragma unroll
-  for (int i = 0; i < 5; i++) p[i] = make_uint2(a.l[2 * i], a.l[2 * i + 1]);
-}
-
 // ---- CSR sparse matrix x assignment (ark-groth16 evaluate_constraint) ---------------------------
 // blockIdx.y selects the matrix.  out[i] = <M_i, z> for i < m; a[m + j] = z[j] for the instance
 // variables (the rows that make the QAP's A polynomials linearly independent); 0 elsewhere.

@@ -36,6 +36,44 @@ struct pcdgpu_pk {
   pcdgpu_bases *a_query, *b_g1_query, *b_g2_query, *h_query, *l_query;
 };
 
+struct pcdgpu_gm17_pk {
+  pcdgpu_ctx* ctx;
+  int pairing;
+  size_t num_sap_vars, num_inputs, h_len;
+  // query vectors with their constant points appended (see pcdgpu_gm17_pk_upload)
+  pcdgpu_bases *a_query, *b_query, *c_query_1, *c_query_2, *g_gamma2_z_t;
+};
+
+#if defined(__CUDACC__)
+template <class F>
+__device__ __forceinline__ F ld10(const u32* g, size_t idx) {
+  const uint2* p = reinterpret_cast<const uint2*>(g + idx * 10);
+  F r;
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    uint2 v = __ldg(p + i);
+    r.l[2 * i] = v.x;
+    r.l[2 * i + 1] = v.y;
+  }
+  return r;
+}
+template <class F>
+__device__ __forceinline__ void st10(u32* g, size_t idx, const F& a) {
+  uint2* p = reinterpret_cast<uint2*>(g + idx * 10);
+#pragma unroll
+  for (int i = 0; i < 5; i++) p[i] = make_uint2(a.l[2 * i], a.l[2 * i + 1]);
+}
+
+#endif
+
+// shared by api.cu and gm17.cu
+int pcd_g1_of(int pairing);
+int pcd_g2_of(int pairing);
+// MSM over points [offset, offset + n) of a resident vector followed by its last n_extra points (the
+// per-proof constant pairs appended at key upload) with plain scalars d_extra; result: one xyzz point
+int bases_msm(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void* d_scalars, int scalars_mont, size_t n,
+              const void* d_extra, size_t n_extra, void* d_out_xyzz);
+
 // a, b, c <- matrices x z; h = coset_ifft((coset_fft(ifft a) * coset_fft(ifft b) - coset_fft(ifft c)) / Z).
 // *d_h points into the context's scratch (n elements, Montgomery form).
 int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h);

@@ -35,6 +35,8 @@ EXPORTS = [
     "pcdgpu_r1cs_upload", "pcdgpu_r1cs_free", "pcdgpu_r1cs_domain_size", "pcdgpu_witness_map", "pcdgpu_pk_upload",
     "pcdgpu_pk_free", "pcdgpu_groth16_prove", "pcdgpu_groth16_prove_dev", "pcdgpu_serialize_proof",
     "pcdgpu_profile_enable", "pcdgpu_profile_read", "pcdgpu_profile_timeline", "pcdgpu_bench_imad",
+    "pcdgpu_sap_domain_size", "pcdgpu_sap_witness_map", "pcdgpu_gm17_pk_upload", "pcdgpu_gm17_pk_free",
+    "pcdgpu_gm17_prove", "pcdgpu_gm17_prove_dev",
 ]
 
 
@@ -104,6 +106,14 @@ def load():
     lib.pcdgpu_profile_timeline.argtypes = [vp, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double),
                                             ctypes.POINTER(ctypes.c_int), sz, ctypes.POINTER(sz)]
     lib.pcdgpu_bench_imad.argtypes = [vp, ci, ci, ctypes.POINTER(ctypes.c_double), ctypes.POINTER(ctypes.c_double)]
+    lib.pcdgpu_sap_domain_size.argtypes = [ci, sz, sz]
+    lib.pcdgpu_sap_domain_size.restype = sz
+    lib.pcdgpu_sap_witness_map.argtypes = [vp] * 7
+    lib.pcdgpu_gm17_pk_upload.argtypes = [vp, ci, sz, sz, sz] + [vp] * 9 + [ci, ctypes.POINTER(vp)]
+    lib.pcdgpu_gm17_pk_free.argtypes = [vp]
+    lib.pcdgpu_gm17_pk_free.restype = None
+    lib.pcdgpu_gm17_prove.argtypes = [vp] * 8
+    lib.pcdgpu_gm17_prove_dev.argtypes = [vp] * 8
     _lib = lib
     return lib
 

@@ -182,3 +182,139 @@ class Groth16:
     def serialize(self, proof: Proof) -> bytes:
         """ark-serialize canonical (compressed) bytes: 152 B (MNT4-298) / 190 B (MNT6-298)."""
         return self.ctx.serialize_proof(self.pairing, proof.affine_limbs())
+
+
+# ---- GM17 ------------------------------------------------------------------------------------------------
+@dataclass
+class GM17ProvingKey:
+    """ark-gm17 `ProvingKey<E>` (the fields the prover reads; vk is not needed to prove)."""
+
+    pairing: int
+    a_query: np.ndarray        # G1, one per SAP variable
+    b_query: np.ndarray        # G2, one per SAP variable
+    c_query_1: np.ndarray      # G1, non-input SAP variables
+    c_query_2: np.ndarray      # G1, one per SAP variable
+    g_gamma_z: np.ndarray      # G1
+    h_gamma_z: np.ndarray      # G2
+    g_ab_gamma_z: np.ndarray   # G1
+    g_gamma2_z2: np.ndarray    # G1
+    g_gamma2_z_t: np.ndarray   # G1, SAP domain size + 1
+
+
+class GM17ProverIndex:
+    """Device-resident GM17 proving key + the R1CS matrices the SAP is derived from."""
+
+    def __init__(self, ctx: L.Context, pk: GM17ProvingKey, cm: ConstraintMatrices, precompute: bool = False):
+        if pk.pairing != cm.pairing:
+            raise ValueError("proving key and constraint matrices are over different pairings")
+        self.ctx, self.pairing = ctx, pk.pairing
+        self.num_inputs = cm.num_instance_variables
+        self.num_witness = cm.num_witness_variables
+        self.num_vars = self.num_inputs + self.num_witness
+        m = cm.num_constraints
+        self.num_sap_vars = self.num_vars + m + self.num_inputs - 1
+        g1 = L.G1_OF[pk.pairing]
+        lib = ctx.lib
+        keep = []
+
+        def arr(a, dt, width=None):
+            a = np.ascontiguousarray(a, dtype=dt)
+            if width:
+                a = a.reshape(-1, width)
+            keep.append(a)
+            return ctypes.c_void_p(a.ctypes.data)
+
+        args = []
+        for (ptr, col, val) in (cm.a, cm.b, cm.c):
+            args += [arr(ptr, np.uint32), arr(col, np.uint32), arr(val, np.uint64)]
+        h = ctypes.c_void_p()
+        ctx._check(lib.pcdgpu_r1cs_upload(ctx.h, pk.pairing, m, self.num_inputs, self.num_witness, *args,
+                                          ctypes.byref(h)))
+        self.r1cs = h
+        self.domain_size = lib.pcdgpu_sap_domain_size(pk.pairing, m, self.num_inputs)
+        if not self.domain_size:
+            lib.pcdgpu_r1cs_free(h)
+            raise L.PcdGpuError(-6, "no evaluation domain large enough for the SAP")
+        a_q = np.ascontiguousarray(pk.a_query, dtype=np.uint64).reshape(-1, L.AFFINE_LIMBS[g1])
+        if a_q.shape[0] != self.num_sap_vars:
+            lib.pcdgpu_r1cs_free(h)
+            raise ValueError("a_query has %d points for %d SAP variables" % (a_q.shape[0], self.num_sap_vars))
+        t_q = np.ascontiguousarray(pk.g_gamma2_z_t, dtype=np.uint64).reshape(-1, L.AFFINE_LIMBS[g1])
+        pkh = ctypes.c_void_p()
+        ctx._check(lib.pcdgpu_gm17_pk_upload(
+            ctx.h, pk.pairing, self.num_sap_vars, self.num_inputs, t_q.shape[0], arr(a_q, np.uint64),
+            arr(pk.b_query, np.uint64), arr(pk.c_query_1, np.uint64), arr(pk.c_query_2, np.uint64), arr(t_q, np.uint64),
+            arr(pk.g_gamma_z, np.uint64), arr(pk.h_gamma_z, np.uint64), arr(pk.g_ab_gamma_z, np.uint64),
+            arr(pk.g_gamma2_z2, np.uint64), int(precompute), ctypes.byref(pkh)))
+        self.pk = pkh
+
+    def close(self):
+        if getattr(self, "pk", None) and self.ctx.h:
+            self.ctx.lib.pcdgpu_gm17_pk_free(self.pk)
+            self.ctx.lib.pcdgpu_r1cs_free(self.r1cs)
+        self.pk = None
+        self.r1cs = None
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+
+class GM17:
+    """`GM17<E>` as the reference binds it (/root/reference/tests/mnt4_gm17.rs:27-28): `prove` and its building
+    blocks on the GPU; setup / verify stay with the CPU implementation on the Rust side of the boundary."""
+
+    def __init__(self, ctx: L.Context, pairing: int):
+        self.ctx, self.pairing = ctx, pairing
+
+    def index(self, pk: GM17ProvingKey, cm: ConstraintMatrices, precompute: bool = False) -> GM17ProverIndex:
+        return GM17ProverIndex(self.ctx, pk, cm, precompute)
+
+    def witness_map(self, index: GM17ProverIndex, z: np.ndarray, d1: np.ndarray, d2: np.ndarray):
+        """R1CStoSAP::witness_map -> (full SAP assignment, the n + 1 coefficients of H); d1, d2 plain-integer limbs."""
+        z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
+        if z.shape[0] != index.num_vars:
+            raise ValueError("assignment has %d elements for %d variables" % (z.shape[0], index.num_vars))
+        d1 = np.ascontiguousarray(d1, dtype=np.uint64)
+        d2 = np.ascontiguousarray(d2, dtype=np.uint64)
+        full = np.zeros((index.num_sap_vars, 5), dtype=np.uint64)
+        h = np.zeros((index.domain_size + 1, 5), dtype=np.uint64)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self.ctx._check(self.ctx.lib.pcdgpu_sap_witness_map(self.ctx.h, index.r1cs, vp(z), vp(d1), vp(d2), vp(full), vp(h)))
+        return full, h
+
+    def create_proof(self, index: GM17ProverIndex, z: np.ndarray, d1: np.ndarray, d2: np.ndarray, r: np.ndarray) -> Proof:
+        """ark-gm17 `create_proof(circuit, pk, d1, d2, r)`; d1, d2, r plain-integer limbs."""
+        z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
+        if z.shape[0] != index.num_vars:
+            raise ValueError("assignment has %d elements for %d variables" % (z.shape[0], index.num_vars))
+        d1, d2, r = (np.ascontiguousarray(x, dtype=np.uint64) for x in (d1, d2, r))
+        g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
+        out = np.zeros(2 * g1 + g2, dtype=np.uint64)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self.ctx._check(self.ctx.lib.pcdgpu_gm17_prove(self.ctx.h, index.pk, index.r1cs, vp(z), vp(d1), vp(d2), vp(r),
+                                                       vp(out)))
+        return Proof(self.pairing, out[:g1].copy(), out[g1:g1 + g2].copy(), out[g1 + g2:].copy())
+
+    def create_proof_dev(self, index: GM17ProverIndex, d_z: int, d1: np.ndarray, d2: np.ndarray, r: np.ndarray) -> Proof:
+        d1, d2, r = (np.ascontiguousarray(x, dtype=np.uint64) for x in (d1, d2, r))
+        g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
+        out = np.zeros(2 * g1 + g2, dtype=np.uint64)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self.ctx._check(self.ctx.lib.pcdgpu_gm17_prove_dev(self.ctx.h, index.pk, index.r1cs, ctypes.c_void_p(d_z), vp(d1),
+                                                           vp(d2), vp(r), vp(out)))
+        return Proof(self.pairing, out[:g1].copy(), out[g1:g1 + g2].copy(), out[g1 + g2:].copy())
+
+    def prove(self, index: GM17ProverIndex, z: np.ndarray, rng: Callable[[int], np.ndarray]) -> Proof:
+        """`SNARK::prove(pk, circuit, rng)`: draws d1, d2, r in this order (`create_random_proof`), then proves."""
+        f = L.SCALAR_FIELD_OF[self.pairing]
+        d1 = rng(f)
+        d2 = rng(f)
+        r = rng(f)
+        return self.create_proof(index, z, d1, d2, r)
+
+    def serialize(self, proof: Proof) -> bytes:
+        """ark-serialize canonical (compressed) bytes of `Proof {a, b, c}`: 152 B (MNT4-298) / 190 B (MNT6-298)."""
+        return self.ctx.serialize_proof(self.pairing, proof.affine_limbs())

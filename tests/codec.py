@@ -76,3 +76,17 @@ def random_field_elems(n, field, seed, plain=False):
 def csr_from_golden(g):
     return (np.array(g["ptr"], dtype=np.uint32), np.array(g["col"], dtype=np.uint32),
             hex_to_u64(g["val"], 5) if g["val"] else np.zeros((0, 5), dtype=np.uint64))
+
+
+GM17_G2_KEYS = ("b_query", "h_gamma_z")
+GM17_SINGLE = ("g_gamma_z", "h_gamma_z", "g_ab_gamma_z", "g_gamma2_z2")
+
+
+def gm17_pk_from_golden(case):
+    """golden gm17.json key -> dict of numpy arrays keyed like c_oracle.GM17_PK_FIELDS"""
+    pid = case["pairing"]
+    g1, g2 = G1_OF[pid], G2_OF[pid]
+    pk = {k: hex_to_u64(v, POINT_LIMBS[g2 if k in GM17_G2_KEYS else g1]) for k, v in case["pk"].items()}
+    for k in GM17_SINGLE:
+        pk[k] = pk[k][0]
+    return pk

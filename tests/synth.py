@@ -120,3 +120,49 @@ def trapdoor_proof(inst, r, s):
     B = co.fixed_base_mul(g2, generator_limbs(g2), codec.ints_to_limbs([b_log]), 1)[0]
     Cc = co.fixed_base_mul(g1, generator_limbs(g1), codec.ints_to_limbs([c_log]), 1)[0]
     return np.concatenate([A, B, Cc])
+
+
+def make_gm17_instance(pairing_id, m, seed=20261017, bitlike=0.3, num_inputs=2):
+    """Satisfiable R1CS + assignment + GM17 key with known trapdoor (c_oracle.GM17_PK_FIELDS as numpy arrays)."""
+    pairing = PAIRINGS[pairing_id]
+    fp = pairing.fr
+    p = fp.p
+    r1cs, z = o.synthetic_r1cs(fp, m, num_inputs=num_inputs, seed=seed, bitlike=bitlike)
+    t = o.gm17_setup_scalars(pairing, r1cs, seed=seed + 100)
+    g1, g2 = codec.G1_OF[pairing_id], codec.G2_OF[pairing_id]
+    G1, G2 = generator_limbs(g1), generator_limbs(g2)
+    sc = lambda vals: codec.ints_to_limbs(vals)
+    gam, zt, ab = t["gamma"], t["zt"], (t["alpha"] + t["beta"]) % p
+    pk = {
+        "a_query": co.fixed_base_mul(g1, G1, sc(t["a_sc"])),
+        "b_query": co.fixed_base_mul(g2, G2, sc(t["a_sc"])),
+        "c_query_1": co.fixed_base_mul(g1, G1, sc(t["c1_sc"])),
+        "c_query_2": co.fixed_base_mul(g1, G1, sc(t["c2_sc"])),
+        "g_gamma2_z_t": co.fixed_base_mul(g1, G1, sc(t["gzt_sc"])),
+        "g_gamma_z": co.fixed_base_mul(g1, G1, sc([gam * zt % p]))[0],
+        "h_gamma_z": co.fixed_base_mul(g2, G2, sc([gam * zt % p]))[0],
+        "g_ab_gamma_z": co.fixed_base_mul(g1, G1, sc([ab * gam % p * zt % p]))[0],
+        "g_gamma2_z2": co.fixed_base_mul(g1, G1, sc([gam * gam % p * zt % p * zt % p]))[0],
+    }
+    A, B, C = r1cs_to_csr(r1cs)
+    return dict(pairing=pairing_id, r1cs=r1cs, z_int=z, z=mont_limbs(z, fp), A=A, B=B, C=C, pk=pk, trapdoor=t,
+                m=m, num_inputs=r1cs.num_inputs, num_witness=r1cs.num_witness)
+
+
+def gm17_trapdoor_proof(inst, d1, d2, r):
+    """The GM17 proof every correct prover must output for this randomness, from the verification equations in
+    the exponent (oracle gm17_trapdoor_check): a = gamma (u + (r + d1) Z), b = a, c = (a + alpha)(a + beta) -
+    alpha beta - gamma psi.  Affine limbs A || B || C."""
+    t, r1cs, z = inst["trapdoor"], inst["r1cs"], inst["z_int"]
+    pid = inst["pairing"]
+    p = PAIRINGS[pid].fr.p
+    full = o.sap_extend_assignment(r1cs, z)
+    u = sum(x * y for x, y in zip(full, t["At"])) % p
+    a_log = t["gamma"] * ((u + (r + d1) * t["zt"]) % p) % p
+    psi = sum(z[i] * t["vk_sc"][i] for i in range(r1cs.num_inputs)) % p
+    c_log = ((a_log + t["alpha"]) * (a_log + t["beta"]) - t["alpha"] * t["beta"] - t["gamma"] * psi) % p
+    g1, g2 = codec.G1_OF[pid], codec.G2_OF[pid]
+    A = co.fixed_base_mul(g1, generator_limbs(g1), codec.ints_to_limbs([a_log]), 1)[0]
+    B = co.fixed_base_mul(g2, generator_limbs(g2), codec.ints_to_limbs([a_log]), 1)[0]
+    Cc = co.fixed_base_mul(g1, generator_limbs(g1), codec.ints_to_limbs([c_log]), 1)[0]
+    return np.concatenate([A, B, Cc])

@@ -286,3 +286,66 @@ def test_groth16_mixed_radix_domain(ctx):
     ref_h = co.witness_map(1, inst["A"], inst["B"], inst["C"], m, inst["num_inputs"], inst["z"], threads=16)
     assert np.array_equal(h, ref_h)
     idx.close()
+
+
+# ---- GM17 ----------------------------------------------------------------------------------
+def _gm17_index(ctx, inst, precompute=False):
+    import pcd_b200
+    pk = pcd_b200.GM17ProvingKey(pairing=inst["pairing"], **inst["pk"])
+    cm = pcd_b200.ConstraintMatrices(inst["pairing"], inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"],
+                                     inst["C"])
+    g = pcd_b200.GM17(ctx, inst["pairing"])
+    return g, g.index(pk, cm, precompute)
+
+
+def test_gm17_golden(ctx):
+    for case in codec.load("gm17"):
+        pid = case["pairing"]
+        inst = dict(pairing=pid, pk=codec.gm17_pk_from_golden(case), num_inputs=case["num_inputs"],
+                    num_witness=case["num_witness"], A=codec.csr_from_golden(case["A"]),
+                    B=codec.csr_from_golden(case["B"]), C=codec.csr_from_golden(case["C"]))
+        z = codec.hex_to_u64(case["z"], 5)
+        d1, d2, r = (codec.hex_to_u64(case[k]) for k in ("d1", "d2", "r"))
+        for pre in (False, True):
+            g, idx = _gm17_index(ctx, inst, pre)
+            assert idx.domain_size == case["domain_size"]
+            full, h = g.witness_map(idx, z, d1, d2)
+            assert codec.u64_to_hex(full) == case["full"]
+            assert codec.u64_to_hex(h) == case["h"]
+            proof = g.create_proof(idx, z, d1, d2, r)
+            assert codec.u64_to_hex(proof.affine_limbs()) == case["proof_affine"]
+            assert g.serialize(proof).hex() == case["proof_bytes"]
+            idx.close()
+
+
+@pytest.mark.parametrize("pairing,m,ni", [(0, 1000, 2), (1, 1000, 4), (0, (1 << 12) - 3, 3), (1, (1 << 11) + 5, 2)])
+def test_gm17_vs_oracle_and_trapdoor(ctx, pairing, m, ni):
+    inst = synth.make_gm17_instance(pairing, m, seed=700 + m, bitlike=0.4, num_inputs=ni)
+    p = codec.FIELD_P[pairing]
+    d1, d2, r = pow(3, 201, p), pow(5, 187, p), pow(7, 173, p)
+    d1l, d2l, rl = (codec.int_to_limbs(x) for x in (d1, d2, r))
+    g, idx = _gm17_index(ctx, inst)
+    full, h = g.witness_map(idx, inst["z"], d1l, d2l)
+    rfull, rh = co.sap_witness_map(pairing, inst["A"], inst["B"], inst["C"], m, inst["num_inputs"], inst["num_witness"],
+                                   inst["z"], d1l, d2l, 8)
+    assert np.array_equal(full, rfull)
+    assert np.array_equal(h, rh)
+    proof = g.create_proof(idx, inst["z"], d1l, d2l, rl)
+    ref = co.gm17_prove(pairing, inst["pk"], inst["A"], inst["B"], inst["C"], m, inst["num_inputs"], inst["num_witness"],
+                        inst["z"], d1l, d2l, rl, threads=8)
+    assert np.array_equal(proof.affine_limbs(), ref)
+    assert np.array_equal(proof.affine_limbs(), synth.gm17_trapdoor_proof(inst, d1, d2, r))
+    assert g.serialize(proof) == co.serialize_proof(pairing, ref)
+    idx.close()
+    g2, idx2 = _gm17_index(ctx, inst, precompute=True)
+    assert np.array_equal(g2.create_proof(idx2, inst["z"], d1l, d2l, rl).affine_limbs(), ref)
+    # the reference's rng contract: prove() draws d1, d2, r in this order
+    draws = iter([d1l, d2l, rl])
+    assert np.array_equal(g2.prove(idx2, inst["z"], lambda f: next(draws)).affine_limbs(), ref)
+    # serialised streams (no lanes) give the same bytes
+    ctx.set_concurrency(False)
+    try:
+        assert np.array_equal(g2.create_proof(idx2, inst["z"], d1l, d2l, rl).affine_limbs(), ref)
+    finally:
+        ctx.set_concurrency(True)
+    idx2.close()

@@ -79,3 +79,33 @@ def test_groth16_golden():
         assert codec.u64_to_hex(proof) == case["proof_affine"]
         assert co.serialize_proof(pid, proof).hex() == case["proof_bytes"]
         assert len(case["proof_bytes"]) // 2 == (152 if pid == 0 else 190)
+
+
+# ---- GM17: C++ oracle vs the Python oracle's golden vectors and the trapdoor check ----------
+def test_gm17_golden():
+    for case in codec.load("gm17"):
+        pid = case["pairing"]
+        A, B, C = (codec.csr_from_golden(case[k]) for k in "ABC")
+        z = codec.hex_to_u64(case["z"], 5)
+        d1, d2, r = (codec.hex_to_u64(case[k]) for k in ("d1", "d2", "r"))
+        assert co.sap_domain_size(pid, case["m"], case["num_inputs"]) == case["domain_size"]
+        full, h = co.sap_witness_map(pid, A, B, C, case["m"], case["num_inputs"], case["num_witness"], z, d1, d2, 2)
+        assert codec.u64_to_hex(full) == case["full"]
+        assert codec.u64_to_hex(h) == case["h"]
+        pk = codec.gm17_pk_from_golden(case)
+        proof = co.gm17_prove(pid, pk, A, B, C, case["m"], case["num_inputs"], case["num_witness"], z, d1, d2, r, 2)
+        assert codec.u64_to_hex(proof) == case["proof_affine"]
+        assert co.serialize_proof(pid, proof).hex() == case["proof_bytes"]
+
+
+@pytest.mark.parametrize("pairing", [0, 1])
+def test_gm17_trapdoor(pairing):
+    """a 300-constraint GM17 proof from the C++ oracle satisfies the verification equations in the exponent"""
+    import synth
+    inst = synth.make_gm17_instance(pairing, 300, seed=41 + pairing, bitlike=0.4, num_inputs=3)
+    p = codec.FIELD_P[pairing]
+    d1, d2, r = pow(3, 150, p), pow(5, 140, p), pow(7, 130, p)
+    proof = co.gm17_prove(pairing, inst["pk"], inst["A"], inst["B"], inst["C"], 300, inst["num_inputs"],
+                          inst["num_witness"], inst["z"], codec.int_to_limbs(d1), codec.int_to_limbs(d2),
+                          codec.int_to_limbs(r), threads=4)
+    assert np.array_equal(proof, synth.gm17_trapdoor_proof(inst, d1, d2, r))

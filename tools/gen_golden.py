@@ -198,10 +198,57 @@ def gen_groth16():
     return out
 
 
+def gen_gm17():
+    """GM17 proofs (oracle/pcd_oracle.py gm17_*): key with a known trapdoor, the SAP witness map outputs and the
+    proof, each checked against GM17's verification equations in the exponent before it is written."""
+    out = []
+    for pid, pairing in ((0, o.MNT4), (1, o.MNT6)):
+        fp = pairing.fr
+        p = fp.p
+        g1fp = CURVES[0 if pid == 0 else 2][1]
+        for (m, ni, bitlike, seed) in ((5, 2, 0.0, 21), (11, 3, 0.4, 22)):
+            r1cs, z = o.synthetic_r1cs(fp, m, num_inputs=ni, seed=seed, bitlike=bitlike)
+            assert r1cs.is_satisfied(z)
+            pk = o.gm17_setup(pairing, r1cs, seed=seed + 100)
+            rng = o.SplitMix64(seed + 200)
+            d1, d2, r = rng.field(p), rng.field(p), rng.field(p)
+            full, h, d = o.sap_witness_map(r1cs, z, d1, d2)
+            proof = o.gm17_prove(pk, r1cs, z, d1, d2, r)
+            assert proof == o.gm17_prove(pk, r1cs, z, d1, d2, r, msm=o.msm_naive)
+            assert o.gm17_trapdoor_check(pk, r1cs, z, d1, d2, r, proof)
+            G1, G2 = pairing.g1, pairing.g2
+            ph1 = lambda P: point_hex(G1, g1fp, P)
+            ph2 = lambda P: point_hex(G2, g1fp, P)
+            out.append({
+                "pairing": pid, "m": m, "num_inputs": r1cs.num_inputs, "num_witness": r1cs.num_witness,
+                "domain_size": d.size,
+                "A": csr_of(r1cs.A, fp), "B": csr_of(r1cs.B, fp), "C": csr_of(r1cs.C, fp),
+                "z": "".join(mont_hex(x, fp) for x in z),
+                "d1": scalar_hex(d1), "d2": scalar_hex(d2), "r": scalar_hex(r),
+                "full": "".join(mont_hex(x, fp) for x in full),
+                "h": "".join(mont_hex(x, fp) for x in h),
+                "pk": {
+                    "a_query": "".join(ph1(P) for P in pk.a_query),
+                    "b_query": "".join(ph2(P) for P in pk.b_query),
+                    "c_query_1": "".join(ph1(P) for P in pk.c_query_1),
+                    "c_query_2": "".join(ph1(P) for P in pk.c_query_2),
+                    "g_gamma2_z_t": "".join(ph1(P) for P in pk.g_gamma2_z_t),
+                    "g_gamma_z": ph1(pk.g_gamma_z), "h_gamma_z": ph2(pk.h_gamma_z),
+                    "g_ab_gamma_z": ph1(pk.g_ab_gamma_z), "g_gamma2_z2": ph1(pk.g_gamma2_z2),
+                },
+                "proof_affine": ph1(proof[0]) + ph2(proof[1]) + ph1(proof[2]),
+                "proof_bytes": o.serialize_proof(pairing, proof).hex(),
+            })
+    return out
+
+
 def main():
     o.self_check()
     os.makedirs(OUT, exist_ok=True)
-    for name, fn in (("fields", gen_fields), ("ntt", gen_ntt), ("msm", gen_msm), ("groth16", gen_groth16)):
+    for name, fn in (("fields", gen_fields), ("ntt", gen_ntt), ("msm", gen_msm), ("groth16", gen_groth16),
+                     ("gm17", gen_gm17)):
+        if len(sys.argv) > 1 and name not in sys.argv[1:]:
+            continue
         data = fn()
         with open(os.path.join(OUT, name + ".json"), "w") as f:
             json.dump(data, f, indent=0)
