@@ -189,8 +189,9 @@ def run_gpu(args, rank, local_rank, world):
 
     # the integer roof: independent accumulate-form IMAD.WIDE.U32 (fmaheavy pipe, 32 lanes/clk/SM on B200 -- the
     # first version of this microbenchmark let ptxas hoist the products and measured 64-bit ADDS instead)
-    imad_peak, _ = ctx.bench_imad(0, 4000)
-    imad_chain, _ = ctx.bench_imad(3, 4000)  # the same multiply-adds as carry chains (.X form)
+    imad_indep, _ = ctx.bench_imad(0, 4000)
+    imad_chain, _ = ctx.bench_imad(3, 4000)  # the same multiply-adds as carry chains (.X form): same pipe, same rate
+    imad_peak = max(imad_indep, imad_chain)
 
     # ---- workload -----------------------------------------------------------------------------------
     log_n = args.log_n
@@ -331,6 +332,8 @@ def run_gpu(args, rank, local_rank, world):
     if rank == 0 and not args.no_pcd_step:
         idx.close()
         extra["pcd_step"] = pcd_step_figure(args, ctx, dev, stream, log)
+    if rank == 0 and not args.no_gm17:
+        extra["gm17"] = gm17_figure(args, ctx, dev, stream, log)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         sample_log = min(log_n, args.cpu_sample_log_n)
@@ -368,7 +371,8 @@ def run_gpu(args, rank, local_rank, world):
         "frac": achieved / (imad_peak / 1e12), "traffic": traffic,
         "traffic_note": "DRAM bytes of one launch from the committed ncu capture (2^20 points, uniform scalars); "
                         "algorithmic: 80 B per gathered point + 4 B per entry",
-        "peak_source": "measured live: independent accumulate-form IMAD.WIDE.U32 on the fmaheavy pipe (carry-chain form: %.2f TIMAD/s)" % (imad_chain / 1e12),
+        "peak_source": "measured live: IMAD.WIDE.U32 issue rate of the fmaheavy pipe (32 lanes/clk/SM), max of the "
+                       "independent accumulate form (%.2f T/s) and the carry-chain form (%.2f T/s)" % (imad_indep / 1e12, imad_chain / 1e12),
         "launch_ms_avg": prof["ms"][dom] / max(prof["spans"][dom], 1),
         "work": "bucket entries x %d Montgomery products (XYZZ mixed add 8M+2S) x %d IMAD" % (MADD_MODMULS[deg], MODMUL_IMADS),
     }
@@ -394,7 +398,7 @@ def run_gpu(args, rank, local_rank, world):
         "serialized_ms_per_step": ms_serial / args.steps,
         "kernel_timing_note": "kernel_* and roofline come from a second pass over the same proofs with the five MSM "
                               "streams serialised (pcdgpu_set_concurrency(0)); value / ms_per_step are the overlapped run",
-        "imad_peak_measured": {"independent_TIMAD_s": imad_peak / 1e12, "carry_chain_TIMAD_s": imad_chain / 1e12},
+        "imad_peak_measured": {"independent_TIMAD_s": imad_indep / 1e12, "carry_chain_TIMAD_s": imad_chain / 1e12},
         "hbm_peak_GBps": {"value": hbm_peak, "source": hbm_src},
     }
     line.update(extra)
@@ -459,6 +463,49 @@ def pcd_step_figure(args, ctx, dev, stream, log):
             "ms": per[0]}, "helper": {"pairing": "MNT6-298", "domain": "2^%d" % args.pcd_help_log_n, "ms": per[1]},
             "note": "prover kernels only (witness map + 4 G1 MSM + 1 G2 MSM + assembly per proof); main then helper, "
                     "sequential as in ECCyclePCD::prove"}
+
+
+def gm17_figure(args, ctx, dev, stream, log):
+    """GM17 proofs/s on MNT4-298 (the second SNARK the reference plugs into ECCyclePCD, tests/mnt4_gm17.rs:27-28):
+    2^(k-1) - 2 constraints, SAP domain 2^k; the proof is checked against GM17's verification equations in the
+    exponent (known trapdoor) before it is timed."""
+    import torch
+
+    import pcd_b200
+    from pcd_b200 import synthetic
+    k = args.gm17_log_n
+    m = (1 << (k - 1)) - 2
+    inst = synthetic.make_gm17_instance(ctx, pcd_b200.MNT4_298, m, seed=4242, verbose=log)
+    assert inst["domain_size"] == 1 << k
+    g = pcd_b200.GM17(ctx, pcd_b200.MNT4_298)
+    idx = g.index(pcd_b200.GM17ProvingKey(pairing=0, **inst["pk"]),
+                  pcd_b200.ConstraintMatrices(0, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"]),
+                  precompute=True)
+    z = torch.from_numpy(inst["z"].view(np.int64)).to(dev)
+    p = inst["p"]
+    d1, d2, r = 0x1234567 * 3 ** 70 % p, 0x7654321 * 5 ** 60 % p, 0xabcdef1 * 7 ** 50 % p
+    lim = lambda v: np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(5)], dtype=np.uint64)
+    proof = g.create_proof_dev(idx, z.data_ptr(), lim(d1), lim(d2), lim(r))
+    if not np.array_equal(proof.affine_limbs(), synthetic.expected_gm17_proof(ctx, inst, d1, d2, r)):
+        raise SystemExit("bench: GM17 proof does not satisfy the verification equations in the exponent")
+    if log:
+        log("GM17 proof (SAP domain 2^%d) verified against the trapdoor" % k)
+    for _ in range(3):
+        g.create_proof_dev(idx, z.data_ptr(), lim(d1), lim(d2), lim(r))
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    torch.cuda.synchronize()
+    reps = 5
+    e0.record(stream)
+    for _ in range(reps):
+        g.create_proof_dev(idx, z.data_ptr(), lim(d1), lim(d2), lim(r))
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / reps
+    idx.close()
+    return {"proofs_per_s": 1e3 / ms, "ms_per_proof": ms, "pairing": "MNT4-298", "constraints": m,
+            "sap_domain": "2^%d" % k, "msm_lengths": {"a": inst["num_inputs"] + inst["num_witness"] + m, "b_g2": "same",
+                                                       "c1": "same - 2", "c2": "same", "g": (1 << k) + 1},
+            "note": "SAP witness map (5 NTTs) + 4 G1 MSMs + 1 G2 MSM + assembly; one proof at a time"}
 
 
 def kernel_figures(args, ctx, dev, stream, imad_peak, rank=0, world=1):
@@ -552,6 +599,8 @@ def main():
     ap.add_argument("--ntt-log-n", type=int, default=24)
     ap.add_argument("--cpu-sample-log-n", type=int, default=17)
     ap.add_argument("--no-precompute", action="store_true")
+    ap.add_argument("--no-gm17", action="store_true", help="skip the GM17 figure")
+    ap.add_argument("--gm17-log-n", type=int, default=18, help="SAP domain of the GM17 figure (2^k)")
     ap.add_argument("--inflight", type=int, default=int(os.environ.get("PCD_BENCH_INFLIGHT", "2")),
                     help="independent proofs issued concurrently per GPU (each on its own context)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
