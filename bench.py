@@ -154,7 +154,7 @@ def run_reference(args, rank, world):
         "cpu_baseline": {"value": value, "unit": "proofs/s", "cores": threads, "kind": "port", "sample": sample},
         "e2e": {"value": value, "unit": "proofs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
     }
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 # ---------------------------------------------------------------------------------------------------
@@ -404,7 +404,7 @@ def run_gpu(args, rank, local_rank, world):
     line.update(extra)
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
-    print(json.dumps(line), flush=True)
+    emit(line)
 
 
 def pcd_step_figure(args, ctx, dev, stream, log):
@@ -588,7 +588,25 @@ def kernel_figures(args, ctx, dev, stream, imad_peak, rank=0, world=1):
     return out
 
 
+_REAL_STDOUT = None
+
+
+def emit(line: dict):
+    """the ONE JSON line, on the process's real stdout (fd 1 is pointed at stderr while the job runs so that
+    library chatter -- NCCL prints its version banner on stdout -- cannot end up next to it)"""
+    data = (json.dumps(line) + "\n").encode()
+    if _REAL_STDOUT is None:
+        sys.stdout.write(data.decode())
+        sys.stdout.flush()
+    else:
+        os.write(_REAL_STDOUT, data)
+
+
 def main():
+    global _REAL_STDOUT
+    sys.stdout.flush()
+    _REAL_STDOUT = os.dup(1)
+    os.dup2(2, 1)
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
     ap.add_argument("--steps", type=int, default=5)
