@@ -178,6 +178,26 @@ int pcdgpu_gm17_prove(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgpu_r1
 int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
                           const void* d1, const void* d2, const void* r, void* out_proof);
 
+/* ---- dense polynomials and KZG10 (ark-poly DensePolynomial, ark-poly-commit kzg10::KZG10::{commit, open}) -----
+ * The operations ark-marlin's prover spends its time in when the reference runs MarlinSNARK over MarlinKZG10
+ * (/root/reference/tests/mnt4_marlin.rs:68-94), reached through IC::MainSNARK::prove / IC::HelpSNARK::prove
+ * (/root/reference/src/ec_cycle_pcd/mod.rs:171,179).  Coefficient vectors are Montgomery elements, lowest degree
+ * first; the committer key's `powers_of_g` / `powers_of_gamma_g` are resident pcdgpu_bases over G1. */
+/* quotient (n - 1 coefficients) and value of p / (X - z): q = (p - p(z)) / (X - z), eval = p(z); z Montgomery */
+int pcdgpu_poly_divide_linear(pcdgpu_ctx* ctx, int field, const void* coeffs, size_t n, const void* z, void* quotient,
+                              void* eval);
+/* DensePolynomial mul: out = a * b (na + nb - 1 coefficients) through GeneralEvaluationDomain::new(na + nb - 1) */
+int pcdgpu_poly_mul(pcdgpu_ctx* ctx, int field, const void* a, size_t na, const void* b, size_t nb, void* out);
+/* KZG10::commit: MSM(powers_of_g, coeffs) + MSM(powers_of_gamma_g, rand_coeffs) (the hiding part is skipped when
+ * n_rand == 0); one affine G1 point.  The blinding polynomial is drawn by the caller (the RNG stays on its side). */
+int pcdgpu_kzg_commit(pcdgpu_ctx* ctx, const pcdgpu_bases* powers_of_g, const void* coeffs, size_t n,
+                      const pcdgpu_bases* powers_of_gamma_g, const void* rand_coeffs, size_t n_rand, void* out_affine);
+/* KZG10::open: w = commit((p - p(z)) / (X - z)) [+ hiding witness over powers_of_gamma_g]; out_value = p(z)
+ * (may be NULL), out_random_v = r(z) (Proof.random_v; written when n_rand > 0) */
+int pcdgpu_kzg_open(pcdgpu_ctx* ctx, const pcdgpu_bases* powers_of_g, const void* coeffs, size_t n,
+                    const pcdgpu_bases* powers_of_gamma_g, const void* rand_coeffs, size_t n_rand, const void* z,
+                    void* out_w_affine, void* out_value, void* out_random_v);
+
 /* ark-serialize CanonicalSerialize of the proof (compressed points: x with flag bits 7 = "y is the
  * larger root", 6 = infinity on the last byte): 152 B (MNT4) / 190 B (MNT6).  out: >= 190 bytes. */
 int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affine, uint8_t* out, size_t* out_len);

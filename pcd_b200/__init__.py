@@ -7,3 +7,4 @@ from .lib import (Bases, Context, PcdGpuError, load, FIELD_R4, FIELD_Q4, MNT4_29
                   MNT6_G1, MNT6_G2, G1_OF, G2_OF, SCALAR_FIELD_OF, AFFINE_LIMBS, XYZZ_LIMBS, TWO_ADICITY)
 from .snark import (ConstraintMatrices, GM17, GM17ProverIndex, GM17ProvingKey, Groth16, Proof, ProverIndex,  # noqa
                     ProvingKey)
+from . import kzg  # noqa

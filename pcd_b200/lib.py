@@ -37,6 +37,7 @@ EXPORTS = [
     "pcdgpu_profile_enable", "pcdgpu_profile_read", "pcdgpu_profile_timeline", "pcdgpu_bench_imad",
     "pcdgpu_sap_domain_size", "pcdgpu_sap_witness_map", "pcdgpu_gm17_pk_upload", "pcdgpu_gm17_pk_free",
     "pcdgpu_gm17_prove", "pcdgpu_gm17_prove_dev",
+    "pcdgpu_poly_divide_linear", "pcdgpu_poly_mul", "pcdgpu_kzg_commit", "pcdgpu_kzg_open",
 ]
 
 
@@ -114,6 +115,10 @@ def load():
     lib.pcdgpu_gm17_pk_free.restype = None
     lib.pcdgpu_gm17_prove.argtypes = [vp] * 8
     lib.pcdgpu_gm17_prove_dev.argtypes = [vp] * 8
+    lib.pcdgpu_poly_divide_linear.argtypes = [vp, ci, vp, sz, vp, vp, vp]
+    lib.pcdgpu_poly_mul.argtypes = [vp, ci, vp, sz, vp, sz, vp]
+    lib.pcdgpu_kzg_commit.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp]
+    lib.pcdgpu_kzg_open.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, vp, vp, vp]
     _lib = lib
     return lib
 
