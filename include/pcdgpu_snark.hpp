@@ -1,4 +1,4 @@
-// pcdgpu_snark.hpp -- C++ host mirror of the reference's SNARK interface for the Groth16 proving path,
+// pcdgpu_snark.hpp -- C++ host mirror of the reference's SNARK interface for the Groth16 and GM17 proving paths,
 // on top of the C ABI (pcdgpu.h).  Header only.
 //
 // The reference binds its SNARKs through ark-snark's traits (re-exported by ark-crypto-primitives):
@@ -243,6 +243,139 @@ class Groth16 {
     res.value.resize(len);
     return res;
   }
+};
+
+// ---- ark-gm17 data structures and GM17<E>: SNARK + CircuitSpecificSetupSNARK -------------------------------
+// Bound by the reference as MainSNARK / HelpSNARK at /root/reference/tests/mnt4_gm17.rs:27-28 and in the two
+// mixed configurations (tests/mnt4_mix_groth16gm17.rs, tests/mnt4_mix_gm17groth16.rs).
+template <class E>
+struct GM17VerifyingKey {
+  G2Affine<E> h_g2{}, h_beta_g2{}, h_gamma_g2{};
+  G1Affine<E> g_alpha_g1{}, g_gamma_g1{};
+  std::vector<G1Affine<E>> query;
+};
+template <class E>
+struct GM17ProvingKey {
+  GM17VerifyingKey<E> vk;
+  std::vector<G1Affine<E>> a_query, c_query_1, c_query_2, g_gamma2_z_t;
+  std::vector<G2Affine<E>> b_query;
+  G1Affine<E> g_gamma_z{}, g_ab_gamma_z{}, g_gamma2_z2{};
+  G2Affine<E> h_gamma_z{};
+};
+
+template <class E>
+class GM17 {
+ public:
+  using ProvingKeyT = GM17ProvingKey<E>;
+  using VerifyingKeyT = GM17VerifyingKey<E>;
+  using ProofT = Proof<E>;  // ark-gm17 Proof { a: G1, b: G2, c: G1 }
+
+  struct Index {
+    pcdgpu_gm17_pk* pk = nullptr;
+    pcdgpu_r1cs* r1cs = nullptr;
+    size_t num_vars = 0;
+    ~Index() {
+      if (pk) pcdgpu_gm17_pk_free(pk);
+      if (r1cs) pcdgpu_r1cs_free(r1cs);
+    }
+    Index() = default;
+    Index(const Index&) = delete;
+    Index& operator=(const Index&) = delete;
+  };
+
+  template <class C, class R>
+  static Result<std::pair<ProvingKeyT, VerifyingKeyT>> circuit_specific_setup(const C&, R&) {
+    Result<std::pair<ProvingKeyT, VerifyingKeyT>> r;
+    r.error = {ErrorKind::Unsupported, 0, "GM17 setup stays with the CPU generator (ark-gm17 generate_random_parameters)"};
+    return r;
+  }
+  static Result<bool> verify(const VerifyingKeyT&, const std::vector<Fr>&, const ProofT&) {
+    Result<bool> r;
+    r.error = {ErrorKind::Unsupported, 0, "verification (pairing checks) stays on the CPU"};
+    return r;
+  }
+
+  static Result<bool> index(const ProvingKeyT& pk, const ConstraintMatrices& m, Index* out, bool precompute = true) {
+    Result<bool> res;
+    auto ctx = Backend::get();
+    if (!ctx) { res.error = ctx.error; return res; }
+    const size_t ni = m.num_instance_variables, nv = ni + m.num_witness_variables;
+    const size_t nsap = nv + m.num_constraints + ni - 1;
+    const size_t n = pcdgpu_sap_domain_size(E::PAIRING, m.num_constraints, ni);
+    if (n == 0) {
+      res.error = {ErrorKind::DomainTooLarge, PCDGPU_E_DOMAIN, "no evaluation domain large enough for the SAP"};
+      return res;
+    }
+    if (ni < 1 || pk.a_query.size() != nsap || pk.b_query.size() != nsap || pk.c_query_2.size() != nsap ||
+        pk.c_query_1.size() != nsap - ni || pk.g_gamma2_z_t.size() != n + 1) {
+      res.error = {ErrorKind::MalformedKey, 0, "query lengths do not match the square arithmetic program"};
+      return res;
+    }
+    std::vector<uint32_t> ptr[3], col[3];
+    std::vector<Fr> val[3];
+    const std::vector<std::vector<std::pair<Fr, size_t>>>* mats[3] = {&m.a, &m.b, &m.c};
+    for (int k = 0; k < 3; k++) {
+      ptr[k].push_back(0);
+      for (const auto& row : *mats[k]) {
+        for (const auto& e : row) {
+          val[k].push_back(e.first);
+          col[k].push_back((uint32_t)e.second);
+        }
+        ptr[k].push_back((uint32_t)col[k].size());
+      }
+      ptr[k].resize(m.num_constraints + 1, (uint32_t)col[k].size());
+    }
+    int rc = pcdgpu_r1cs_upload(ctx.value, E::PAIRING, m.num_constraints, ni, m.num_witness_variables, ptr[0].data(),
+                                col[0].data(), val[0].data(), ptr[1].data(), col[1].data(), val[1].data(), ptr[2].data(),
+                                col[2].data(), val[2].data(), &out->r1cs);
+    if (rc == PCDGPU_OK)
+      rc = pcdgpu_gm17_pk_upload(ctx.value, E::PAIRING, nsap, ni, n + 1, pk.a_query.data(), pk.b_query.data(),
+                                 pk.c_query_1.data(), pk.c_query_2.data(), pk.g_gamma2_z_t.data(), pk.g_gamma_z.data(),
+                                 pk.h_gamma_z.data(), pk.g_ab_gamma_z.data(), pk.g_gamma2_z2.data(), precompute ? 1 : 0,
+                                 &out->pk);
+    if (rc != PCDGPU_OK) {
+      res.error = {ErrorKind::Backend, rc, pcdgpu_last_error(ctx.value)};
+      return res;
+    }
+    out->num_vars = nv;
+    res.value = true;
+    return res;
+  }
+
+  // ark-gm17 create_proof(circuit, pk, d1, d2, r); d1, d2, r as plain integers (into_repr)
+  static Result<ProofT> create_proof(const Index& idx, const SynthesizedCircuit& circuit, const Fr& d1, const Fr& d2,
+                                     const Fr& r) {
+    Result<ProofT> res;
+    auto ctx = Backend::get();
+    if (!ctx) { res.error = ctx.error; return res; }
+    std::vector<Fr> z(circuit.instance_assignment);
+    z.insert(z.end(), circuit.witness_assignment.begin(), circuit.witness_assignment.end());
+    if (z.size() != idx.num_vars || z.empty()) {
+      res.error = {ErrorKind::AssignmentMissing, 0, "assignment length does not match the indexed circuit"};
+      return res;
+    }
+    std::vector<uint64_t> out(2 * E::G1_LIMBS + E::G2_LIMBS);
+    int rc = pcdgpu_gm17_prove(ctx.value, idx.pk, idx.r1cs, z.data(), d1.data(), d2.data(), r.data(), out.data());
+    if (rc != PCDGPU_OK) {
+      res.error = {rc == PCDGPU_E_DOMAIN ? ErrorKind::DomainTooLarge : ErrorKind::Backend, rc, pcdgpu_last_error(ctx.value)};
+      return res;
+    }
+    std::memcpy(res.value.a.data(), out.data(), 8 * E::G1_LIMBS);
+    std::memcpy(res.value.b.data(), out.data() + E::G1_LIMBS, 8 * E::G2_LIMBS);
+    std::memcpy(res.value.c.data(), out.data() + E::G1_LIMBS + E::G2_LIMBS, 8 * E::G1_LIMBS);
+    return res;
+  }
+
+  // SNARK::prove(pk, circuit, rng): d1, d2, r = Fr::rand(rng) in this order (create_random_proof)
+  template <class Rng>
+  static Result<ProofT> prove(const Index& idx, const SynthesizedCircuit& circuit, Rng& rng) {
+    Fr d1 = rng.next_scalar(E::PAIRING);
+    Fr d2 = rng.next_scalar(E::PAIRING);
+    Fr r = rng.next_scalar(E::PAIRING);
+    return create_proof(idx, circuit, d1, d2, r);
+  }
+
+  static Result<std::vector<uint8_t>> serialize(const ProofT& p) { return Groth16<E>::serialize(p); }
 };
 
 }  // namespace pcdgpu

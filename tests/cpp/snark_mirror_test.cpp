@@ -19,8 +19,8 @@ template <size_t N> static std::array<uint64_t, N> rda() {
   return a;
 }
 
-struct FixtureRng {  // the caller's rng: yields the fixture's r, then s
-  Fr draws[2];
+struct FixtureRng {  // the caller's rng: yields the fixture's r, then s (GM17: d1, d2, r)
+  Fr draws[3];
   int next = 0;
   Fr next_scalar(int) { return draws[next++]; }
 };
@@ -91,6 +91,68 @@ static int run(FILE* out) {
   return 0;
 }
 
+// GM17 fixture (tests/golden/gm17.json): `GM17::<E>::prove` as tests/mnt4_gm17.rs:27-28 binds it
+template <class E>
+static int run_gm17(FILE* out) {
+  SynthesizedCircuit circ;
+  ConstraintMatrices& m = circ.matrices;
+  m.num_constraints = rd();
+  m.num_instance_variables = rd();
+  m.num_witness_variables = rd();
+  std::vector<std::vector<std::pair<Fr, size_t>>>* mats[3] = {&m.a, &m.b, &m.c};
+  for (int k = 0; k < 3; k++) {
+    mats[k]->resize(m.num_constraints);
+    for (size_t i = 0; i < m.num_constraints; i++) {
+      size_t cnt = rd();
+      for (size_t e = 0; e < cnt; e++) {
+        Fr co = rda<5>();
+        size_t col = rd();
+        (*mats[k])[i].push_back({co, col});
+      }
+    }
+  }
+  for (size_t i = 0; i < m.num_instance_variables; i++) circ.instance_assignment.push_back(rda<5>());
+  for (size_t i = 0; i < m.num_witness_variables; i++) circ.witness_assignment.push_back(rda<5>());
+  FixtureRng rng;
+  for (int i = 0; i < 3; i++) rng.draws[i] = rda<5>();
+  GM17ProvingKey<E> pk;
+  size_t nsap = rd(), hlen = rd();
+  for (size_t i = 0; i < nsap; i++) pk.a_query.push_back(rda<E::G1_LIMBS>());
+  for (size_t i = 0; i < nsap; i++) pk.b_query.push_back(rda<E::G2_LIMBS>());
+  for (size_t i = 0; i < nsap - m.num_instance_variables; i++) pk.c_query_1.push_back(rda<E::G1_LIMBS>());
+  for (size_t i = 0; i < nsap; i++) pk.c_query_2.push_back(rda<E::G1_LIMBS>());
+  for (size_t i = 0; i < hlen; i++) pk.g_gamma2_z_t.push_back(rda<E::G1_LIMBS>());
+  pk.g_gamma_z = rda<E::G1_LIMBS>();
+  pk.h_gamma_z = rda<E::G2_LIMBS>();
+  pk.g_ab_gamma_z = rda<E::G1_LIMBS>();
+  pk.g_gamma2_z2 = rda<E::G1_LIMBS>();
+  auto setup = GM17<E>::circuit_specific_setup(circ, rng);
+  if (setup.is_ok() || setup.error.kind != ErrorKind::Unsupported) return 1;
+  typename GM17<E>::Index idx;
+  auto ok = GM17<E>::index(pk, m, &idx, true);
+  if (!ok) {
+    fprintf(stderr, "gm17 index: %s (code %d)\n", ok.error.message.c_str(), ok.error.code);
+    return ok.error.code == PCDGPU_E_NODEVICE ? 2 : 1;
+  }
+  auto proof = GM17<E>::prove(idx, circ, rng);
+  if (!proof) {
+    fprintf(stderr, "gm17 prove: %s\n", proof.error.message.c_str());
+    return 1;
+  }
+  auto bytes = GM17<E>::serialize(proof.value);
+  if (!bytes || bytes.value.size() != E::PROOF_BYTES) return 1;
+  fwrite(proof.value.a.data(), 8, E::G1_LIMBS, out);
+  fwrite(proof.value.b.data(), 8, E::G2_LIMBS, out);
+  fwrite(proof.value.c.data(), 8, E::G1_LIMBS, out);
+  fwrite(bytes.value.data(), 1, bytes.value.size(), out);
+  // a key whose lengths do not match the SAP is an error, not a crash
+  pk.c_query_1.pop_back();
+  typename GM17<E>::Index bad_idx;
+  auto bad = GM17<E>::index(pk, m, &bad_idx, false);
+  if (bad.is_ok() || bad.error.kind != ErrorKind::MalformedKey) return 1;
+  return 0;
+}
+
 int main(int argc, char** argv) {
   if (argc != 3) return 1;
   FILE* f = fopen(argv[1], "rb");
@@ -103,8 +165,11 @@ int main(int argc, char** argv) {
   fclose(f);
   FILE* out = fopen(argv[2], "wb");
   if (!out) return 1;
-  uint64_t pairing = rd();
-  int rc = pairing == 0 ? run<MNT4_298>(out) : run<MNT6_298>(out);
+  uint64_t head = rd();  // pairing | scheme << 8 (0 = Groth16, 1 = GM17)
+  uint64_t pairing = head & 0xff, scheme = head >> 8;
+  int rc;
+  if (scheme == 0) rc = pairing == 0 ? run<MNT4_298>(out) : run<MNT6_298>(out);
+  else rc = pairing == 0 ? run_gm17<MNT4_298>(out) : run_gm17<MNT6_298>(out);
   fclose(out);
   return rc;
 }

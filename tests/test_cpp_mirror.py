@@ -54,6 +54,29 @@ def _fixture(case, path):
     del g2
 
 
+def _gm17_fixture(case, path):
+    pid = case["pairing"]
+    g1 = codec.G1_OF[pid]
+    words = [pid | (1 << 8), case["m"], case["num_inputs"], case["num_witness"]]
+    for k in "ABC":
+        ptr, col, val = codec.csr_from_golden(case[k])
+        for i in range(case["m"]):
+            lo, hi = int(ptr[i]), int(ptr[i + 1])
+            words.append(hi - lo)
+            for e in range(lo, hi):
+                words += [int(x) for x in val[e]] + [int(col[e])]
+    words += [int(x) for x in codec.hex_to_u64(case["z"])]
+    for k in ("d1", "d2", "r"):
+        words += [int(x) for x in codec.hex_to_u64(case[k])]
+    pk = case["pk"]
+    nsap = codec.hex_to_u64(pk["a_query"], codec.POINT_LIMBS[g1]).shape[0]
+    words += [nsap, case["domain_size"] + 1]
+    for k in ("a_query", "b_query", "c_query_1", "c_query_2", "g_gamma2_z_t", "g_gamma_z", "h_gamma_z", "g_ab_gamma_z",
+              "g_gamma2_z2"):
+        words += [int(x) for x in codec.hex_to_u64(pk[k])]
+    np.array(words, dtype=np.uint64).tofile(path)
+
+
 def test_cpp_mirror_builds_and_refuses_cpu(tmp_path):
     import torch
     exe = _build()
@@ -65,6 +88,9 @@ def test_cpp_mirror_builds_and_refuses_cpu(tmp_path):
         assert rc == 0
     else:
         assert rc == 2  # PCDGPU_E_NODEVICE surfaced through Groth16::index: no CPU fallback
+    _gm17_fixture(codec.load("gm17")[0], fx)
+    rc = subprocess.call([exe, fx, out])
+    assert rc == (0 if torch.cuda.is_available() else 2)
 
 
 @pytest.mark.gpu
@@ -73,6 +99,19 @@ def test_cpp_mirror_matches_golden(tmp_path):
     for i, case in enumerate(codec.load("groth16")):
         fx, out = str(tmp_path / ("fx%d.bin" % i)), str(tmp_path / ("out%d.bin" % i))
         _fixture(case, fx)
+        assert subprocess.call([exe, fx, out]) == 0
+        blob = open(out, "rb").read()
+        n_aff = len(case["proof_affine"]) // 2
+        assert blob[:n_aff].hex() == case["proof_affine"]
+        assert blob[n_aff:].hex() == case["proof_bytes"]
+
+
+@pytest.mark.gpu
+def test_cpp_mirror_gm17_matches_golden(tmp_path):
+    exe = _build()
+    for i, case in enumerate(codec.load("gm17")):
+        fx, out = str(tmp_path / ("gfx%d.bin" % i)), str(tmp_path / ("gout%d.bin" % i))
+        _gm17_fixture(case, fx)
         assert subprocess.call([exe, fx, out]) == 0
         blob = open(out, "rb").read()
         n_aff = len(case["proof_affine"]) // 2
