@@ -584,7 +584,8 @@ def kernel_figures(args, ctx, dev, stream, imad_peak, rank=0, world=1):
     out["ntt"] = {"log_n": log_n, "field": "r4 (MNT4-298 Fr)", "flavour": "coset_fft", "ms": ms_ntt, "GBps": gbs}
     out["roofline_ntt"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                            "traffic": None, "imad_frac": timad / (imad_peak / 1e12),
-                           "note": "algorithmic bytes 2*N*40; a 298-bit NTT is bound by the integer pipe, see imad_frac"}
+                           "note": "algorithmic bytes 2*N*40; a 298-bit NTT is bound by the integer pipe: imad_frac = "
+                                   "(N/2 log2 N butterflies x 210 IMAD) / time / the IMAD.WIDE roof"}
     return out
 
 
