@@ -582,16 +582,19 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
   const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
   size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
-  // misc layout: rs (80 B) | extras: 7 scalars | sums1: h, l', g_a, g1_b (G1 xyzz) | sum2: g2_b | proof
+  // misc layout: rs (80 B) | extras: 7 scalars | sums1: h, l', g_a, g1_b, T (G1 xyzz) | sum2: g2_b | proof
   void* misc;
   PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
   char* mb = (char*)misc;
   u32* d_rs = (u32*)mb;
   char* extras = mb + 128;  // r, 1, 1, s, 1, 1, -(r s)
   void* sums1 = mb + 512;
-  void* sum2 = (char*)sums1 + 4 * x1;
-  void* d_proof = (char*)sum2 + x2;
+  void* sum2 = (char*)sums1 + 5 * x1;
+  char* d_proof = (char*)sum2 + x2;
   size_t proof_bytes = 2 * o1->affine_bytes + o2->affine_bytes;
+  char* d_A = d_proof;
+  char* d_B = d_proof + o1->affine_bytes;
+  char* d_C = d_proof + o1->affine_bytes + o2->affine_bytes;
   memcpy(ctx->pinned, r, 40);
   memcpy((char*)ctx->pinned + 40, s, 40);
   PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
@@ -600,6 +603,9 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   size_t nv = pk->num_vars, ni = pk->num_inputs;
   // Fork: the four MSMs over the assignment only need z and the extra scalars, so they start on lanes
   // 1-4 while lane 0 runs the witness map and then the h MSM (the G2 MSM, the longest, goes first).
+  // Each lane finishes its own piece of the proof: lane 1 normalises B, lane 2 (a) normalises A, lane 3
+  // (b_g1) waits for lane 2 and runs the double-scalar multiplication T = s g_a + r g1_b -- all of it under
+  // the witness map / h MSM, so that after the join only C = T + l' + h is left.
   const bool fork = ctx->concurrent;
   if (fork) {
     PCD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
@@ -614,6 +620,16 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   for (int j = 0; j < 4 && rc == 0; j++) {
     ctx->lane = fork ? j + 1 : 0;
     rc = bases_msm(ctx, jobs[j].b, 0, jobs[j].sc, 1, jobs[j].n, jobs[j].ex, jobs[j].nex, jobs[j].out);
+    if (rc == 0 && j == 0) rc = point_to_affine(ctx, g2, sum2, 0, d_B);
+    if (rc == 0 && j == 1) {
+      rc = point_to_affine(ctx, g1, sums1, 2, d_A);
+      // lane 3's Straus needs g_a: an event of its own, recorded before lane 2's tail would also do, but the
+      // normalisation is short
+    }
+    if (rc == 0 && j == 2) {
+      if (fork && cudaStreamWaitEvent(ctx->lane_stream[3], ctx->ev_join[2], 0) != cudaSuccess) rc = PCDGPU_E_CUDA;
+      if (rc == 0) rc = groth16_straus(ctx, pk->pairing, d_rs, sums1);
+    }
     if (fork && rc == 0 && cudaEventRecord(ctx->ev_join[j + 1], ctx->lane_stream[j + 1]) != cudaSuccess) rc = PCDGPU_E_CUDA;
   }
   ctx->lane = 0;
@@ -624,7 +640,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   PCD_TRY(bases_msm(ctx, pk->h_query, 0, d_h, 1, r1cs->n, nullptr, 0, (char*)sums1 + 0 * x1));
   if (fork)
     for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
-  PCD_TRY(groth16_assemble(ctx, pk->pairing, d_rs, sums1, sum2, d_proof));
+  PCD_TRY(groth16_finish(ctx, pk->pairing, sums1, d_C));
   PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;

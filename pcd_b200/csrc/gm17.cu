@@ -137,24 +137,20 @@ __global__ void gm17_prepare_kernel(const u32* __restrict__ ddr, u32* __restrict
   }
 }
 
-// sums1 = {G', C1', C2', A} (G1 xyzz), sum2 = B.  warp 0: A, C = C1' + G' + [r] C2';  warp 1: B.
-template <class G1, class G2>
-__global__ void gm17_assemble_kernel(const u32* __restrict__ ddr, const void* __restrict__ sums1,
-                                     const void* __restrict__ sum2, void* __restrict__ out) {
-  if (threadIdx.x & 31) return;
-  int w = threadIdx.x >> 5;
-  char* o = reinterpret_cast<char*>(out);
-  typedef typename G1::F F1;
-  typedef typename G2::F F2;
-  if (w == 0) {
-    XYZZ<G1> acc = XYZZ<G1>::mul(ld_xyzz<G1>(sums1, 2), ddr + 20, 10);
-    acc.add(ld_xyzz<G1>(sums1, 1));
-    acc.add(ld_xyzz<G1>(sums1, 0));
-    st_aff<G1>(o, 0, ld_xyzz<G1>(sums1, 3).to_affine());
-    st_aff<G1>(o + sizeof(AffinePoint<F1>) + sizeof(AffinePoint<F2>), 0, acc.to_affine());
-  } else if (w == 1) {
-    st_aff<G2>(o + sizeof(AffinePoint<F1>), 0, ld_xyzz<G2>(sum2, 0).to_affine());
-  }
+// The proof's tail, split like Groth16's (groth16.cu): [r] C2' right after the c_query_2 MSM on its lane, A and B
+// normalised on their lanes, and after the join only C = C1' + G' + [r] C2'.  sums1 = {G', C1', C2', A} (G1 xyzz).
+template <class G1>
+__global__ void gm17_scale_kernel(const u32* __restrict__ ddr, void* __restrict__ sums1) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st_xyzz<G1>(sums1, 2, XYZZ<G1>::mul(ld_xyzz<G1>(sums1, 2), ddr + 20, 10));
+}
+template <class G1>
+__global__ void gm17_finish_kernel(const void* __restrict__ sums1, void* __restrict__ out_c) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  XYZZ<G1> acc = ld_xyzz<G1>(sums1, 2);
+  acc.add(ld_xyzz<G1>(sums1, 1));
+  acc.add(ld_xyzz<G1>(sums1, 0));
+  st_aff<G1>(out_c, 0, acc.to_affine());
 }
 
 static int sap_domain(int pairing, size_t m, size_t ni, size_t* n, int* da, int* db) {
@@ -347,8 +343,11 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
   u32* d_dm = (u32*)(mb + 384);
   void* sums1 = mb + 512;
   void* sum2 = (char*)sums1 + 4 * x1;
-  void* d_proof = (char*)sum2 + x2;
+  char* d_proof = (char*)sum2 + x2;
   size_t proof_bytes = 2 * o1->affine_bytes + o2->affine_bytes;
+  char* d_A = d_proof;
+  char* d_B = d_proof + o1->affine_bytes;
+  char* d_C = d_proof + o1->affine_bytes + o2->affine_bytes;
   memcpy(ctx->pinned, d1, 40);
   memcpy((char*)ctx->pinned + 40, d2, 40);
   memcpy((char*)ctx->pinned + 80, r, 40);
@@ -372,6 +371,16 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
     for (int j = 0; j < 4 && rc == 0; j++) {
       ctx->lane = fork ? j + 1 : 0;
       rc = bases_msm(ctx, jobs[j].b, 0, jobs[j].sc, 1, jobs[j].n, jobs[j].ex, jobs[j].nex, jobs[j].out);
+      if (rc == 0 && j == 0) rc = point_to_affine(ctx, g2, sum2, 0, d_B);
+      if (rc == 0 && j == 1) rc = point_to_affine(ctx, g1, sums1, 3, d_A);
+      if (rc == 0 && j == 2) {  // [r] C2' on the lane that produced C2'
+        int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
+        ctx->launches += 1;
+        if (pk->pairing == PCDGPU_MNT4_298) gm17_scale_kernel<CurveMnt4G1><<<1, 32, 0, ctx->cur()>>>(d_ddr, sums1);
+        else gm17_scale_kernel<CurveMnt6G1><<<1, 32, 0, ctx->cur()>>>(d_ddr, sums1);
+        if (cudaGetLastError() != cudaSuccess) rc = PCDGPU_E_CUDA;
+        ctx->prof_end(ps);
+      }
       if (fork && rc == 0 && cudaEventRecord(ctx->ev_join[j + 1], ctx->lane_stream[j + 1]) != cudaSuccess) rc = PCDGPU_E_CUDA;
     }
     ctx->lane = 0;
@@ -386,10 +395,8 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
     for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
   ctx->launches += 1;
-  if (pk->pairing == PCDGPU_MNT4_298)
-    gm17_assemble_kernel<CurveMnt4G1, CurveMnt4G2><<<1, 64, 0, ctx->stream>>>(d_ddr, sums1, sum2, d_proof);
-  else
-    gm17_assemble_kernel<CurveMnt6G1, CurveMnt6G2><<<1, 64, 0, ctx->stream>>>(d_ddr, sums1, sum2, d_proof);
+  if (pk->pairing == PCDGPU_MNT4_298) gm17_finish_kernel<CurveMnt4G1><<<1, 32, 0, ctx->stream>>>(sums1, d_C);
+  else gm17_finish_kernel<CurveMnt6G1><<<1, 32, 0, ctx->stream>>>(sums1, d_C);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));

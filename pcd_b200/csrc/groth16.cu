@@ -127,52 +127,77 @@ int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras
   return 0;
 }
 
-// warp 0: A = g_a, C = s g_a + r g1_b + l' + h;  warp 1: B = g2_b.  Output affine A || B || C.
-template <class G1, class G2>
-__global__ void groth16_assemble_kernel(const u32* __restrict__ rs, const void* __restrict__ sums1,
-                                        const void* __restrict__ sum2, void* __restrict__ out) {
-  if (threadIdx.x & 31) return;
-  int w = threadIdx.x >> 5;
-  char* o = reinterpret_cast<char*>(out);
-  typedef typename G1::F F1;
-  typedef typename G2::F F2;
-  if (w == 0) {
-    XYZZ<G1> ga = ld_xyzz<G1>(sums1, 2);
-    XYZZ<G1> gb = ld_xyzz<G1>(sums1, 3);
-    // s g_a + r g1_b jointly (Straus): one doubling chain, table {ga, gb, ga + gb}
-    XYZZ<G1> gab = ga;
-    gab.add(gb);
-    XYZZ<G1> acc = XYZZ<G1>::inf();
-    bool started = false;
-    for (int i = 9; i >= 0; i--) {
-      u32 rw = rs[i], sw = rs[10 + i];
-      for (int b = 31; b >= 0; b--) {
-        if (started) acc = acc.dbl();
-        u32 sel = ((sw >> b) & 1) | (((rw >> b) & 1) << 1);
-        if (sel) {
-          acc.add(sel == 1 ? ga : (sel == 2 ? gb : gab));
-          started = true;
-        }
+// The tail of a proof is split so that only two additions and one normalisation are left after the last MSM:
+//   groth16_straus   T = s g_a + r g1_b, as soon as the a and b_g1 MSMs are done (overlaps the witness map / h MSM)
+//   point_to_affine  A = g_a and B = g2_b, each right after its MSM, on that MSM's lane
+//   groth16_finish   C = T + l' + h
+// (one kernel doing all of it after the join cost 4.9 ms of single-thread latency per proof).
+// sums1 = {h_acc, l', g_a, g1_b, T} (G1 xyzz).
+template <class G1>
+__global__ void groth16_straus_kernel(const u32* __restrict__ rs, void* __restrict__ sums1) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  XYZZ<G1> ga = ld_xyzz<G1>(sums1, 2);
+  XYZZ<G1> gb = ld_xyzz<G1>(sums1, 3);
+  // s g_a + r g1_b jointly (Straus): one doubling chain, table {ga, gb, ga + gb}
+  XYZZ<G1> gab = ga;
+  gab.add(gb);
+  XYZZ<G1> acc = XYZZ<G1>::inf();
+  bool started = false;
+  for (int i = 9; i >= 0; i--) {
+    u32 rw = rs[i], sw = rs[10 + i];
+    for (int b = 31; b >= 0; b--) {
+      if (started) acc = acc.dbl();
+      u32 sel = ((sw >> b) & 1) | (((rw >> b) & 1) << 1);
+      if (sel) {
+        acc.add(sel == 1 ? ga : (sel == 2 ? gb : gab));
+        started = true;
       }
     }
-    acc.add(ld_xyzz<G1>(sums1, 1));
-    acc.add(ld_xyzz<G1>(sums1, 0));
-    AffinePoint<F1> A = ga.to_affine(), Cc = acc.to_affine();
-    st_aff<G1>(o, 0, A);
-    st_aff<G1>(o + sizeof(AffinePoint<F1>) + sizeof(AffinePoint<F2>), 0, Cc);
-  } else if (w == 1) {
-    XYZZ<G2> gb = ld_xyzz<G2>(sum2, 0);
-    st_aff<G2>(o + sizeof(AffinePoint<F1>), 0, gb.to_affine());
   }
+  st_xyzz<G1>(sums1, 4, acc);
+}
+template <class C>
+__global__ void point_to_affine_kernel(const void* __restrict__ src, size_t idx, void* __restrict__ dst) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  st_aff<C>(dst, 0, ld_xyzz<C>(src, idx).to_affine());
+}
+template <class G1>
+__global__ void groth16_finish_kernel(const void* __restrict__ sums1, void* __restrict__ out_c) {
+  if (threadIdx.x != 0 || blockIdx.x != 0) return;
+  XYZZ<G1> acc = ld_xyzz<G1>(sums1, 4);
+  acc.add(ld_xyzz<G1>(sums1, 1));
+  acc.add(ld_xyzz<G1>(sums1, 0));
+  st_aff<G1>(out_c, 0, acc.to_affine());
 }
 
-int groth16_assemble(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, const void* sums1, const void* sum2, void* d_out) {
+int groth16_straus(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, void* sums1) {
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
   ctx->launches += 1;
-  if (pairing == PCDGPU_MNT4_298)
-    groth16_assemble_kernel<CurveMnt4G1, CurveMnt4G2><<<1, 64, 0, ctx->stream>>>(d_rs, sums1, sum2, d_out);
-  else
-    groth16_assemble_kernel<CurveMnt6G1, CurveMnt6G2><<<1, 64, 0, ctx->stream>>>(d_rs, sums1, sum2, d_out);
+  if (pairing == PCDGPU_MNT4_298) groth16_straus_kernel<CurveMnt4G1><<<1, 32, 0, ctx->cur()>>>(d_rs, sums1);
+  else groth16_straus_kernel<CurveMnt6G1><<<1, 32, 0, ctx->cur()>>>(d_rs, sums1);
+  PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
+  return 0;
+}
+int point_to_affine(pcdgpu_ctx* ctx, int curve, const void* src, size_t idx, void* dst) {
+  int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
+  ctx->launches += 1;
+  cudaStream_t st = ctx->cur();
+  switch (curve) {
+    case PCDGPU_MNT4_G1: point_to_affine_kernel<CurveMnt4G1><<<1, 32, 0, st>>>(src, idx, dst); break;
+    case PCDGPU_MNT4_G2: point_to_affine_kernel<CurveMnt4G2><<<1, 32, 0, st>>>(src, idx, dst); break;
+    case PCDGPU_MNT6_G1: point_to_affine_kernel<CurveMnt6G1><<<1, 32, 0, st>>>(src, idx, dst); break;
+    default: point_to_affine_kernel<CurveMnt6G2><<<1, 32, 0, st>>>(src, idx, dst); break;
+  }
+  PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
+  return 0;
+}
+int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_c) {
+  int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
+  ctx->launches += 1;
+  if (pairing == PCDGPU_MNT4_298) groth16_finish_kernel<CurveMnt4G1><<<1, 32, 0, ctx->cur()>>>(sums1, d_out_c);
+  else groth16_finish_kernel<CurveMnt6G1><<<1, 32, 0, ctx->cur()>>>(sums1, d_out_c);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   return 0;

@@ -79,7 +79,9 @@ int bases_msm(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void*
 int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h);
 // extras <- {r, 1, 1, s, 1, 1, -(r s) mod p} as plain integers (the scalars of the constant pairs)
 int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras);
-// sums1 = {h_acc, l_acc - (r s) delta, g_a, g1_b} (G1 xyzz), sum2 = g2_b: writes A || B || C affine
-int groth16_assemble(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, const void* sums1, const void* sum2, void* d_out);
+// the proof's tail, on the context's current lane (ctx->cur()): sums1 = {h_acc, l_acc - (r s) delta, g_a, g1_b, T}
+int groth16_straus(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, void* sums1);      // T = s g_a + r g1_b
+int point_to_affine(pcdgpu_ctx* ctx, int curve, const void* src_xyzz, size_t idx, void* dst_affine);
+int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_c);  // C = T + l' + h, affine
 int groth16_serialize(pcdgpu_ctx* ctx, int pairing, const void* d_proof, unsigned char* d_out);
 int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double* ms_out);
