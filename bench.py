@@ -199,7 +199,10 @@ def run_gpu(args, rank, local_rank, world):
     g = pcd_b200.Groth16(ctx, pcd_b200.MNT4_298)
     pk = pcd_b200.ProvingKey(pairing=0, **inst["pk"])
     cm = pcd_b200.ConstraintMatrices(0, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"])
+    if os.environ.get("PCD_MSM_WINDOW"):  # development aid: override the window size of the resident tables
+        ctx.set_msm_window(int(os.environ["PCD_MSM_WINDOW"]))
     idx = g.index(pk, cm, precompute=not args.no_precompute)
+    ctx.set_msm_window(0)
     ctx.sync()
     if log:
         log("key resident on the GPU (precompute=%s)" % (not args.no_precompute))

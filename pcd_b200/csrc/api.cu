@@ -265,7 +265,13 @@ int pcdgpu_bases_upload(pcdgpu_ctx* ctx, int curve, const void* bases, size_t n,
   b->table = nullptr;
   size_t rows = 1;
   if (precompute && n > 0) {
+    // key queries (ctx->key_upload): the five MSMs of a proof run side by side, so the latency-bound bucket
+    // reduction competes with the other lanes' accumulation for issue slots and a window one bit smaller (half
+    // the buckets) wins even though the accumulation grows: measured with the full proof at 2^20, c = 18: 26.5 ms,
+    // 19: 29.4, 20: 35.8; at 2^18, c = 17: 9.8 ms, 18: 11.6, 16: 10.2 (a lone MSM still prefers the larger window)
+    // (at 2^16 the larger window still wins: 5.1 vs 6.0 ms; at 2^17 they tie -- hence only from 2^18 up)
     b->c = ctx->msm_window > 0 ? ctx->msm_window : msm_auto_window_c(n, 1);
+    if (ctx->msm_window <= 0 && ctx->key_upload && b->c >= 18) b->c -= 1;
     b->nwin = msm_num_windows_c(b->c);
     rows = b->nwin;
   }
@@ -542,6 +548,7 @@ int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_i
     for (int i = 0; i < n_extra; i++) memcpy(buf.data() + (n + i) * pb, extra[i], pb);
     return pcdgpu_bases_upload(ctx, curve, buf.data(), n + n_extra, precompute, out);
   };
+  ctx->key_upload = true;
   const void* ea[3] = {delta_g1, a_query, alpha_g1};
   const void* eb1[3] = {delta_g1, b_g1_query, beta_g1};
   const void* eb2[3] = {delta_g2, b_g2_query, beta_g2};
@@ -551,6 +558,7 @@ int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_i
   rc = rc ? rc : upload_ext(g2, b_g2_query, 1, num_vars - 1, eb2, 3, &pk->b_g2_query);
   rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, h_query, h_len, precompute, &pk->h_query);
   rc = rc ? rc : upload_ext(g1, l_query, 0, num_vars - num_inputs, el, 1, &pk->l_query);
+  ctx->key_upload = false;
   (void)s1;
   (void)s2;
   if (rc) {

@@ -62,6 +62,7 @@ struct pcdgpu_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   int msm_window = 0;
+  bool key_upload = false;  // set while a proving key's queries are uploaded (window rule of concurrent MSMs)
   char err[512] = {0};
   // Lanes: the five MSMs of a proof are independent, so each runs on its own stream with its own
   // scratch and their latency-bound phases (bucket reduction, window combination) overlap the

@@ -299,11 +299,13 @@ int pcdgpu_gm17_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_sap_vars, siz
   const void* ec2[1] = {c_query_2};
   const void* eg[1] = {g_gamma2_z_t};
   int rc = 0;
+  ctx->key_upload = true;  // window rule of concurrent MSMs (pcdgpu_bases_upload)
   rc = rc ? rc : upload_ext(g1, a_query, 1, num_sap_vars - 1, ea, 2, &pk->a_query);
   rc = rc ? rc : upload_ext(g2, b_query, 1, num_sap_vars - 1, eb, 2, &pk->b_query);
   rc = rc ? rc : upload_ext(g1, c_query_1, 0, num_sap_vars - num_inputs, ec1, 2, &pk->c_query_1);
   rc = rc ? rc : upload_ext(g1, c_query_2, 1, num_sap_vars - 1, ec2, 1, &pk->c_query_2);
   rc = rc ? rc : upload_ext(g1, g_gamma2_z_t, 0, h_len, eg, 1, &pk->g_gamma2_z_t);
+  ctx->key_upload = false;
   if (rc) {
     pcdgpu_gm17_pk_free(pk);
     return rc;

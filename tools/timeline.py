@@ -15,10 +15,11 @@ from pcd_b200 import synthetic  # noqa: E402
 log_n = int(os.environ.get("LOG_N", "20"))
 ctx = pcd_b200.Context(0)
 dev = torch.device("cuda:0")
-inst = synthetic.make_groth16_instance(ctx, 0, log_n)
-g = pcd_b200.Groth16(ctx, 0)
-idx = g.index(pcd_b200.ProvingKey(pairing=0, **inst["pk"]),
-              pcd_b200.ConstraintMatrices(0, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"]),
+PAIRING = int(os.environ.get("PAIRING", "0"))
+inst = synthetic.make_groth16_instance(ctx, PAIRING, log_n)
+g = pcd_b200.Groth16(ctx, PAIRING)
+idx = g.index(pcd_b200.ProvingKey(pairing=PAIRING, **inst["pk"]),
+              pcd_b200.ConstraintMatrices(PAIRING, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"]),
               precompute=True)
 z = torch.from_numpy(inst["z"].view(np.int64)).to(dev)
 r = np.array([5, 6, 7, 8, 0], dtype=np.uint64)
