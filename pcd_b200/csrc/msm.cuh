@@ -21,6 +21,8 @@
 // With precomputed bases (pcdgpu_bases_upload(..., precompute = 1)) the table holds 2^(c j) P for
 // every window j, all windows share ONE bucket set and step 6's doubling chain disappears.
 #pragma once
+#include <cstdlib>
+
 #include <cub/device/device_radix_sort.cuh>
 #include <cub/device/device_scan.cuh>
 
@@ -473,7 +475,10 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   if (acc_ctas < 1) acc_ctas = 1;
   // two CTAs (8 warps) per SM already saturate the multiply pipe (tools/probe_modmul.py); the registers left
   // free let the other lanes' latency-bound kernels (reduction, sorting, assembly) run beside this one
-  if (ctx->concurrent && acc_ctas > 2) acc_ctas = 2;
+  static const int acc_cap_env = getenv("PCDGPU_ACC_CTAS") ? atoi(getenv("PCDGPU_ACC_CTAS")) : 0;  // development aid
+  const int acc_cap = acc_cap_env > 0 ? acc_cap_env : 2;
+  // (measured again with 3 and 4 CTAs per SM, forced to 128 registers: the accumulation gets slower, not faster)
+  if (acc_ctas > acc_cap) acc_ctas = acc_cap;
   size_t acc_grid = (size_t)acc_ctas * ctx->sm_count;
   if (acc_grid > (nbuckets + 127) / 128) acc_grid = (nbuckets + 127) / 128;
   // One thread walks a bucket only up to 4 x the average size.  Real witnesses repeat values (0, 1, 2, -1,
