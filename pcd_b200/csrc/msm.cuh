@@ -36,6 +36,7 @@ static constexpr int MSM_MAX_HEAVY = 16384;  // size of the heavy-bucket list
 static constexpr int MSM_HEAVY_CHUNK = 1024;  // entries of a heavy bucket summed by one CTA at a time
 static constexpr int MSM_SUM_PER_CTA = 256;   // points folded by one CTA of msm_sum_kernel (two per thread + tree)
 static constexpr int MSM_REDUCE_LOGL = 3;     // bucket reduction: 2^3 buckets per thread
+static constexpr int MSM_MAX_SPLIT = 4;       // parts a bucket's entry list may be cut into (msm_accumulate_kernel)
 
 // Window layout.  Plain MSMs use windows of c bits from bit 0 up.  With precomputed tables all windows
 // share one bucket set, and a short top window (299 mod c real bits) would pile every scalar's top digit
@@ -144,34 +145,51 @@ __device__ __forceinline__ AffinePoint<typename C::Fast::F> ld_base(const void* 
   else return fast_affine<C>(ld_vec<AffinePoint<typename C::F>>(bases, idx));
 }
 
+// `split` > 1: every bucket's entry list is cut into `split` equal parts walked by different threads (their sums land in
+// partials[g * split + part] and msm_fold_parts adds them up).  With one thread per bucket and equally long buckets the
+// kernel's time is the number of bucket "waves" rounded UP (2^17 buckets on 296 x 128 threads: 3.46 -> 4); parts make
+// the waves short enough for the rounding not to matter.
 template <class C, bool PRE>
 __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restrict__ bases,
                                                              const u32* __restrict__ offsets,
                                                              const u32* __restrict__ entries,
                                                              const u32* __restrict__ perm, size_t nbuckets,
                                                              void* __restrict__ buckets, u32* __restrict__ heavy,
-                                                             u32* __restrict__ queue, u32 heavy_thr) {
+                                                             u32* __restrict__ queue, u32 heavy_thr, u32 split,
+                                                             u32* __restrict__ hflag) {
   typedef typename C::F F;
   typedef typename C::Fast CF;    // the radix-2^30 twin of a G1 curve (ec.cuh); C itself for G2
   typedef typename CF::F FF;
   const unsigned lane = threadIdx.x & 31;
+  const size_t nitems = nbuckets * split;
   for (;;) {
     u32 first = 0;
     if (lane == 0) first = atomicAdd(queue, 32u);
     first = __shfl_sync(0xffffffffu, first, 0);
-    if (first >= nbuckets) break;
+    if (first >= nitems) break;
     size_t t = (size_t)first + lane;
-    if (t >= nbuckets) continue;
-    size_t g = perm[t];
+    if (t >= nitems) continue;
+    const u32 part = (u32)(t % split);
+    size_t g = perm[t / split];
     u32 lo = offsets[g], hi = offsets[g + 1];
     XYZZ<CF> acc = XYZZ<CF>::inf();
     if (hi - lo > heavy_thr) {
+      if (part != 0) continue;  // part 0 speaks for the whole bucket
       u32 slot = atomicAdd(&heavy[0], 1u);
       if (slot < (u32)MSM_MAX_HEAVY) {
         heavy[1 + slot] = (u32)g;
-        continue;  // msm_accumulate_heavy writes the bucket
+        hflag[g] = 0xffffffffu;  // msm_accumulate_heavy writes the bucket; msm_fold_parts leaves it alone
+        continue;
       }
-      // list full: fall through and do it serially (correct, slow)
+      // list full: fall through and do it serially (correct, slow); the other parts stay infinity
+      if (split > 1) {
+        for (u32 q = 1; q < split; q++) st_vec(buckets, g * split + q, slow_xyzz<C>(acc));
+      }
+    } else if (split > 1) {
+      const u32 len = hi - lo;
+      const u32 a = lo + (u32)(((unsigned long long)len * part) / split);
+      hi = lo + (u32)(((unsigned long long)len * (part + 1)) / split);
+      lo = a;
     }
     for (u32 e = lo; e < hi; e++) {
       u32 ent = entries[e];
@@ -179,8 +197,18 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
       if (ent >> 31) p.y = p.y.neg();
       acc.madd(p);
     }
-    st_vec(buckets, g, slow_xyzz<C>(acc));
+    st_vec(buckets, g * split + part, slow_xyzz<C>(acc));
   }
+}
+// buckets[g] = sum of the `split` partial sums of bucket g (unless the heavy path owns the bucket)
+template <class C>
+__global__ void __launch_bounds__(128) msm_fold_parts_kernel(const void* __restrict__ partials, size_t nbuckets, u32 split,
+                                                             const u32* __restrict__ hflag, void* __restrict__ buckets) {
+  size_t g = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (g >= nbuckets || hflag[g] == 0xffffffffu) return;
+  XYZZ<C> acc = ld_vec_rw<XYZZ<C>>(partials, g * split);
+  for (u32 q = 1; q < split; q++) acc.add(ld_vec_rw<XYZZ<C>>(partials, g * split + q));
+  st_vec(buckets, g, acc);
 }
 
 // CTA-wide tree sum of one xyzz point per thread (shared memory, MSM_HEAVY_THREADS entries)
@@ -423,7 +451,6 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   // counts | offsets | cursor | size keys (in, out) | bucket ids (in, out), each nbuckets + 1, then the heavy list
   size_t cstride = (nbuckets + 1 + 3) & ~(size_t)3;
   PCD_TRY(ctx->scratch(SLOT_MSM_CNT, (7 * cstride + MSM_MAX_HEAVY + 8) * 4, &cnt));
-  PCD_TRY(ctx->scratch(SLOT_MSM_BKT, nbuckets * sizeof(XYZZ<C>), &bkt));
   u32* counts = (u32*)cnt;
   u32* offsets = counts + cstride;
   u32* cursor = offsets + cstride;
@@ -480,19 +507,29 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   // (measured again with 3 and 4 CTAs per SM, forced to 128 registers: the accumulation gets slower, not faster)
   if (acc_ctas > acc_cap) acc_ctas = acc_cap;
   size_t acc_grid = (size_t)acc_ctas * ctx->sm_count;
-  if (acc_grid > (nbuckets + 127) / 128) acc_grid = (nbuckets + 127) / 128;
   // One thread walks a bucket only up to 4 x the average size.  Real witnesses repeat values (0, 1, 2, -1,
   // ...): every copy of a value lands in the same bucket of each window, and a 500-entry bucket walked by
   // one thread (7 ms) would set the kernel's duration; such buckets go to the CTA-parallel heavy path.
   size_t avg_entries = total / nbuckets;
   u32 heavy_thr = (u32)(4 * avg_entries < 64 ? 64 : (4 * avg_entries > (size_t)MSM_HEAVY ? (size_t)MSM_HEAVY : 4 * avg_entries));
+  // bucket parts: at least ~6 waves of work items, at least 8 entries per part
+  u32 split = 1;
+  while (split < (u32)MSM_MAX_SPLIT && nbuckets * split < 6 * acc_grid * 128 && avg_entries / (2 * split) >= 8) split *= 2;
+  if (acc_grid > (nbuckets * split + 127) / 128) acc_grid = (nbuckets * split + 127) / 128;
+  PCD_TRY(ctx->scratch(SLOT_MSM_BKT, nbuckets * sizeof(XYZZ<C>) * (split > 1 ? 1 + split : 1), &bkt));  // buckets | parts
+  void* acc_out = split > 1 ? (void*)((char*)bkt + nbuckets * sizeof(XYZZ<C>)) : bkt;
   if (shared)
     msm_accumulate_kernel<C, true><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                     bkt, heavy, queue, heavy_thr);
+                                                                     acc_out, heavy, queue, heavy_thr, split, cursor);
   else
     msm_accumulate_kernel<C, false><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                      bkt, heavy, queue, heavy_thr);
+                                                                      acc_out, heavy, queue, heavy_thr, split, cursor);
   PCD_CUDA(ctx, cudaGetLastError());
+  if (split > 1) {
+    msm_fold_parts_kernel<C><<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(acc_out, nbuckets, split, cursor, bkt);
+    PCD_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+  }
   size_t heavy_smem = MSM_HEAVY_THREADS * sizeof(XYZZ<C>);
   // heavy-bucket partial list: at most one partial per MSM_HEAVY_CHUNK entries plus one per bucket
   size_t hp_cap = total / MSM_HEAVY_CHUNK + MSM_MAX_HEAVY + 8;
