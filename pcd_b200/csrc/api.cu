@@ -587,6 +587,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   CHECK_ARG(ctx, pk->num_vars == r1cs->num_inputs + r1cs->num_witness && pk->num_inputs == r1cs->num_inputs,
             "key and constraint system disagree on the variable counts");
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  InProofGuard in_proof(ctx);
   int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
   const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
   size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;

@@ -62,6 +62,7 @@ struct pcdgpu_ctx {
   cudaStream_t own_stream = nullptr;
   cudaStream_t stream = nullptr;
   int msm_window = 0;
+  bool in_proof = false;     // inside a prover entry point: its MSMs run side by side on the lanes
   bool key_upload = false;  // set while a proving key's queries are uploaded (window rule of concurrent MSMs)
   char err[512] = {0};
   // Lanes: the five MSMs of a proof are independent, so each runs on its own stream with its own
@@ -135,6 +136,12 @@ struct pcdgpu_ctx {
     *out = slot[id];
     return 0;
   }
+};
+
+struct InProofGuard {  // marks the context as "inside a prover call" for the MSM launch heuristics
+  pcdgpu_ctx* c;
+  explicit InProofGuard(pcdgpu_ctx* ctx) : c(ctx) { c->in_proof = true; }
+  ~InProofGuard() { c->in_proof = false; }
 };
 
 enum {

@@ -500,11 +500,11 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   if (shared) PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, true>, 128, 0));
   else PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, false>, 128, 0));
   if (acc_ctas < 1) acc_ctas = 1;
-  // two CTAs (8 warps) per SM already saturate the multiply pipe (tools/probe_modmul.py); the registers left
-  // free let the other lanes' latency-bound kernels (reduction, sorting, assembly) run beside this one
+  // CTAs per SM (measured, bench.py): side by side with the other lanes of a proof two CTAs (8 warps) are best -- the
+  // registers left free let the latency-bound kernels (reduction, sorting, tails) run beside this one; a lone MSM
+  // gains 4 % from a third CTA (5.99 -> 5.77 ms at 2^20); a fourth, forced to 128 registers, is slower.
   static const int acc_cap_env = getenv("PCDGPU_ACC_CTAS") ? atoi(getenv("PCDGPU_ACC_CTAS")) : 0;  // development aid
-  const int acc_cap = acc_cap_env > 0 ? acc_cap_env : 2;
-  // (measured again with 3 and 4 CTAs per SM, forced to 128 registers: the accumulation gets slower, not faster)
+  const int acc_cap = acc_cap_env > 0 ? acc_cap_env : (ctx->concurrent && ctx->in_proof ? 2 : 3);
   if (acc_ctas > acc_cap) acc_ctas = acc_cap;
   size_t acc_grid = (size_t)acc_ctas * ctx->sm_count;
   // One thread walks a bucket only up to 4 x the average size.  Real witnesses repeat values (0, 1, 2, -1,

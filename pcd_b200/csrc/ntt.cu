@@ -16,9 +16,23 @@
 #include "common.cuh"
 #include "ntt.cuh"
 
-static constexpr int NTT_THREADS = 256;
-static constexpr int NTT_TILE_LOG = 11;  // elements per CTA tile (2^11 x 40 B = 80 KiB)
+#include <cstdlib>
+static constexpr int NTT_THREADS = 256;  // upper bound (launch bounds); the launch uses ntt_threads()
 static constexpr int NTT_MAX_R = 8;
+// Elements per CTA tile and threads per CTA.  Measured on B200 (tools/probe_ntt.py, coset FFT over r4, ms at
+// 2^16 / 2^20 / 2^24): tile 2^11 x 256 threads 0.133 / 0.534 / 8.29;  2^10 x 128: 0.096 / 0.436 / 7.42;
+// 2^9 x 128: 0.054 / 0.416 / 7.29 (chosen);  2^9 x 256: 0.045 / 0.507 / 9.27;  2^8 x 64: 0.056 / 0.412 / 7.94.
+// A 20 KiB tile lets ~10 CTAs share an SM, so one CTA's barriers and twiddle loads hide behind the others'
+// butterflies; the shorter runs of contiguous elements per row (2^9 / 2^r x 40 B) cost nothing because DRAM is
+// < 10 % busy.  PCDGPU_NTT_TILE_LOG / PCDGPU_NTT_THREADS override them for sweeps (development aid).
+static int ntt_tile_log() {
+  static const int v = getenv("PCDGPU_NTT_TILE_LOG") ? atoi(getenv("PCDGPU_NTT_TILE_LOG")) : 9;
+  return v < NTT_MAX_R ? NTT_MAX_R : (v > 12 ? 12 : v);
+}
+static int ntt_threads() {
+  static const int v = getenv("PCDGPU_NTT_THREADS") ? atoi(getenv("PCDGPU_NTT_THREADS")) : 128;
+  return v < 32 ? 32 : (v > NTT_THREADS ? NTT_THREADS : v);
+}
 
 template <class F>
 __device__ __forceinline__ F ld_elem(const u32* g, size_t idx) {
@@ -74,6 +88,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass a) {
   const int k = a.log_n;
   const size_t b = blockIdx.x;
   const int tid = threadIdx.x;
+  const int nthr = blockDim.x;
   a.src += (size_t)blockIdx.y * a.batch_stride * 10;
   a.dst += (size_t)blockIdx.y * a.batch_stride * 10;
 
@@ -84,7 +99,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass a) {
     high = b >> lb;
   }
   // ---- load ------------------------------------------------------------------------------
-  for (int e = tid; e < tile; e += NTT_THREADS) {
+  for (int e = tid; e < tile; e += nthr) {
     int j = e >> a.logW, c = e & (W - 1);
     size_t idx;
     if (a.first) {
@@ -105,7 +120,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass a) {
   for (int u = 0; u < a.r; u++) {
     __syncthreads();
     const int sh = k - a.s - u - 1;
-    for (int q = tid; q < (tile >> 1); q += NTT_THREADS) {
+    for (int q = tid; q < (tile >> 1); q += nthr) {
       int c = q & (W - 1), jj = q >> a.logW;
       int lo = jj & ((1 << u) - 1);
       int j = ((jj >> u) << (u + 1)) | lo;
@@ -142,7 +157,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass a) {
   // ---- store -----------------------------------------------------------------------------
   F pc;
   if (a.last && a.post_c) pc = ldg_elem<F>(a.post_c, 0);
-  for (int e = tid; e < tile; e += NTT_THREADS) {
+  for (int e = tid; e < tile; e += nthr) {
     int j, c;
     size_t idx;
     if (a.first) {  // rows are contiguous in the output: j fastest
@@ -248,7 +263,10 @@ static int ntt_run_t(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int in
   if (log_n == 0) return 0;  // n = 1: every flavour is the identity
   NttTablesDev t;
   PCD_TRY(ntt_tables(ctx, field, log_n, &t));
-  const int max_smem = 10 * (1 << NTT_MAX_R) * ((1 << (NTT_TILE_LOG - NTT_MAX_R)) + 1) * 4;  // r = 8, W = 8
+  const int NTT_TILE_LOG = ntt_tile_log();
+  // largest tile in shared memory: a multi-pass tile (r = 8, W = 2^(tile - 8)) or the single-pass case (r = 10, W = 1)
+  int max_smem = 10 * (1 << NTT_MAX_R) * ((1 << (NTT_TILE_LOG - NTT_MAX_R)) + 1) * 4;
+  if (max_smem < 10 * 1024 * 2 * 4) max_smem = 10 * 1024 * 2 * 4;
   PCD_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   int passes = log_n <= 10 ? 1 : (log_n + NTT_MAX_R - 1) / NTT_MAX_R;
   void* scratch = nullptr;
@@ -276,7 +294,7 @@ static int ntt_run_t(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int in
     int R = 1 << r, W = 1 << a.logW;
     size_t smem = (size_t)10 * R * (W + 1) * 4;
     dim3 grid((unsigned)(((size_t)1 << log_n) >> (r + a.logW)), (unsigned)batch);
-    ntt_pass_kernel<F><<<grid, NTT_THREADS, smem, ctx->stream>>>(a);
+    ntt_pass_kernel<F><<<grid, ntt_threads(), smem, ctx->stream>>>(a);
     PCD_CUDA(ctx, cudaGetLastError());
     s += r;
   }
