@@ -9,7 +9,7 @@
 // into passes of r <= 8 stages; one CTA owns a tile of 2^r "rows" (the indices that interact in
 // those stages) x W "columns" (neighbouring independent transforms, so that every global access is
 // a run of W contiguous 40-byte elements), keeps it in shared memory in limb-major planes
-// (bank-conflict free for the butterflies) and runs the r stages there.  The first pass folds the
+// (swizzled so that the butterflies are bank-conflict free, ntt_sm_index) and runs the r stages there.  The first pass folds the
 // bit reversal into its (strided) load and writes contiguous rows; later passes work in place.
 // Coset scaling (g^i before a forward transform, g^-i / n after an inverse one) is fused into
 // the first load / last store.  HBM traffic per pass = one read + one write of the vector.
@@ -77,14 +77,24 @@ struct NttPass {
   size_t batch_stride;  // elements between consecutive transforms of a batch (blockIdx.y)
 };
 
+// Shared-memory word of element (row j, column c) inside a limb plane: i = j W + c with the low five bits flipped
+// when bit 5 is set.  In butterfly stage u the 32 lanes of a warp touch rows whose index has bit u fixed, i.e.
+// i has one of its low five bits fixed and bit 5 varying -- with a linear (or padded-pitch) layout that is a
+// two-way bank conflict on every access of the first 5 - log W stages (ncu: 21 M conflicts per pass); the flip
+// moves the two halves onto complementary banks.  Conflict free for every stage, W and r (checked by enumeration).
+__device__ __forceinline__ int ntt_sm_index(int j, int c, int logW) {
+  int i = (j << logW) | c;
+  return i ^ ((i & 32) ? 31 : 0);
+}
+
 template <class F>
 __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass a) {
   extern __shared__ u32 sm[];
   const int W = 1 << a.logW;
   const int R = 1 << a.r;
-  const int pitch = W + 1;            // row pitch (odd for W >= 2: column reads are conflict free)
-  const int plane = R * pitch;        // words per limb plane
   const int tile = 1 << (a.r + a.logW);
+  const int plane = tile;             // words per limb plane
+  (void)R;
   const int k = a.log_n;
   const size_t b = blockIdx.x;
   const int tid = threadIdx.x;
@@ -111,7 +121,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass a) {
     }
     F v = ld_elem<F>(a.src, idx);
     if (a.first && a.pre) v = v * ldg_elem<F>(a.pre, idx);
-    u32* dst = sm + j * pitch + c;
+    u32* dst = sm + ntt_sm_index(j, c, a.logW);
 #pragma unroll
     for (int l = 0; l < 10; l++) dst[l * plane] = v.l[l];
   }
@@ -124,8 +134,8 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass a) {
       int c = q & (W - 1), jj = q >> a.logW;
       int lo = jj & ((1 << u) - 1);
       int j = ((jj >> u) << (u + 1)) | lo;
-      u32* p1 = sm + j * pitch + c;
-      u32* p2 = p1 + (pitch << u);
+      u32* p1 = sm + ntt_sm_index(j, c, a.logW);
+      u32* p2 = sm + ntt_sm_index(j + (1 << u), c, a.logW);
       F A, B;
 #pragma unroll
       for (int l = 0; l < 10; l++) {
@@ -173,7 +183,7 @@ __global__ void __launch_bounds__(NTT_THREADS) ntt_pass_kernel(NttPass a) {
       c = e & (W - 1);
       idx = (high << (a.s + a.r)) | ((size_t)j << a.s) | lowbase | (size_t)c;
     }
-    const u32* srcp = sm + j * pitch + c;
+    const u32* srcp = sm + ntt_sm_index(j, c, a.logW);
     F v;
 #pragma unroll
     for (int l = 0; l < 10; l++) v.l[l] = srcp[l * plane];
@@ -264,9 +274,9 @@ static int ntt_run_t(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int in
   NttTablesDev t;
   PCD_TRY(ntt_tables(ctx, field, log_n, &t));
   const int NTT_TILE_LOG = ntt_tile_log();
-  // largest tile in shared memory: a multi-pass tile (r = 8, W = 2^(tile - 8)) or the single-pass case (r = 10, W = 1)
-  int max_smem = 10 * (1 << NTT_MAX_R) * ((1 << (NTT_TILE_LOG - NTT_MAX_R)) + 1) * 4;
-  if (max_smem < 10 * 1024 * 2 * 4) max_smem = 10 * 1024 * 2 * 4;
+  // largest tile in shared memory: a multi-pass tile (2^tile elements) or the single-pass case (2^10)
+  int max_smem = 10 * (1 << NTT_TILE_LOG) * 4;
+  if (max_smem < 10 * 1024 * 4) max_smem = 10 * 1024 * 4;
   PCD_CUDA(ctx, cudaFuncSetAttribute(ntt_pass_kernel<F>, cudaFuncAttributeMaxDynamicSharedMemorySize, max_smem));
   int passes = log_n <= 10 ? 1 : (log_n + NTT_MAX_R - 1) / NTT_MAX_R;
   void* scratch = nullptr;
@@ -292,7 +302,7 @@ static int ntt_run_t(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int in
     a.inverse = inverse;
     a.batch_stride = (size_t)1 << log_n;
     int R = 1 << r, W = 1 << a.logW;
-    size_t smem = (size_t)10 * R * (W + 1) * 4;
+    size_t smem = (size_t)10 * R * W * 4;
     dim3 grid((unsigned)(((size_t)1 << log_n) >> (r + a.logW)), (unsigned)batch);
     ntt_pass_kernel<F><<<grid, ntt_threads(), smem, ctx->stream>>>(a);
     PCD_CUDA(ctx, cudaGetLastError());
