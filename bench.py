@@ -324,6 +324,7 @@ def run_gpu(args, rank, local_rank, world):
     prof = {"ms": list(ms), "units": list(units), "spans": list(spans)}
 
     # ---- timed region 2: end to end through the C ABI with host buffers ---------------------------------
+    run_steps(0, len(lanes), host=True)  # untimed: grows the host path's staging scratch on every in-flight context
     barrier()
     dev_ms, wall_ms = run_steps(args.warmup + args.steps, args.steps, host=True)
     barrier()

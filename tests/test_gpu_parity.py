@@ -318,7 +318,8 @@ def test_gm17_golden(ctx):
             idx.close()
 
 
-@pytest.mark.parametrize("pairing,m,ni", [(0, 1000, 2), (1, 1000, 4), (0, (1 << 12) - 3, 3), (1, (1 << 11) + 5, 2)])
+@pytest.mark.parametrize("pairing,m,ni", [(0, 1000, 2), (1, 1000, 4), (0, (1 << 12) - 3, 3), (1, (1 << 11) + 5, 2),
+                                          (0, 300, 1), (1, 7, 1)])
 def test_gm17_vs_oracle_and_trapdoor(ctx, pairing, m, ni):
     inst = synth.make_gm17_instance(pairing, m, seed=700 + m, bitlike=0.4, num_inputs=ni)
     p = codec.FIELD_P[pairing]

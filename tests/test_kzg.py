@@ -133,6 +133,16 @@ def test_gpu_kzg_commit_open(ctx, pairing, deg, pre):
             assert _unmont(proof.random_v, field)[0] == rv
         wlog = ko.expected_open_log(p, beta, gamma, poly, z, blind_ints)
         assert np.array_equal(proof.w, co.fixed_base_mul(g1, G, codec.ints_to_limbs([wlog]), 1)[0])
+    # the zero polynomial and a polynomial with leading / trailing zero coefficients (upstream skips leading zeros)
+    zero = [0] * 9
+    c, _ = K.commit(powers, _mont(zero, field))
+    assert not c.any() and np.array_equal(c, ko.commit(pairing, pg, pgg, zero, None))
+    sparse = [0, 0, 0, 5, 0, pow(3, 50, p), 0, 0]
+    c, rand = K.commit(powers, _mont(sparse, field))
+    assert np.array_equal(c, ko.commit(pairing, pg, pgg, sparse, None, 2))
+    proof, value = K.open(powers, _mont(sparse, field), _mont([0], field)[0], rand)   # opening at z = 0
+    w, v, _ = ko.open_(pairing, pg, pgg, sparse, 0, None, 2)
+    assert np.array_equal(proof.w, w) and _unmont(value, field)[0] == v == 0
     # a polynomial larger than the committer key is refused (check_degree_is_within_bounds)
     import pcd_b200
     with pytest.raises(ValueError):
