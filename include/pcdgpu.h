@@ -135,6 +135,13 @@ void pcdgpu_r1cs_free(pcdgpu_r1cs* r);
 size_t pcdgpu_r1cs_domain_size(const pcdgpu_r1cs* r);
 /* z: num_inputs + num_witness elements (instance || witness, z[0] = 1); h: n elements */
 int pcdgpu_witness_map(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* z, void* h);
+/* The same map in two stages, for spreading its three independent vectors over the GPUs of a box (the a, b, c
+ * chains of R1CStoQAP::witness_map never interact before the pointwise step; a single NTT is not split):
+ *   stage 1 (any GPU holding the matrices): d_out = coset_fft(ifft(M z)), which = 0: A (with the instance rows),
+ *            1: B, 2: C; n = pcdgpu_r1cs_domain_size elements, device memory, asynchronous on the context's stream
+ *   stage 2 (one GPU, after the vectors were copied to it): d_a <- coset_ifft((a * b - c) / Z) = h */
+int pcdgpu_qap_vector_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, int which, const void* d_z, void* d_out);
+int pcdgpu_qap_combine_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, void* d_a, const void* d_b, const void* d_c);
 
 /* ---- Groth16 --------------------------------------------------------------------------------
  * Replaces ark-groth16 create_proof_with_reduction (Groth16::prove).  The key is uploaded once

@@ -510,6 +510,20 @@ int pcdgpu_witness_map(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* z, voi
   return 0;
 }
 
+int pcdgpu_qap_vector_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, int which, const void* d_z, void* d_out) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, r && d_z && d_out && which >= 0 && which <= 2, "bad argument");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return qap_vector_dev(ctx, r, which, d_z, d_out);
+}
+
+int pcdgpu_qap_combine_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, void* d_a, const void* d_b, const void* d_c) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, r && d_a && d_b && d_c, "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  return qap_combine_dev(ctx, r, d_a, d_b, d_c);
+}
+
 // ---- Groth16 ------------------------------------------------------------------------------------------
 int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_inputs, size_t h_len,
                      const void* alpha_g1, const void* beta_g1, const void* delta_g1, const void* beta_g2,

@@ -15,10 +15,10 @@
 // variables (the rows that make the QAP's A polynomials linearly independent); 0 elsewhere.
 template <class F>
 __global__ void __launch_bounds__(128) spmv_kernel(CsrDev A, CsrDev B, CsrDev C, const u32* __restrict__ z, size_t m,
-                                                   size_t num_inputs, size_t n, u32* a, u32* b, u32* c) {
+                                                   size_t num_inputs, size_t n, u32* a, u32* b, u32* c, int mat_base) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
-  int mat = blockIdx.y;
+  int mat = blockIdx.y + mat_base;
   const CsrDev& M = mat == 0 ? A : (mat == 1 ? B : C);
   u32* out = mat == 0 ? a : (mat == 1 ? b : c);
   F acc = F::zero();
@@ -63,7 +63,7 @@ static int witness_map_t(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z,
   int ps = ctx->prof_begin(PROF_SPMV, (double)r->m * 3);
   ctx->launches += 2;
   spmv_kernel<F><<<grid, 128, 0, ctx->stream>>>(r->A, r->B, r->C, (const u32*)d_z, r->m, r->num_inputs, n, (u32*)a,
-                                                (u32*)b, (u32*)c);
+                                                (u32*)b, (u32*)c, 0);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   void* v[3] = {a, b, c};
@@ -79,6 +79,48 @@ static int witness_map_t(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z,
   PCD_TRY(ntt_run_general(ctx, field, a, r->dom_a, r->dom_b, 1, 1));
   *d_h = a;
   return 0;
+}
+
+// ---- the witness map in two stages, for distributing the three vectors over GPUs -------------
+// stage 1: d_out = coset_fft(ifft(M z)) for ONE of the matrices (which = 0: A with the instance rows, 1: B, 2: C)
+template <class F>
+static int qap_vector_t(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, int which, const void* d_z, void* d_out) {
+  int field = r->pairing == PCDGPU_MNT4_298 ? PCDGPU_FIELD_R4 : PCDGPU_FIELD_Q4;
+  if (r->dom_a < 0) {
+    ctx->set_error("witness map needs a domain of %zu elements; the field has none that large", r->m + r->num_inputs);
+    return PCDGPU_E_DOMAIN;
+  }
+  size_t n = r->n;
+  dim3 grid((unsigned)((n + 127) / 128), 1);
+  int ps = ctx->prof_begin(PROF_SPMV, (double)r->m);
+  ctx->launches += 1;
+  spmv_kernel<F><<<grid, 128, 0, ctx->stream>>>(r->A, r->B, r->C, (const u32*)d_z, r->m, r->num_inputs, n, (u32*)d_out,
+                                                (u32*)d_out, (u32*)d_out, which);
+  PCD_CUDA(ctx, cudaGetLastError());
+  ctx->prof_end(ps);
+  PCD_TRY(ntt_run_general(ctx, field, d_out, r->dom_a, r->dom_b, 1, 0));
+  PCD_TRY(ntt_run_general(ctx, field, d_out, r->dom_a, r->dom_b, 0, 1));
+  return 0;
+}
+int qap_vector_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, int which, const void* d_z, void* d_out) {
+  if (r->pairing == PCDGPU_MNT4_298) return qap_vector_t<FpR4>(ctx, r, which, d_z, d_out);
+  return qap_vector_t<FpQ4>(ctx, r, which, d_z, d_out);
+}
+// stage 2: d_a <- coset_ifft((a * b - c) / Z)  (a, b, c: the three stage-1 vectors; the result replaces a)
+int qap_combine_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, void* d_a, const void* d_b, const void* d_c) {
+  int field = r->pairing == PCDGPU_MNT4_298 ? PCDGPU_FIELD_R4 : PCDGPU_FIELD_Q4;
+  size_t n = r->n;
+  const u32* zinv;
+  PCD_TRY(ntt_zinv_general(ctx, field, n, &zinv));
+  ctx->launches += 1;
+  if (field == PCDGPU_FIELD_R4)
+    qap_combine_kernel<FpR4><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((u32*)d_a, (const u32*)d_b,
+                                                                                   (const u32*)d_c, zinv, n);
+  else
+    qap_combine_kernel<FpQ4><<<(unsigned)((n + 255) / 256), 256, 0, ctx->stream>>>((u32*)d_a, (const u32*)d_b,
+                                                                                   (const u32*)d_c, zinv, n);
+  PCD_CUDA(ctx, cudaGetLastError());
+  return ntt_run_general(ctx, field, d_a, r->dom_a, r->dom_b, 1, 1);
 }
 
 int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h) {

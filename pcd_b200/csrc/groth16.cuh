@@ -77,6 +77,8 @@ int bases_msm(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void*
 // a, b, c <- matrices x z; h = coset_ifft((coset_fft(ifft a) * coset_fft(ifft b) - coset_fft(ifft c)) / Z).
 // *d_h points into the context's scratch (n elements, Montgomery form).
 int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h);
+int qap_vector_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, int which, const void* d_z, void* d_out);
+int qap_combine_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, void* d_a, const void* d_b, const void* d_c);
 // extras <- {r, 1, 1, s, 1, 1, -(r s) mod p} as plain integers (the scalars of the constant pairs)
 int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras);
 // the proof's tail, on the context's current lane (ctx->cur()): sums1 = {h_acc, l_acc - (r s) delta, g_a, g1_b, T}

@@ -1,4 +1,7 @@
-"""Point-range sharding of one MSM across the GPUs of a box.
+"""Sharding of the proving path across the GPUs of a box: one MSM by point range, and the witness
+map's three independent vectors by GPU.
+
+Point-range sharding of one MSM:
 
 sum_i s_i P_i is a sum of independent partial sums: rank g keeps points [lo_g, hi_g) of every query
 vector resident, computes an xyzz partial over its range, and the partials (160 / 320 / 480 bytes)
@@ -56,3 +59,40 @@ def sharded_msm(local_partial: Callable[[int, int], np.ndarray], combine: Callab
     lo, hi = shard_range(n, world, rank)
     parts = gather_partials(local_partial(lo, hi), group=group, device=device)
     return combine(parts)
+
+
+# ---- the witness map's three vectors on different GPUs ----------------------------------------------------
+def vector_owner(which: int, world: int) -> int:
+    """Rank that computes vector `which` (0: A z, 1: B z, 2: C z) of R1CStoQAP::witness_map.  Rank 0 combines, so
+    with three or more ranks it keeps a and the others go to ranks 1 and 2; with two ranks rank 1 takes b."""
+    if world <= 0 or not (0 <= which <= 2):
+        raise ValueError("bad vector / world size")
+    return which % world if world < 3 else which
+
+
+def witness_map_by_vector(vector_fn: Callable[[int], "object"], combine_fn: Callable[["object", "object", "object"], "object"],
+                          alloc_fn: Callable[[], "object"], group=None):
+    """a, b, c chains (iFFT -> coset FFT) on different ranks, results sent to rank 0 for (a b - c) / Z and the coset
+    iFFT.  vector_fn(which) -> tensor with this rank's result of stage 1; alloc_fn() -> empty tensor of that shape
+    (receive buffer on rank 0); combine_fn(a, b, c) -> h.  Two point-to-point transfers of n x 40 bytes; a single
+    NTT is never split.  Returns h on rank 0 and None elsewhere."""
+    import torch.distributed as dist
+    if dist.is_available() and dist.is_initialized():
+        world, rank = dist.get_world_size(group), dist.get_rank(group)
+    else:
+        world, rank = 1, 0
+    owners = [vector_owner(k, world) for k in range(3)]
+    mine = {k: vector_fn(k) for k in range(3) if owners[k] == rank}
+    if rank == 0:
+        vecs = []
+        for k in range(3):
+            if owners[k] == 0:
+                vecs.append(mine[k])
+            else:
+                buf = alloc_fn()
+                dist.recv(buf, src=owners[k], group=group)
+                vecs.append(buf)
+        return combine_fn(*vecs)
+    for k, t in mine.items():
+        dist.send(t, dst=0, group=group)
+    return None
