@@ -656,11 +656,18 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
     if (fork && rc == 0 && cudaEventRecord(ctx->ev_join[j + 1], ctx->lane_stream[j + 1]) != cudaSuccess) rc = PCDGPU_E_CUDA;
   }
   ctx->lane = 0;
-  if (rc) return rc;
+  if (rc) {
+    ctx->drain_lanes();
+    return rc;
+  }
   void* d_h;
-  PCD_TRY(witness_map_dev(ctx, r1cs, d_z, &d_h));
+  rc = witness_map_dev(ctx, r1cs, d_z, &d_h);
   // h: n coefficients vs n - 1 query points: truncated to the shorter
-  PCD_TRY(bases_msm(ctx, pk->h_query, 0, d_h, 1, r1cs->n, nullptr, 0, (char*)sums1 + 0 * x1));
+  if (rc == 0) rc = bases_msm(ctx, pk->h_query, 0, d_h, 1, r1cs->n, nullptr, 0, (char*)sums1 + 0 * x1);
+  if (rc) {
+    ctx->drain_lanes();
+    return rc;
+  }
   if (fork)
     for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
   PCD_TRY(groth16_finish(ctx, pk->pairing, sums1, d_C));

@@ -109,6 +109,14 @@ struct pcdgpu_ctx {
     if (id >= 0) cudaEventRecord(spans[id].b, cur());
   }
 
+  // after a failure inside a forked region: let every lane drain before the caller sees the error, so that the
+  // next call cannot reuse scratch a lane is still reading
+  void drain_lanes() {
+    for (int l = 1; l < NLANE; l++)
+      if (lane_stream[l]) cudaStreamSynchronize(lane_stream[l]);
+    lane = 0;
+  }
+
   void set_error(const char* fmt, ...) {
     va_list ap;
     va_start(ap, fmt);

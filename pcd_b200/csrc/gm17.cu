@@ -390,10 +390,17 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
     return rc;
   };
   void *d_full, *d_h;
-  size_t n;
-  PCD_TRY(sap_witness_map_dev(ctx, r1cs, d_z, d_dm, &d_full, &d_h, &n, start_msms));
-  GM17_CHECK_ARG(ctx, pk->h_len == n + 1, "key's g_gamma2_z_t length is not the SAP domain size + 1");
-  PCD_TRY(bases_msm(ctx, pk->g_gamma2_z_t, 0, d_h, 1, n + 1, extras + 5 * 40, 1, (char*)sums1 + 0 * x1));
+  size_t n = 0;
+  int rc = sap_witness_map_dev(ctx, r1cs, d_z, d_dm, &d_full, &d_h, &n, start_msms);
+  if (rc == 0 && pk->h_len != n + 1) {
+    ctx->set_error("key's g_gamma2_z_t length is not the SAP domain size + 1");
+    rc = PCDGPU_E_ARG;
+  }
+  if (rc == 0) rc = bases_msm(ctx, pk->g_gamma2_z_t, 0, d_h, 1, n + 1, extras + 5 * 40, 1, (char*)sums1 + 0 * x1);
+  if (rc) {
+    ctx->drain_lanes();
+    return rc;
+  }
   if (fork)
     for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);

@@ -258,7 +258,7 @@ __device__ unsigned char* ser_x(const Fp<P>& x, unsigned char* out, unsigned cha
   return out + 38;
 }
 template <class B, u32 NR>
-__device__ unsigned char* ser_x(const Fp2T<B, NR>& x, unsigned char* out, unsigned char flags) {
+__device__ unsigned char* ser_x(const Fp2T<B, NR, false>& x, unsigned char* out, unsigned char flags) {
   ser_fp(x.c0, out, 0);
   ser_fp(x.c1, out + 38, flags);
   return out + 76;

@@ -251,7 +251,7 @@ __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_accumulate_heavy_kernel
         u32 ent = entries[e];
         AffinePoint<typename C::Fast::F> p = ld_base<C, PRE>(bases, ent & 0x7fffffffu);
         if (ent >> 31) p.y = p.y.neg();
-        acc.madd(p);
+        acc.madd(p);  // out of line for G2 (inlining it here as well takes msm_c3.cu from 80 s to 5 min of ptxas)
       }
       cta_tree_sum<C>(sm, slow_xyzz<C>(acc));
       if (threadIdx.x == 0) {
