@@ -205,6 +205,20 @@ int pcdgpu_kzg_open(pcdgpu_ctx* ctx, const pcdgpu_bases* powers_of_g, const void
                     const pcdgpu_bases* powers_of_gamma_g, const void* rand_coeffs, size_t n_rand, const void* z,
                     void* out_w_affine, void* out_value, void* out_random_v);
 
+/* The last step of a Groth16 proof computed by several GPUs (MSM point ranges split per GPU): every
+ * rank computes xyzz partial sums of the five MSMs over its slice of each query (pcdgpu_msm_bases_dev; the rank that
+ * holds the constant points delta, query[0], alpha / beta adds them to its slices with scalars r or s, 1, 1 and
+ * -(r s)), the partials are gathered, and one GPU adds them and assembles the proof in two steps so that the
+ * double-scalar multiplication runs while the MSM over h is still going:
+ *   begin  (asynchronous): d_partials_ab = world x 2 xyzz G1 points, rank-major, (a, b_g1) per rank; d_partials_g2 =
+ *          world x 1 (b_g2).  Normalises A and B and computes s g_a + r g1_b.
+ *   finish (synchronous, same context): d_partials_hl = world x 2 (h, l) per rank; writes A || B || C (affine).
+ * The result is bit-identical to pcdgpu_groth16_prove for any number of GPUs (affine points are canonical). */
+int pcdgpu_groth16_assemble_begin_dev(pcdgpu_ctx* ctx, int pairing, const void* r, const void* s, int world,
+                                      const void* d_partials_ab, const void* d_partials_g2);
+int pcdgpu_groth16_assemble_finish_dev(pcdgpu_ctx* ctx, int pairing, int world, const void* d_partials_hl,
+                                       void* out_proof);
+
 /* ark-serialize CanonicalSerialize of the proof (compressed points: x with flag bits 7 = "y is the
  * larger root", 6 = infinity on the last byte): 152 B (MNT4) / 190 B (MNT6).  out: >= 190 bytes. */
 int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affine, uint8_t* out, size_t* out_len);

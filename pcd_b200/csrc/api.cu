@@ -676,6 +676,57 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   return 0;
 }
 
+// layout of the assembly state in SLOT_MISC (shared by the two calls below): rs | sums1 (h, l', g_a, g1_b, T) | sum2 | proof
+int pcdgpu_groth16_assemble_begin_dev(pcdgpu_ctx* ctx, int pairing, const void* r, const void* s, int world,
+                                      const void* d_partials_ab, const void* d_partials_g2) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pairing == PCDGPU_MNT4_298 || pairing == PCDGPU_MNT6_298, "unknown pairing id");
+  CHECK_ARG(ctx, r && s && d_partials_ab && d_partials_g2 && world >= 1, "bad argument");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int g1 = g1_of(pairing), g2 = g2_of(pairing);
+  const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
+  size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
+  void* misc;
+  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
+  char* mb = (char*)misc;
+  u32* d_rs = (u32*)mb;
+  void* sums1 = mb + 512;
+  void* sum2 = (char*)sums1 + 5 * x1;
+  char* d_proof = (char*)sum2 + x2;
+  memcpy(ctx->pinned, r, 40);
+  memcpy((char*)ctx->pinned + 40, s, 40);
+  PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
+  // g_a, g1_b -> sums1[2], sums1[3]; g2_b -> sum2
+  PCD_TRY(groth16_sum_partials(ctx, pairing, d_partials_ab, d_partials_g2, world, 2, 2, (char*)sums1 + 2 * x1, sum2));
+  PCD_TRY(point_to_affine(ctx, g1, sums1, 2, d_proof));
+  PCD_TRY(point_to_affine(ctx, g2, sum2, 0, d_proof + o1->affine_bytes));
+  return groth16_straus(ctx, pairing, d_rs, sums1);
+}
+
+int pcdgpu_groth16_assemble_finish_dev(pcdgpu_ctx* ctx, int pairing, int world, const void* d_partials_hl,
+                                       void* out_proof) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pairing == PCDGPU_MNT4_298 || pairing == PCDGPU_MNT6_298, "unknown pairing id");
+  CHECK_ARG(ctx, d_partials_hl && out_proof && world >= 1, "bad argument");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  int g1 = g1_of(pairing), g2 = g2_of(pairing);
+  const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
+  size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
+  void* misc;
+  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
+  char* mb = (char*)misc;
+  void* sums1 = mb + 512;
+  void* sum2 = (char*)sums1 + 5 * x1;
+  char* d_proof = (char*)sum2 + x2;
+  size_t proof_bytes = 2 * o1->affine_bytes + o2->affine_bytes;
+  // h, l' -> sums1[0], sums1[1]
+  PCD_TRY(groth16_sum_partials(ctx, pairing, d_partials_hl, nullptr, world, 2, 0, sums1, nullptr));
+  PCD_TRY(groth16_finish(ctx, pairing, sums1, d_proof + o1->affine_bytes + o2->affine_bytes));
+  PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
+}
+
 int pcdgpu_groth16_prove(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* z, const void* r,
                          const void* s, void* out_proof) {
   if (!ctx) return PCDGPU_E_ARG;

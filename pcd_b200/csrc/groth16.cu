@@ -212,6 +212,33 @@ __global__ void groth16_finish_kernel(const void* __restrict__ sums1, void* __re
   st_aff<G1>(out_c, 0, acc.to_affine());
 }
 
+// multi-GPU prover: out1[k] = sum over ranks of partials1[rank * n1 + k], k < n1 (G1); out2 = sum of partials2 (G2, n2 = 0 / 1)
+template <class G1, class G2>
+__global__ void groth16_sum_partials_kernel(const void* __restrict__ partials1, const void* __restrict__ partials2,
+                                            int world, int n1, int n2, void* __restrict__ out1, void* __restrict__ out2) {
+  const int k = threadIdx.x >> 5;  // one warp (its lane 0) per point
+  if (threadIdx.x & 31) return;
+  if (k < n1) {
+    XYZZ<G1> acc = XYZZ<G1>::inf();
+    for (int r = 0; r < world; r++) acc.add(ld_xyzz<G1>(partials1, (size_t)r * n1 + k));
+    st_xyzz<G1>(out1, k, acc);
+  } else if (k < n1 + n2) {
+    XYZZ<G2> acc = XYZZ<G2>::inf();
+    for (int r = 0; r < world; r++) acc.add(ld_xyzz<G2>(partials2, r));
+    st_xyzz<G2>(out2, 0, acc);
+  }
+}
+int groth16_sum_partials(pcdgpu_ctx* ctx, int pairing, const void* p1, const void* p2, int world, int n1, int n2,
+                         void* out1, void* out2) {
+  ctx->launches += 1;
+  if (pairing == PCDGPU_MNT4_298)
+    groth16_sum_partials_kernel<CurveMnt4G1, CurveMnt4G2><<<1, 32 * (n1 + n2), 0, ctx->cur()>>>(p1, p2, world, n1, n2, out1, out2);
+  else
+    groth16_sum_partials_kernel<CurveMnt6G1, CurveMnt6G2><<<1, 32 * (n1 + n2), 0, ctx->cur()>>>(p1, p2, world, n1, n2, out1, out2);
+  PCD_CUDA(ctx, cudaGetLastError());
+  return 0;
+}
+
 int groth16_straus(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, void* sums1) {
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
   ctx->launches += 1;

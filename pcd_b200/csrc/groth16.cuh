@@ -82,6 +82,8 @@ int qap_combine_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, void* d_a, const void
 // extras <- {r, 1, 1, s, 1, 1, -(r s) mod p} as plain integers (the scalars of the constant pairs)
 int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras);
 // the proof's tail, on the context's current lane (ctx->cur()): sums1 = {h_acc, l_acc - (r s) delta, g_a, g1_b, T}
+int groth16_sum_partials(pcdgpu_ctx* ctx, int pairing, const void* p1, const void* p2, int world, int n1, int n2,
+                         void* out1, void* out2);
 int groth16_straus(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, void* sums1);      // T = s g_a + r g1_b
 int point_to_affine(pcdgpu_ctx* ctx, int curve, const void* src_xyzz, size_t idx, void* dst_affine);
 int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_c);  // C = T + l' + h, affine

@@ -158,3 +158,22 @@ def test_witness_map_by_vector_multi_gpu():
                         os.path.join(ROOT, "tools", "check_wm_by_vector.py")], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.gpu
+def test_sharded_groth16_prove_multi_gpu():
+    """one Groth16 proof over the GPUs of the box (MSM point ranges per GPU, gathered partial sums) == the single-GPU
+    proof == the instance's discrete logarithms; with one GPU the same code runs as a single rank"""
+    import subprocess
+    import torch
+    ngpu = torch.cuda.device_count()
+    world = min(ngpu, 4)
+    env = dict(os.environ, LOG_N="14", LOG_N_HELP="12")
+    script = os.path.join(ROOT, "tools", "check_sharded_prove.py")
+    if world < 2:
+        cmd = [sys.executable, script]
+    else:
+        cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
+               "--master-addr", "127.0.0.1", "--master-port", "29534", script]
+    r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
