@@ -205,6 +205,12 @@ int pcdgpu_kzg_open(pcdgpu_ctx* ctx, const pcdgpu_bases* powers_of_g, const void
                     const pcdgpu_bases* powers_of_gamma_g, const void* rand_coeffs, size_t n_rand, const void* z,
                     void* out_w_affine, void* out_value, void* out_random_v);
 
+/* Launch heuristics for callers that run several MSMs side by side on contexts of their own (the multi-GPU prover):
+ * on != 0 selects, for bases uploaded and MSMs launched through this context afterwards, the window and occupancy
+ * rules the single-GPU prover uses for its five concurrent MSMs (one bit smaller window from 2^18 points up, two
+ * accumulate CTAs per SM) instead of the lone-MSM rules.  Results do not depend on it. */
+int pcdgpu_set_msm_side_by_side(pcdgpu_ctx* ctx, int on);
+
 /* The last step of a Groth16 proof computed by several GPUs (MSM point ranges split per GPU): every
  * rank computes xyzz partial sums of the five MSMs over its slice of each query (pcdgpu_msm_bases_dev; the rank that
  * holds the constant points delta, query[0], alpha / beta adds them to its slices with scalars r or s, 1, 1 and

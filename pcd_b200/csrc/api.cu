@@ -807,6 +807,13 @@ int pcdgpu_profile_timeline(pcdgpu_ctx* ctx, double* t0_ms, double* t1_ms, int* 
   return 0;
 }
 
+int pcdgpu_set_msm_side_by_side(pcdgpu_ctx* ctx, int on) {
+  if (!ctx) return PCDGPU_E_ARG;
+  ctx->in_proof = on != 0;
+  ctx->key_upload = on != 0;
+  return 0;
+}
+
 int pcdgpu_bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* out_ops_per_s, double* out_ms) {
   if (!ctx) return PCDGPU_E_ARG;
   CHECK_ARG(ctx, out_ops_per_s && out_ms && iters > 0, "bad argument");

@@ -38,7 +38,7 @@ EXPORTS = [
     "pcdgpu_sap_domain_size", "pcdgpu_sap_witness_map", "pcdgpu_gm17_pk_upload", "pcdgpu_gm17_pk_free",
     "pcdgpu_gm17_prove", "pcdgpu_gm17_prove_dev",
     "pcdgpu_poly_divide_linear", "pcdgpu_poly_mul", "pcdgpu_kzg_commit", "pcdgpu_kzg_open",
-    "pcdgpu_qap_vector_dev", "pcdgpu_qap_combine_dev", "pcdgpu_groth16_assemble_begin_dev", "pcdgpu_groth16_assemble_finish_dev",
+    "pcdgpu_qap_vector_dev", "pcdgpu_qap_combine_dev", "pcdgpu_set_msm_side_by_side", "pcdgpu_groth16_assemble_begin_dev", "pcdgpu_groth16_assemble_finish_dev",
 ]
 
 
@@ -116,6 +116,7 @@ def load():
     lib.pcdgpu_gm17_pk_free.restype = None
     lib.pcdgpu_gm17_prove.argtypes = [vp] * 8
     lib.pcdgpu_gm17_prove_dev.argtypes = [vp] * 8
+    lib.pcdgpu_set_msm_side_by_side.argtypes = [vp, ci]
     lib.pcdgpu_groth16_assemble_begin_dev.argtypes = [vp, ci, vp, vp, ci, vp, vp]
     lib.pcdgpu_groth16_assemble_finish_dev.argtypes = [vp, ci, ci, vp, vp]
     lib.pcdgpu_qap_vector_dev.argtypes = [vp, vp, ci, vp, vp]

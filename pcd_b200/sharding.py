@@ -136,6 +136,8 @@ class ShardedGroth16:
         self.n = ctx.lib.pcdgpu_r1cs_domain_size(h)
         # the four MSMs over the assignment run on contexts (streams + scratch) of their own, beside the witness map
         self.side = [L.Context(ctx.device) for _ in range(4)]
+        for c in [ctx] + self.side:  # five MSMs side by side: the prover's window / occupancy rules, not a lone MSM's
+            c._check(c.lib.pcdgpu_set_msm_side_by_side(c.h, 1))
         import torch
         self.comm_stream = torch.cuda.Stream(device=device)
         l1, l2 = L.AFFINE_LIMBS[self.g1], L.AFFINE_LIMBS[self.g2]
@@ -257,6 +259,7 @@ class ShardedGroth16:
         for c in self.side:
             c.close()
         self.side = []
+        self.ctx.lib.pcdgpu_set_msm_side_by_side(self.ctx.h, 0)
         if self.r1cs:
             self.ctx.lib.pcdgpu_r1cs_free(self.r1cs)
             self.r1cs = None
