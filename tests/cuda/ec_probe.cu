@@ -30,9 +30,10 @@ __global__ void ec_probe_kernel(int op, const u32* p, const u32* q, const u32* k
     case 8: { r = XYZZ<C>::inf(); for (int d = 0; d < klimbs; d++) r.madd(P); break; }
     case 9: { r = XYZZ<C>::inf(); for (int d = 0; d < klimbs; d++) { r.madd(P); AffinePoint<F> t = r.to_affine(); if (t.x.is_zero()) r.madd(P); } break; }
     case 10: { r = XYZZ<C>::from_affine(P).dbl(); r.add(XYZZ<C>::from_affine(Q)); break; }
-    case 11: { r = XYZZ<C>::from_affine(P).dbl_impl(); r.madd(Q); break; }
-    case 12: { r = XYZZ<C>::from_affine(P).dbl(); r.madd_impl(Q); break; }
-    case 13: { r = XYZZ<C>::from_affine(P).dbl_impl(); r.madd_impl(Q); break; }
+    // 11-13: the inline bodies, G1 only (for the G2 curves every inlined copy of the group law costs minutes of ptxas)
+    case 11: if constexpr (!C::OUTLINE) { r = XYZZ<C>::from_affine(P).dbl_impl(); r.madd(Q); } else r = XYZZ<C>::inf(); break;
+    case 12: if constexpr (!C::OUTLINE) { r = XYZZ<C>::from_affine(P).dbl(); r.madd_impl(Q); } else r = XYZZ<C>::inf(); break;
+    case 13: if constexpr (!C::OUTLINE) { r = XYZZ<C>::from_affine(P).dbl_impl(); r.madd_impl(Q); } else r = XYZZ<C>::inf(); break;
     case 14: { r = XYZZ<C>::from_affine(P).dbl(); AffinePoint<F> t = r.to_affine(); r = XYZZ<C>::from_affine(t); r.madd(Q); break; }
     default: r = XYZZ<C>::inf();
   }
@@ -40,22 +41,42 @@ __global__ void ec_probe_kernel(int op, const u32* p, const u32* q, const u32* k
   for (int i = 0; i < (int)(sizeof(a) / 4); i++) out[i] = ((u32*)&a)[i];
 }
 
-extern "C" int probe_ec_op(int curve, int op, const void* p, const void* q, const void* k, int klimbs, void* out) {
-  size_t pb = curve == 0 || curve == 2 ? 80 : (curve == 1 ? 160 : 240);
+// Compiled once per curve (-DPROBE_CURVE=0..3, in parallel: the G2 curves take minutes of ptxas each) plus once as the
+// dispatcher (-DPROBE_MAIN); __graft_entry__.build() links the five objects into libecprobe.so.
+template <class C>
+static int run_probe(size_t pb, int op, const void* p, const void* q, const void* k, int klimbs, void* out) {
   u32* d;
   if (cudaMalloc(&d, 3 * pb + 64) != cudaSuccess) return -1;
   u32 *dp = d, *dq = d + pb / 4, *dout = d + 2 * pb / 4, *dk = d + 3 * pb / 4;
   cudaMemcpy(dp, p, pb, cudaMemcpyHostToDevice);
   cudaMemcpy(dq, q, pb, cudaMemcpyHostToDevice);
   cudaMemcpy(dk, k, 40, cudaMemcpyHostToDevice);
-  switch (curve) {
-    case 0: ec_probe_kernel<CurveMnt4G1><<<1, 32>>>(op, dp, dq, dk, klimbs, dout); break;
-    case 1: ec_probe_kernel<CurveMnt4G2><<<1, 32>>>(op, dp, dq, dk, klimbs, dout); break;
-    case 2: ec_probe_kernel<CurveMnt6G1><<<1, 32>>>(op, dp, dq, dk, klimbs, dout); break;
-    default: ec_probe_kernel<CurveMnt6G2><<<1, 32>>>(op, dp, dq, dk, klimbs, dout); break;
-  }
+  ec_probe_kernel<C><<<1, 32>>>(op, dp, dq, dk, klimbs, dout);
   cudaError_t e = cudaDeviceSynchronize();
   cudaMemcpy(out, dout, pb, cudaMemcpyDeviceToHost);
   cudaFree(d);
   return e == cudaSuccess ? 0 : -(int)e;
 }
+
+#if defined(PROBE_MAIN)
+extern "C" int probe_ec_op_0(int, const void*, const void*, const void*, int, void*);
+extern "C" int probe_ec_op_1(int, const void*, const void*, const void*, int, void*);
+extern "C" int probe_ec_op_2(int, const void*, const void*, const void*, int, void*);
+extern "C" int probe_ec_op_3(int, const void*, const void*, const void*, int, void*);
+extern "C" int probe_ec_op(int curve, int op, const void* p, const void* q, const void* k, int klimbs, void* out) {
+  switch (curve) {
+    case 0: return probe_ec_op_0(op, p, q, k, klimbs, out);
+    case 1: return probe_ec_op_1(op, p, q, k, klimbs, out);
+    case 2: return probe_ec_op_2(op, p, q, k, klimbs, out);
+    default: return probe_ec_op_3(op, p, q, k, klimbs, out);
+  }
+}
+#elif PROBE_CURVE == 0
+extern "C" int probe_ec_op_0(int op, const void* p, const void* q, const void* k, int kl, void* out) { return run_probe<CurveMnt4G1>(80, op, p, q, k, kl, out); }
+#elif PROBE_CURVE == 1
+extern "C" int probe_ec_op_1(int op, const void* p, const void* q, const void* k, int kl, void* out) { return run_probe<CurveMnt4G2>(160, op, p, q, k, kl, out); }
+#elif PROBE_CURVE == 2
+extern "C" int probe_ec_op_2(int op, const void* p, const void* q, const void* k, int kl, void* out) { return run_probe<CurveMnt6G1>(80, op, p, q, k, kl, out); }
+#else
+extern "C" int probe_ec_op_3(int op, const void* p, const void* q, const void* k, int kl, void* out) { return run_probe<CurveMnt6G2>(240, op, p, q, k, kl, out); }
+#endif
