@@ -577,6 +577,22 @@ def kernel_figures(args, ctx, dev, stream, imad_peak, rank=0, world=1):
     out["g1_msm"] = {"points": n, "scalars": "uniform 298-bit", "mpts_per_s": n / ms_pre / 1e3, "ms": ms_pre,
                      "mode": "resident bases with precomputed window tables",
                      "variable_base_mpts_per_s": n / ms_plain / 1e3, "variable_base_ms": ms_plain}
+    if world == 1 and not args.no_sweep:
+        # the other sizes BASELINE.json names for the MSM (2^16 .. 2^22), resident tables, uniform scalars
+        sweep = {}
+        for lg in (16, 18, 22):
+            if lg == args.msm_log_n:
+                continue
+            m = 1 << lg
+            p_ = synthetic.random_points_dev(ctx, pcd_b200.MNT4_G1, m, seed=30 + lg)
+            s_ = torch.from_numpy(synthetic.random_limbs(m, 0, 40 + lg).view(np.int64)).to(dev)
+            b_ = pcd_b200.Bases(ctx, 0, p_.cpu().numpy().view(np.uint64), precompute=True)
+            del p_
+            t_ = timed(lambda: b_.msm_dev(s_.data_ptr(), m, res.data_ptr()), 5)
+            sweep["2^%d" % lg] = {"ms": t_, "mpts_per_s": m / t_ / 1e3}
+            b_.close()
+            del s_
+        out["g1_msm_sweep"] = sweep
     log_n = args.ntt_log_n
     x = torch.from_numpy(synthetic.random_limbs(1 << min(log_n, 20), 0, 5).view(np.int64)).to(dev)
     if log_n > 20:
@@ -586,6 +602,17 @@ def kernel_figures(args, ctx, dev, stream, imad_peak, rank=0, world=1):
     butterflies = (1 << (log_n - 1)) * log_n
     timad = butterflies * MODMUL_IMADS / (ms_ntt * 1e-3) / 1e12
     out["ntt"] = {"log_n": log_n, "field": "r4 (MNT4-298 Fr)", "flavour": "coset_fft", "ms": ms_ntt, "GBps": gbs}
+    if world == 1 and not args.no_sweep:
+        nsw = {}
+        for lg in (16, 20):
+            if lg >= log_n:
+                continue
+            t_ = timed(lambda: ctx.ntt_dev(0, x.data_ptr(), lg, False, True), 10)
+            nsw["2^%d" % lg] = {"ms": t_, "GBps": 2 * 40 * (1 << lg) / (t_ * 1e-3) / 1e9}
+        y = x[:1 << 17].contiguous()
+        t_ = timed(lambda: ctx.ntt_dev(1, y.data_ptr(), 17, False, True), 10)  # the helper field's largest radix-2 domain
+        nsw["q4_2^17"] = {"ms": t_, "GBps": 2 * 40 * (1 << 17) / (t_ * 1e-3) / 1e9, "note": "L2-resident, not an HBM figure"}
+        out["ntt_sweep"] = nsw
     out["roofline_ntt"] = {"bound": "hbm", "achieved": gbs, "peak": hbm_peak, "unit": "GB/s", "frac": gbs / hbm_peak,
                            "traffic": None, "imad_frac": timad / (imad_peak / 1e12),
                            "note": "algorithmic bytes 2*N*40; a 298-bit NTT is bound by the integer pipe: imad_frac = "
@@ -628,6 +655,7 @@ def main():
                     help="independent proofs issued concurrently per GPU (each on its own context)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-pcd-step", action="store_true")
+    ap.add_argument("--no-sweep", action="store_true", help="skip the MSM / NTT size sweeps")
     ap.add_argument("--pcd-main-log-n", type=int, default=18)
     ap.add_argument("--pcd-help-log-n", type=int, default=16)
     ap.add_argument("--no-concurrency", action="store_true", help="run the five MSMs of a proof on one stream")
