@@ -350,3 +350,27 @@ def test_gm17_vs_oracle_and_trapdoor(ctx, pairing, m, ni):
     finally:
         ctx.set_concurrency(True)
     idx2.close()
+
+
+def test_gm17_mixed_radix_sap_domain(ctx):
+    """helper side (MNT6-298, Fr = q4): 65540 constraints give a SAP of 131083 rows, beyond q4's 2-adicity -- the domain is
+    49 * 2^12 = 200704; the proof must still satisfy GM17's verification equations in the exponent"""
+    import pcd_b200
+    from pcd_b200 import synthetic
+    m = (1 << 16) + 4
+    inst = synthetic.make_gm17_instance(ctx, 1, m, seed=8)
+    assert inst["domain_size"] == 200704
+    g = pcd_b200.GM17(ctx, 1)
+    idx = g.index(pcd_b200.GM17ProvingKey(pairing=1, **inst["pk"]),
+                  pcd_b200.ConstraintMatrices(1, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"]),
+                  precompute=True)
+    p = inst["p"]
+    d1, d2, r = pow(3, 71, p), pow(5, 61, p), pow(7, 51, p)
+    proof = g.create_proof(idx, inst["z"], codec.int_to_limbs(d1), codec.int_to_limbs(d2), codec.int_to_limbs(r))
+    assert np.array_equal(proof.affine_limbs(), synthetic.expected_gm17_proof(ctx, inst, d1, d2, r))
+    # the SAP witness map alone against the C++ oracle
+    full, h = g.witness_map(idx, inst["z"], codec.int_to_limbs(d1), codec.int_to_limbs(d2))
+    rfull, rh = co.sap_witness_map(1, inst["A"], inst["B"], inst["C"], m, inst["num_inputs"], inst["num_witness"], inst["z"],
+                                   codec.int_to_limbs(d1), codec.int_to_limbs(d2), 16)
+    assert np.array_equal(full, rfull) and np.array_equal(h, rh)
+    idx.close()
