@@ -227,7 +227,7 @@ int pcdgpu_msm_dev(pcdgpu_ctx* ctx, int curve, const void* d_bases, const void* 
 
 static int finish_to_host(pcdgpu_ctx* ctx, const MsmOps* ops, void* d_xyzz, void* out_affine) {
   void* d_aff = (char*)d_xyzz + ops->xyzz_bytes;
-  PCD_TRY(ops->to_affine(ctx, d_xyzz, 1, d_aff));
+  PCD_TRY(ops->to_affine_at(ctx, d_xyzz, 0, d_aff));
   PCD_CUDA(ctx, cudaMemcpyAsync(out_affine, d_aff, ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -367,7 +367,7 @@ int pcdgpu_xyzz_sum(pcdgpu_ctx* ctx, int curve, const void* xyzz, size_t n, void
   PCD_TRY(ctx->scratch(SLOT_IO, (n + 1) * ops->xyzz_bytes, &d));
   void* d_aff = (char*)d + n * ops->xyzz_bytes;
   PCD_CUDA(ctx, cudaMemcpyAsync(d, xyzz, n * ops->xyzz_bytes, cudaMemcpyHostToDevice, ctx->stream));
-  PCD_TRY(ops->xyzz_sum(ctx, d, n, d_aff));
+  PCD_TRY(ops->sum_points(ctx, d, 0, 1, (int)n, nullptr, 0, d_aff));
   PCD_CUDA(ctx, cudaMemcpyAsync(out_affine, d_aff, ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -605,7 +605,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
   const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
   size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
-  // misc layout: rs (80 B) | extras: 7 scalars | sums1: h, l', g_a, g1_b, T (G1 xyzz) | sum2: g2_b | proof
+  // misc layout: rs (80 B) | extras: 7 scalars | sums1: h, l', T, g_a, g1_b (G1 xyzz) | sum2: g2_b | proof
   void* misc;
   PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
   char* mb = (char*)misc;
@@ -636,8 +636,8 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   }
   struct Job { const pcdgpu_bases* b; const char* sc; size_t n; const char* ex; size_t nex; void* out; };
   Job jobs[4] = {{pk->b_g2_query, z + 40, nv - 1, extras + 3 * 40, 3, sum2},
-                 {pk->a_query, z + 40, nv - 1, extras, 3, (char*)sums1 + 2 * x1},
-                 {pk->b_g1_query, z + 40, nv - 1, extras + 3 * 40, 3, (char*)sums1 + 3 * x1},
+                 {pk->a_query, z + 40, nv - 1, extras, 3, (char*)sums1 + 3 * x1},
+                 {pk->b_g1_query, z + 40, nv - 1, extras + 3 * 40, 3, (char*)sums1 + 4 * x1},
                  {pk->l_query, z + 40 * ni, nv - ni, extras + 6 * 40, 1, (char*)sums1 + 1 * x1}};
   int rc = 0;
   for (int j = 0; j < 4 && rc == 0; j++) {
@@ -645,7 +645,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
     rc = bases_msm(ctx, jobs[j].b, 0, jobs[j].sc, 1, jobs[j].n, jobs[j].ex, jobs[j].nex, jobs[j].out);
     if (rc == 0 && j == 0) rc = point_to_affine(ctx, g2, sum2, 0, d_B);
     if (rc == 0 && j == 1) {
-      rc = point_to_affine(ctx, g1, sums1, 2, d_A);
+      rc = point_to_affine(ctx, g1, sums1, 3, d_A);
       // lane 3's Straus needs g_a: an event of its own, recorded before lane 2's tail would also do, but the
       // normalisation is short
     }
@@ -676,7 +676,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   return 0;
 }
 
-// layout of the assembly state in SLOT_MISC (shared by the two calls below): rs | sums1 (h, l', g_a, g1_b, T) | sum2 | proof
+// layout of the assembly state in SLOT_MISC (shared by the two calls below): rs | sums1 (h, l', T, g_a, g1_b) | sum2 | proof
 int pcdgpu_groth16_assemble_begin_dev(pcdgpu_ctx* ctx, int pairing, const void* r, const void* s, int world,
                                       const void* d_partials_ab, const void* d_partials_g2) {
   if (!ctx) return PCDGPU_E_ARG;
@@ -696,9 +696,9 @@ int pcdgpu_groth16_assemble_begin_dev(pcdgpu_ctx* ctx, int pairing, const void* 
   memcpy(ctx->pinned, r, 40);
   memcpy((char*)ctx->pinned + 40, s, 40);
   PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
-  // g_a, g1_b -> sums1[2], sums1[3]; g2_b -> sum2
-  PCD_TRY(groth16_sum_partials(ctx, pairing, d_partials_ab, d_partials_g2, world, 2, 2, (char*)sums1 + 2 * x1, sum2));
-  PCD_TRY(point_to_affine(ctx, g1, sums1, 2, d_proof));
+  // g_a, g1_b -> sums1[3], sums1[4]; g2_b -> sum2
+  PCD_TRY(groth16_sum_partials(ctx, pairing, d_partials_ab, d_partials_g2, world, 2, 1, (char*)sums1 + 3 * x1, sum2));
+  PCD_TRY(point_to_affine(ctx, g1, sums1, 3, d_proof));
   PCD_TRY(point_to_affine(ctx, g2, sum2, 0, d_proof + o1->affine_bytes));
   return groth16_straus(ctx, pairing, d_rs, sums1);
 }

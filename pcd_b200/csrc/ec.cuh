@@ -9,7 +9,6 @@
 #pragma once
 #include <type_traits>
 
-#include "fp30.cuh"
 #include "fpx.cuh"
 
 template <class F>
@@ -20,63 +19,23 @@ struct AffinePoint {
   PCD_HD AffinePoint neg() const { AffinePoint p; p.x = x; p.y = y.neg(); return p; }
 };
 
-// Radix-2^30 twins of the two G1 curves: same group law over Fp30 (carry-free products, values in [0, 2p),
-// Montgomery radix 2^300).  With -DPCD_FAST30 the bucket-accumulation kernels compute in them (points enter
-// through fast_affine() / tables stored in that form, buckets leave through slow_xyzz()).  OFF by default:
-// measured on B200 the radix-2^30 product is no faster than the carry-chain one (42.4 vs 44.1 G products/s)
-// because IMAD.WIDE issues on the fmaheavy pipe at 32 lanes/clk/SM whatever its carry predicates, and both
-// products keep that pipe 93-97 % busy (profiles/r01_ncu_modmul.csv); the extra shifts/masks made
-// msm_accumulate 16 % slower.  Kept (and tested in tests/hostemu) as the starting point for a product that
-// leaves the fmaheavy pipe (e.g. FP64 DFMA limbs), which is the only way past that roof.
-struct CurveMnt4G1Fast {
-  typedef Fp30Q4 F; static constexpr bool OUTLINE = false;
-  PCD_HD static F mul_a(const F& v) { return v.dbl(); }
-};
-struct CurveMnt6G1Fast {
-  typedef Fp30R4 F; static constexpr bool OUTLINE = false;
-  PCD_HD static F mul_a(const F& v) { return v.template mul_small<11>(); }
-};
-
 // Curve tags: coordinate field + multiplication by the curve coefficient a.
 struct CurveMnt4G1 {  // y^2 = x^3 + 2x + b over F_q4, order r4
-#ifdef PCD_FAST30
-  typedef CurveMnt4G1Fast Fast;
-#else
-  typedef CurveMnt4G1 Fast;
-#endif
   typedef FpQ4 F; typedef ParamsR4 ScalarParams; typedef GenMnt4G1 Gen; static constexpr int ID = 0;
   static constexpr bool OUTLINE = false;
   PCD_HD static F mul_a(const F& v) { return v.dbl(); }
 };
-// Measured (B200, 2^20 proof): with the base products inlined as well the G2 walk needs 255 registers + spills and
-// takes 8.3 ms against 7.3 ms with out-of-line products (and msm_c1.cu compiles in 6 min instead of 25 s) -- so
-// the twin is OFF unless -DPCD_G2_INLINE_PRODUCTS; only the group law (madd_impl) is inlined in the walk.
-struct CurveMnt4G2Inl {  // CurveMnt4G2 with inlined base products and group law: the accumulate kernels' twin
-  typedef Fq2I F; static constexpr bool OUTLINE = false; static constexpr bool BITCAST = true;
-  PCD_HD static F mul_a(const F& v) { return v.template mul_small<34>(); }
-};
 struct CurveMnt4G2 {  // twist over Fq2: a' = (34, 0)
-#ifdef PCD_G2_INLINE_PRODUCTS
-  typedef CurveMnt4G2Inl Fast;
-#else
-  typedef CurveMnt4G2 Fast;
-#endif
   typedef Fq2 F; typedef ParamsR4 ScalarParams; typedef GenMnt4G2 Gen; static constexpr int ID = 1;
   static constexpr bool OUTLINE = true;  // group operations are real function calls (code size, compile time)
   PCD_HD static F mul_a(const F& v) { return v.template mul_small<34>(); }
 };
 struct CurveMnt6G1 {  // y^2 = x^3 + 11x + b over F_r4, order q4
-#ifdef PCD_FAST30
-  typedef CurveMnt6G1Fast Fast;
-#else
-  typedef CurveMnt6G1 Fast;
-#endif
   typedef FpR4 F; typedef ParamsQ4 ScalarParams; typedef GenMnt6G1 Gen; static constexpr int ID = 2;
   static constexpr bool OUTLINE = false;
   PCD_HD static F mul_a(const F& v) { return v.template mul_small<11>(); }
 };
 struct CurveMnt6G2 {  // twist over Fq3: a' = (0, 0, 11) = 11 u^2;  u^3 = 5
-  typedef CurveMnt6G2 Fast;
   typedef Fq3 F; typedef ParamsQ4 ScalarParams; typedef GenMnt6G2 Gen; static constexpr int ID = 3;
   static constexpr bool OUTLINE = true;
   PCD_HD static F mul_a(const F& v) {
@@ -87,47 +46,6 @@ struct CurveMnt6G2 {  // twist over Fq3: a' = (0, 0, 11) = 11 u^2;  u^3 = 5
     return r;
   }
 };
-
-// ABI field element (ten 32-bit words of x * 2^320 mod p, canonical) <-> radix-2^30 element (x * 2^300, < 2p):
-// bit repacking and one product by a constant each way.
-template <class P30, class P>
-PCD_HD Fp30<P30> to_fast(const Fp<P>& a) {
-  static_assert(P30::ID == P::ID, "same field");
-  return Fp30<P30>::from_words(a.l) * Fp30<P30>::konst(P30::abi_to_int);
-}
-template <class P, class P30>
-PCD_HD Fp<P> from_fast(const Fp30<P30>& a) {
-  static_assert(P30::ID == P::ID, "same field");
-  Fp<P> r;
-  (a * Fp30<P30>::konst(P30::int_to_abi)).canonical().to_words(r.l);
-  return r;
-}
-
-template <class C>
-struct XYZZ;
-// the same for points; identity for the curves without a radix-2^30 twin (C::Fast == C)
-template <class C>
-PCD_HD AffinePoint<typename C::Fast::F> fast_affine(const AffinePoint<typename C::F>& p) {
-  if constexpr (std::is_same<C, typename C::Fast>::value) {
-    return p;
-  } else if constexpr (sizeof(AffinePoint<typename C::Fast::F>) == sizeof(AffinePoint<typename C::F>) &&
-                       C::Fast::F::WORDS > FP_LIMBS) {  // layout-identical twin of an extension field: same words
-    AffinePoint<typename C::Fast::F> q;
-    const u32* s = reinterpret_cast<const u32*>(&p);
-    u32* d = reinterpret_cast<u32*>(&q);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(q) / 4); i++) d[i] = s[i];
-    return q;
-  } else {
-    typedef typename C::Fast::F::Params P30;
-    AffinePoint<typename C::Fast::F> q;
-    q.x = to_fast<P30>(p.x);
-    q.y = to_fast<P30>(p.y);
-    return q;
-  }
-}
-template <class C>
-PCD_HD XYZZ<C> slow_xyzz(const XYZZ<typename C::Fast>& p);
 
 template <class C>
 struct XYZZ {
@@ -271,25 +189,3 @@ struct XYZZ {
     return acc;
   }
 };
-
-template <class C>
-PCD_HD XYZZ<C> slow_xyzz(const XYZZ<typename C::Fast>& p) {
-  if constexpr (std::is_same<C, typename C::Fast>::value) {
-    return p;
-  } else if constexpr (sizeof(XYZZ<typename C::Fast>) == sizeof(XYZZ<C>) && C::Fast::F::WORDS > FP_LIMBS) {
-    XYZZ<C> q;
-    const u32* s = reinterpret_cast<const u32*>(&p);
-    u32* d = reinterpret_cast<u32*>(&q);
-#pragma unroll
-    for (int i = 0; i < (int)(sizeof(q) / 4); i++) d[i] = s[i];
-    return q;
-  } else {
-    typedef typename C::F::Params P;
-    XYZZ<C> q;
-    q.x = from_fast<P>(p.x);
-    q.y = from_fast<P>(p.y);
-    q.zz = from_fast<P>(p.zz);
-    q.zzz = from_fast<P>(p.zzz);
-    return q;
-  }
-}

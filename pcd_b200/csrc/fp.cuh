@@ -156,11 +156,7 @@ struct Fp {
   }
 
   PCD_HD friend Fp operator*(const Fp& a, const Fp& b) {
-#ifdef PCD_MUL_SC
-    return mul_sc(a, b);
-#else
     return mul_cc(a, b);
-#endif
   }
   // carry-chain product (IMAD.WIDE.U32.X rows)
   PCD_HD static Fp mul_cc(const Fp& a, const Fp& b) {
@@ -176,74 +172,6 @@ struct Fp {
 #pragma unroll
     for (int i = 1; i < FP_LIMBS - 1; i++) r.l[i] = prims::addc_cc(even[i], odd[i + 1]);
     r.l[FP_LIMBS - 1] = prims::addc(even[FP_LIMBS - 1], 0);
-    reduce_once(r.l);
-    return r;
-  }
-  // Alternative product with SEPARATED carries (mul_sc): every 64-bit multiply-add is a plain
-  // IMAD.WIDE.U32 with a carry-OUT only; the carry is counted into a side word by one IADD3.X on the alu
-  // pipe (prims::mac_carry), instead of the long mad.lo.cc/madc.hi.cc chains above whose carry-IN form
-  // IMAD.WIDE.U32.X issues at half rate.  T = X + Y*2^32 + sum_w C[w]*2^(32w): X holds the 64-bit pairs
-  // at word positions 0,2,4,6,8, Y those at 1,3,5,7,9 (register-pair aligned, no moves), C[w] the pending
-  // carries of word w (2 <= w <= 10).  Per row: 20 multiply-adds (18 carry counts: the pair at words 9,10
-  // cannot overflow because T < 2^352), then T >>= 32 by renaming: Y becomes X, X's upper pairs become Y,
-  // the top pair starts from C[10], and word 1 of X plus C[2] is added into the new bottom pair so that the
-  // next quotient digit sees an exact word 0.
-  PCD_HD static Fp mul_sc(const Fp& a, const Fp& b) {
-    u32 X[FP_LIMBS], Y[FP_LIMBS], C[FP_LIMBS + 1];
-#pragma unroll
-    for (int k = 0; k <= FP_LIMBS; k++) C[k] = 0;
-#pragma unroll
-    for (int i = 0; i < FP_LIMBS; i++) {
-      const u32 bi = b.l[i];
-      if (i == 0) {
-#pragma unroll
-        for (int k = 0; k < FP_LIMBS; k += 2) {
-          prims::mul_wide(X[k], X[k + 1], a.l[k], bi);
-          prims::mul_wide(Y[k], Y[k + 1], a.l[k + 1], bi);
-        }
-      } else {
-#pragma unroll
-        for (int k = 0; k < FP_LIMBS; k += 2) prims::mac_carry(X[k], X[k + 1], C[k + 2], a.l[k], bi);
-#pragma unroll
-        for (int k = 0; k < FP_LIMBS - 2; k += 2) prims::mac_carry(Y[k], Y[k + 1], C[k + 3], a.l[k + 1], bi);
-        prims::mac(Y[FP_LIMBS - 2], Y[FP_LIMBS - 1], a.l[FP_LIMBS - 1], bi);
-      }
-      const u32 m = prims::mul_lo(X[0], P::INV);
-#pragma unroll
-      for (int k = 0; k < FP_LIMBS; k += 2) prims::mac_carry(X[k], X[k + 1], C[k + 2], P::mod(k), m);
-#pragma unroll
-      for (int k = 0; k < FP_LIMBS - 2; k += 2) prims::mac_carry(Y[k], Y[k + 1], C[k + 3], P::mod(k + 1), m);
-      prims::mac(Y[FP_LIMBS - 2], Y[FP_LIMBS - 1], P::mod(FP_LIMBS - 1), m);
-      // X[0] == 0 now.  (Y[1]:Y[0]) += (C[2]:X[1]), carry to word 3; then shift one word down.
-      prims::add64_carry(Y[0], Y[1], C[3], X[1], C[2]);
-      u32 nX[FP_LIMBS], nY[FP_LIMBS];
-#pragma unroll
-      for (int k = 0; k < FP_LIMBS; k++) nX[k] = Y[k];
-#pragma unroll
-      for (int k = 0; k < FP_LIMBS - 2; k++) nY[k] = X[k + 2];
-      nY[FP_LIMBS - 2] = C[FP_LIMBS];
-      nY[FP_LIMBS - 1] = 0;
-#pragma unroll
-      for (int k = 0; k < FP_LIMBS; k++) {
-        X[k] = nX[k];
-        Y[k] = nY[k];
-      }
-#pragma unroll
-      for (int k = 2; k < FP_LIMBS - 1; k++) C[k] = C[k + 1];
-      C[FP_LIMBS - 1] = 0;
-      C[FP_LIMBS] = 0;
-    }
-    // T = X + (Y << 32) + sum C[w] << 32w, w = 2..8; T < 2p < 2^299 so nothing leaves word 9
-    Fp r;
-    r.l[0] = X[0];
-    r.l[1] = prims::add_cc(X[1], Y[0]);
-#pragma unroll
-    for (int k = 2; k < FP_LIMBS - 1; k++) r.l[k] = prims::addc_cc(X[k], Y[k - 1]);
-    r.l[FP_LIMBS - 1] = prims::addc(X[FP_LIMBS - 1], Y[FP_LIMBS - 2]);
-    r.l[2] = prims::add_cc(r.l[2], C[2]);
-#pragma unroll
-    for (int k = 3; k < FP_LIMBS - 1; k++) r.l[k] = prims::addc_cc(r.l[k], C[k]);
-    r.l[FP_LIMBS - 1] = prims::addc(r.l[FP_LIMBS - 1], 0);
     reduce_once(r.l);
     return r;
   }
@@ -281,8 +209,9 @@ struct Fp {
     }
     return out;
   }
-  // a^-1 = a^(p-2); zero maps to zero
-  PCD_HD Fp inverse() const {
+  // a^-1 = a^(p-2) (Fermat): ~450 dependent products.  Kept as the independent cross-check of inverse() in
+  // tests/hostemu; the product path uses the binary Euclid below.
+  PCD_HD Fp inverse_fermat() const {
     Fp r = one();
     bool started = false;
     for (int i = FP_LIMBS - 1; i >= 0; i--) {
@@ -299,6 +228,76 @@ struct Fp {
       }
     }
     return r;
+  }
+  // ---- inversion by the binary extended Euclidean algorithm -------------------------------------------------
+  // Invariants: x1 * A = u, x2 * A = v (mod p) with A the integer held in the limbs (the Montgomery representative
+  // a R); u and v lose a bit per step (< 2 * 298 halvings in all), every step is shifts and additions on ten limbs --
+  // about a tenth of the ~450 dependent Montgomery products of Fermat's a^(p-2), which is what the single-thread
+  // normalisations at the end of every MSM and proof used to wait for (0.3 - 0.4 ms each on B200).
+  // The result (a R)^-1 is brought back to Montgomery form a^-1 R with two products by R^2.  Zero maps to zero.
+  PCD_HD static void shr1(u32* a) {
+#pragma unroll
+    for (int i = 0; i < FP_LIMBS - 1; i++) a[i] = (a[i] >> 1) | (a[i + 1] << 31);
+    a[FP_LIMBS - 1] >>= 1;
+  }
+  // x <- x / 2 mod p (x < p; p odd, x + p < 2^320)
+  PCD_HD static void halve_mod(u32* x) {
+    if (x[0] & 1) {
+      x[0] = prims::add_cc(x[0], P::mod(0));
+#pragma unroll
+      for (int i = 1; i < FP_LIMBS - 1; i++) x[i] = prims::addc_cc(x[i], P::mod(i));
+      x[FP_LIMBS - 1] = prims::addc(x[FP_LIMBS - 1], P::mod(FP_LIMBS - 1));
+    }
+    shr1(x);
+  }
+  // a >= b as integers
+  PCD_HD static bool geq(const u32* a, const u32* b) {
+    prims::sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < FP_LIMBS; i++) prims::subc_cc(a[i], b[i]);
+    return prims::subc(0, 0) == 0;  // no borrow
+  }
+  PCD_HD static void sub_raw(u32* a, const u32* b) {  // a -= b, a >= b
+    a[0] = prims::sub_cc(a[0], b[0]);
+#pragma unroll
+    for (int i = 1; i < FP_LIMBS - 1; i++) a[i] = prims::subc_cc(a[i], b[i]);
+    a[FP_LIMBS - 1] = prims::subc(a[FP_LIMBS - 1], b[FP_LIMBS - 1]);
+  }
+  PCD_HD static bool is_one_raw(const u32* a) {
+    u32 t = a[0] ^ 1u;
+#pragma unroll
+    for (int i = 1; i < FP_LIMBS; i++) t |= a[i];
+    return t == 0;
+  }
+  PCD_HD Fp inverse() const {
+    if (is_zero()) return *this;
+    u32 u[FP_LIMBS], v[FP_LIMBS];
+    Fp x1 = zero(), x2 = zero();
+    x1.l[0] = 1;
+#pragma unroll
+    for (int i = 0; i < FP_LIMBS; i++) {
+      u[i] = l[i];
+      v[i] = P::mod(i);
+    }
+    while (!is_one_raw(u) && !is_one_raw(v)) {
+      while (!(u[0] & 1)) {
+        shr1(u);
+        halve_mod(x1.l);
+      }
+      while (!(v[0] & 1)) {
+        shr1(v);
+        halve_mod(x2.l);
+      }
+      if (geq(u, v)) {
+        sub_raw(u, v);
+        x1 = x1 - x2;
+      } else {
+        sub_raw(v, u);
+        x2 = x2 - x1;
+      }
+    }
+    Fp r = is_one_raw(u) ? x1 : x2;  // (a R)^-1 as a plain integer
+    return (r * r2()) * r2();         // -> a^-1 (plain) -> a^-1 R
   }
   // generic power by a 64-bit exponent
   PCD_HD Fp pow64(u64 e) const {

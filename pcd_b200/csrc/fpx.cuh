@@ -5,17 +5,12 @@
 #pragma once
 #include "fp.cuh"
 
-// INL: base-field products inlined (operator*) instead of the out-of-line B::mul_ni.  The default keeps one copy of
-// the 260-instruction product per kernel; the inline twin (Fq2I) is used in the bucket-accumulation walk only, where
-// the call overhead and the operands' round trip through local memory cost ~15 % of the pipe.
-template <class B, u32 NR, bool INL = false>
+template <class B, u32 NR>
 struct Fp2T {
   B c0, c1;
   typedef B Base;
-  PCD_HD static B mulb(const B& a, const B& b) {
-    if constexpr (INL) return a * b;
-    else return B::mul_ni(a, b);
-  }
+  // base products are out-of-line calls: one copy of the 260-instruction product per kernel
+  PCD_HD static B mulb(const B& a, const B& b) { return B::mul_ni(a, b); }
   static constexpr int WORDS = 2 * B::WORDS;
   PCD_HD static Fp2T zero() { Fp2T r; r.c0 = B::zero(); r.c1 = B::zero(); return r; }
   PCD_HD static Fp2T one() { Fp2T r; r.c0 = B::one(); r.c1 = B::zero(); return r; }
@@ -115,5 +110,4 @@ struct Fp3T {
 };
 
 typedef Fp2T<FpQ4, 17> Fq2;  // MNT4-298 twist field
-typedef Fp2T<FpQ4, 17, true> Fq2I;  // same element, base products inlined (layout identical)
 typedef Fp3T<FpR4, 5> Fq3;   // MNT6-298 twist field

@@ -139,20 +139,6 @@ __global__ void gm17_prepare_kernel(const u32* __restrict__ ddr, u32* __restrict
 
 // The proof's tail, split like Groth16's (groth16.cu): [r] C2' right after the c_query_2 MSM on its lane, A and B
 // normalised on their lanes, and after the join only C = C1' + G' + [r] C2'.  sums1 = {G', C1', C2', A} (G1 xyzz).
-template <class G1>
-__global__ void gm17_scale_kernel(const u32* __restrict__ ddr, void* __restrict__ sums1) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  st_xyzz<G1>(sums1, 2, XYZZ<G1>::mul(ld_xyzz<G1>(sums1, 2), ddr + 20, 10));
-}
-template <class G1>
-__global__ void gm17_finish_kernel(const void* __restrict__ sums1, void* __restrict__ out_c) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<G1> acc = ld_xyzz<G1>(sums1, 2);
-  acc.add(ld_xyzz<G1>(sums1, 1));
-  acc.add(ld_xyzz<G1>(sums1, 0));
-  st_aff<G1>(out_c, 0, acc.to_affine());
-}
-
 static int sap_domain(int pairing, size_t m, size_t ni, size_t* n, int* da, int* db) {
   int field = pairing == PCDGPU_MNT4_298 ? PCDGPU_FIELD_R4 : PCDGPU_FIELD_Q4;
   return ntt_domain_shape(field, 2 * m + 2 * (ni - 1) + 1, n, da, db);
@@ -378,10 +364,7 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
       if (rc == 0 && j == 1) rc = point_to_affine(ctx, g1, sums1, 3, d_A);
       if (rc == 0 && j == 2) {  // [r] C2' on the lane that produced C2'
         int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
-        ctx->launches += 1;
-        if (pk->pairing == PCDGPU_MNT4_298) gm17_scale_kernel<CurveMnt4G1><<<1, 32, 0, ctx->cur()>>>(d_ddr, sums1);
-        else gm17_scale_kernel<CurveMnt6G1><<<1, 32, 0, ctx->cur()>>>(d_ddr, sums1);
-        if (cudaGetLastError() != cudaSuccess) rc = PCDGPU_E_CUDA;
+        rc = o1->multi_mul(ctx, sums1, 2, 2, d_ddr + 20, 1, sums1, 2);  // lane-cooperative double-and-add (wec.cuh)
         ctx->prof_end(ps);
       }
       if (fork && rc == 0 && cudaEventRecord(ctx->ev_join[j + 1], ctx->lane_stream[j + 1]) != cudaSuccess) rc = PCDGPU_E_CUDA;
@@ -404,10 +387,7 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
   if (fork)
     for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
-  ctx->launches += 1;
-  if (pk->pairing == PCDGPU_MNT4_298) gm17_finish_kernel<CurveMnt4G1><<<1, 32, 0, ctx->stream>>>(sums1, d_C);
-  else gm17_finish_kernel<CurveMnt6G1><<<1, 32, 0, ctx->stream>>>(sums1, d_C);
-  PCD_CUDA(ctx, cudaGetLastError());
+  PCD_TRY(o1->sum_points(ctx, sums1, 0, 1, 3, nullptr, 0, d_C));  // C = G' + C1' + [r] C2'
   ctx->prof_end(ps);
   PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));

@@ -6,7 +6,6 @@
 // affine proof points are bit-identical to any correct CPU evaluation of the same formulas.
 #include "groth16.cuh"
 
-#include "fp30.cuh"
 #include "msm_ops.cuh"
 #include "ntt.cuh"
 
@@ -173,103 +172,36 @@ int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras
 //   groth16_straus   T = s g_a + r g1_b, as soon as the a and b_g1 MSMs are done (overlaps the witness map / h MSM)
 //   point_to_affine  A = g_a and B = g2_b, each right after its MSM, on that MSM's lane
 //   groth16_finish   C = T + l' + h
-// (one kernel doing all of it after the join cost 4.9 ms of single-thread latency per proof).
-// sums1 = {h_acc, l', g_a, g1_b, T} (G1 xyzz).
-template <class G1>
-__global__ void groth16_straus_kernel(const u32* __restrict__ rs, void* __restrict__ sums1) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<G1> ga = ld_xyzz<G1>(sums1, 2);
-  XYZZ<G1> gb = ld_xyzz<G1>(sums1, 3);
-  // s g_a + r g1_b jointly (Straus): one doubling chain, table {ga, gb, ga + gb}
-  XYZZ<G1> gab = ga;
-  gab.add(gb);
-  XYZZ<G1> acc = XYZZ<G1>::inf();
-  bool started = false;
-  for (int i = 9; i >= 0; i--) {
-    u32 rw = rs[i], sw = rs[10 + i];
-    for (int b = 31; b >= 0; b--) {
-      if (started) acc = acc.dbl();
-      u32 sel = ((sw >> b) & 1) | (((rw >> b) & 1) << 1);
-      if (sel) {
-        acc.add(sel == 1 ? ga : (sel == 2 ? gb : gab));
-        started = true;
-      }
-    }
-  }
-  st_xyzz<G1>(sums1, 4, acc);
-}
-template <class C>
-__global__ void point_to_affine_kernel(const void* __restrict__ src, size_t idx, void* __restrict__ dst) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  st_aff<C>(dst, 0, ld_xyzz<C>(src, idx).to_affine());
-}
-template <class G1>
-__global__ void groth16_finish_kernel(const void* __restrict__ sums1, void* __restrict__ out_c) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<G1> acc = ld_xyzz<G1>(sums1, 4);
-  acc.add(ld_xyzz<G1>(sums1, 1));
-  acc.add(ld_xyzz<G1>(sums1, 0));
-  st_aff<G1>(out_c, 0, acc.to_affine());
-}
-
+// All of it runs on the lane-cooperative group law (wec.cuh, through the per-curve MsmOps entries): round 1's
+// single-thread versions cost 3.5 - 4 ms (Straus), 0.33 - 0.41 ms (each normalisation, Fermat inversion) per proof.
+// sums1 = {h_acc, l', T, g_a, g1_b} (G1 xyzz).
 // multi-GPU prover: out1[k] = sum over ranks of partials1[rank * n1 + k], k < n1 (G1); out2 = sum of partials2 (G2, n2 = 0 / 1)
-template <class G1, class G2>
-__global__ void groth16_sum_partials_kernel(const void* __restrict__ partials1, const void* __restrict__ partials2,
-                                            int world, int n1, int n2, void* __restrict__ out1, void* __restrict__ out2) {
-  const int k = threadIdx.x >> 5;  // one warp (its lane 0) per point
-  if (threadIdx.x & 31) return;
-  if (k < n1) {
-    XYZZ<G1> acc = XYZZ<G1>::inf();
-    for (int r = 0; r < world; r++) acc.add(ld_xyzz<G1>(partials1, (size_t)r * n1 + k));
-    st_xyzz<G1>(out1, k, acc);
-  } else if (k < n1 + n2) {
-    XYZZ<G2> acc = XYZZ<G2>::inf();
-    for (int r = 0; r < world; r++) acc.add(ld_xyzz<G2>(partials2, r));
-    st_xyzz<G2>(out2, 0, acc);
-  }
-}
 int groth16_sum_partials(pcdgpu_ctx* ctx, int pairing, const void* p1, const void* p2, int world, int n1, int n2,
                          void* out1, void* out2) {
-  ctx->launches += 1;
-  if (pairing == PCDGPU_MNT4_298)
-    groth16_sum_partials_kernel<CurveMnt4G1, CurveMnt4G2><<<1, 32 * (n1 + n2), 0, ctx->cur()>>>(p1, p2, world, n1, n2, out1, out2);
-  else
-    groth16_sum_partials_kernel<CurveMnt6G1, CurveMnt6G2><<<1, 32 * (n1 + n2), 0, ctx->cur()>>>(p1, p2, world, n1, n2, out1, out2);
-  PCD_CUDA(ctx, cudaGetLastError());
+  const MsmOps *o1 = msm_ops(pcd_g1_of(pairing)), *o2 = msm_ops(pcd_g2_of(pairing));
+  for (int k = 0; k < n1; k++) PCD_TRY(o1->sum_points(ctx, p1, (size_t)k, (size_t)n1, world, out1, (size_t)k, nullptr));
+  if (n2) PCD_TRY(o2->sum_points(ctx, p2, 0, 1, world, out2, 0, nullptr));
   return 0;
 }
 
 int groth16_straus(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, void* sums1) {
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
-  ctx->launches += 1;
-  if (pairing == PCDGPU_MNT4_298) groth16_straus_kernel<CurveMnt4G1><<<1, 32, 0, ctx->cur()>>>(d_rs, sums1);
-  else groth16_straus_kernel<CurveMnt6G1><<<1, 32, 0, ctx->cur()>>>(d_rs, sums1);
-  PCD_CUDA(ctx, cudaGetLastError());
+  // d_rs = r | s (plain): T = [r] g1_b + [s] g_a -> pairs (sums1[4], r), (sums1[3], s); T -> sums1[2]
+  int rc = msm_ops(pcd_g1_of(pairing))->multi_mul(ctx, sums1, 4, 3, d_rs, 2, sums1, 2);
   ctx->prof_end(ps);
-  return 0;
+  return rc;
 }
 int point_to_affine(pcdgpu_ctx* ctx, int curve, const void* src, size_t idx, void* dst) {
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
-  ctx->launches += 1;
-  cudaStream_t st = ctx->cur();
-  switch (curve) {
-    case PCDGPU_MNT4_G1: point_to_affine_kernel<CurveMnt4G1><<<1, 32, 0, st>>>(src, idx, dst); break;
-    case PCDGPU_MNT4_G2: point_to_affine_kernel<CurveMnt4G2><<<1, 32, 0, st>>>(src, idx, dst); break;
-    case PCDGPU_MNT6_G1: point_to_affine_kernel<CurveMnt6G1><<<1, 32, 0, st>>>(src, idx, dst); break;
-    default: point_to_affine_kernel<CurveMnt6G2><<<1, 32, 0, st>>>(src, idx, dst); break;
-  }
-  PCD_CUDA(ctx, cudaGetLastError());
+  int rc = msm_ops(curve)->to_affine_at(ctx, src, idx, dst);
   ctx->prof_end(ps);
-  return 0;
+  return rc;
 }
 int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_c) {
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
-  ctx->launches += 1;
-  if (pairing == PCDGPU_MNT4_298) groth16_finish_kernel<CurveMnt4G1><<<1, 32, 0, ctx->cur()>>>(sums1, d_out_c);
-  else groth16_finish_kernel<CurveMnt6G1><<<1, 32, 0, ctx->cur()>>>(sums1, d_out_c);
-  PCD_CUDA(ctx, cudaGetLastError());
+  int rc = msm_ops(pcd_g1_of(pairing))->sum_points(ctx, sums1, 0, 1, 3, nullptr, 0, d_out_c);  // C = h + l' + T
   ctx->prof_end(ps);
-  return 0;
+  return rc;
 }
 
 // ---- ark-serialize compressed proof bytes -------------------------------------------------------
@@ -285,7 +217,7 @@ __device__ unsigned char* ser_x(const Fp<P>& x, unsigned char* out, unsigned cha
   return out + 38;
 }
 template <class B, u32 NR>
-__device__ unsigned char* ser_x(const Fp2T<B, NR, false>& x, unsigned char* out, unsigned char flags) {
+__device__ unsigned char* ser_x(const Fp2T<B, NR>& x, unsigned char* out, unsigned char flags) {
   ser_fp(x.c0, out, 0);
   ser_fp(x.c1, out + 38, flags);
   return out + 76;
@@ -392,79 +324,6 @@ __global__ void __launch_bounds__(256) bench_modmul_kernel(u32* out, int iters, 
   if (x.l[0] == 0x12345u && y.l[3] == 7u) out[0] = x.l[1];
 }
 
-// the same with an explicit choice of product: SC = 1 separated carries (Fp::mul_sc), 0 carry chains (Fp::mul_cc)
-template <class F, int SC>
-__global__ void __launch_bounds__(256) bench_modmul_sel_kernel(u32* out, int iters, u32 seed) {
-  F x, y;
-  const u32* in = out + 64 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 20;
-#pragma unroll
-  for (int i = 0; i < 10; i++) {
-    x.l[i] = in[i];
-    y.l[i] = in[10 + i] ^ seed;
-  }
-  x.l[9] &= 0xff;
-  y.l[9] &= 0xff;
-  for (int i = 0; i < iters; i++) {
-    if (SC) {
-      x = F::mul_sc(x, y);
-      y = F::mul_sc(y, x);
-    } else {
-      x = F::mul_cc(x, y);
-      y = F::mul_cc(y, x);
-    }
-  }
-  if (x.l[0] == 0x12345u && y.l[3] == 7u) out[0] = x.l[1];
-}
-// independent multiply-adds with a carry OUT only, counted on the alu pipe (the building block of mul_sc)
-__global__ void __launch_bounds__(256) bench_imad_cout_kernel(u32* out, int iters, u32 seed) {
-  u32 lo[8], hi[8], c[8];
-  u32 a = seed + threadIdx.x, b = seed * 3 + blockIdx.x;
-#pragma unroll
-  for (int j = 0; j < 8; j++) {
-    lo[j] = j + threadIdx.x;
-    hi[j] = j * 3 + threadIdx.x;
-    c[j] = 0;
-  }
-  for (int i = 0; i < iters; i++) {
-#pragma unroll
-    for (int rep = 0; rep < 8; rep++) {
-#pragma unroll
-      for (int j = 0; j < 8; j++) prims::mac_carry(lo[j], hi[j], c[j], a + j, b);
-    }
-  }
-  u32 s = 0;
-#pragma unroll
-  for (int j = 0; j < 8; j++) s ^= lo[j] ^ hi[j] ^ c[j];
-  if (s == 0x1234567u) out[0] = s;
-}
-
-// the radix-2^30 carry-free product (fp30.cuh), same shape of benchmark
-template <class F, int CHAINS>
-__global__ void __launch_bounds__(256) bench_modmul30_kernel(u32* out, int iters, u32 seed) {
-  F x[CHAINS], y[CHAINS];
-  const u32* in = out + 64 + ((size_t)blockIdx.x * blockDim.x + threadIdx.x) * 20;  // per-thread operands
-#pragma unroll
-  for (int c = 0; c < CHAINS; c++) {
-#pragma unroll
-    for (int i = 0; i < 10; i++) {
-      x[c].l[i] = (in[i] + c) & 0x3fffffffu;
-      y[c].l[i] = (in[10 + i] ^ seed) & 0x3fffffffu;
-    }
-    x[c].l[9] &= 0xfffff;
-    y[c].l[9] &= 0xfffff;
-  }
-  for (int i = 0; i < iters; i++) {
-#pragma unroll
-    for (int c = 0; c < CHAINS; c++) x[c] = x[c] * y[c];
-#pragma unroll
-    for (int c = 0; c < CHAINS; c++) y[c] = y[c] * x[c];
-  }
-  u32 acc = 0;
-#pragma unroll
-  for (int c = 0; c < CHAINS; c++) acc ^= x[c].l[0] ^ y[c].l[3];
-  if (acc == 0x12345u) out[0] = acc;
-}
-
 int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double* ms_out) {
   void* d;
   size_t bytes = 4096 + (size_t)ctx->sm_count * 8 * 256 * 80;
@@ -474,27 +333,14 @@ int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double
   PCD_CUDA(ctx, cudaEventCreate(&e0));
   PCD_CUDA(ctx, cudaEventCreate(&e1));
   int blocks = ctx->sm_count * 8;
-  if (modmul == 9) blocks = ctx->sm_count;
-  double per_thread = modmul == 3 ? 64.0 * iters : (modmul ? 2.0 * iters : 64.0 * iters);
-  if (modmul == 6) per_thread = 4.0 * iters;
-  if (modmul >= 7 && modmul <= 9) blocks = ctx->sm_count * (modmul == 7 ? 2 : 1);  // low occupancy: 16 / 8 warps per SM
-  if (modmul == 12 || modmul == 15) blocks = ctx->sm_count;                         // 8 warps per SM
-  if (modmul == 16) per_thread = 64.0 * iters;
+  double per_thread = modmul == 1 || modmul == 2 || modmul == 9 ? 2.0 * iters : 64.0 * iters;
+  if (modmul == 9) blocks = ctx->sm_count;  // low occupancy: 8 warps per SM
   for (int rep = 0; rep < 2; rep++) {  // first round warms up
     PCD_CUDA(ctx, cudaEventRecord(e0, ctx->stream));
     if (modmul == 1) bench_modmul_kernel<FpR4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else if (modmul == 2) bench_modmul_kernel<FpQ4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else if (modmul == 3) bench_imadx_kernel<<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 4) bench_modmul30_kernel<Fp30R4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 5) bench_modmul30_kernel<Fp30Q4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 6) bench_modmul30_kernel<Fp30Q4, 2><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 7 || modmul == 8) bench_modmul30_kernel<Fp30Q4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 9) bench_modmul_kernel<FpQ4><<<ctx->sm_count, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 10) bench_modmul_sel_kernel<FpR4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 11 || modmul == 12) bench_modmul_sel_kernel<FpQ4, 1><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 13) bench_modmul_sel_kernel<FpR4, 0><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 14 || modmul == 15) bench_modmul_sel_kernel<FpQ4, 0><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
-    else if (modmul == 16) bench_imad_cout_kernel<<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
+    else if (modmul == 9) bench_modmul_kernel<FpQ4><<<blocks, 256, 0, ctx->stream>>>((u32*)d, iters, 7u);
     else bench_imad_kernel<<<blocks, 256, 0, ctx->stream>>>((unsigned long long*)d, iters, 7u);
     PCD_CUDA(ctx, cudaEventRecord(e1, ctx->stream));
     PCD_CUDA(ctx, cudaEventSynchronize(e1));

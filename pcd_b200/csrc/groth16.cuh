@@ -81,7 +81,7 @@ int qap_vector_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, int which, const void*
 int qap_combine_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, void* d_a, const void* d_b, const void* d_c);
 // extras <- {r, 1, 1, s, 1, 1, -(r s) mod p} as plain integers (the scalars of the constant pairs)
 int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras);
-// the proof's tail, on the context's current lane (ctx->cur()): sums1 = {h_acc, l_acc - (r s) delta, g_a, g1_b, T}
+// the proof's tail, on the context's current lane (ctx->cur()): sums1 = {h_acc, l_acc - (r s) delta, T, g_a, g1_b}
 int groth16_sum_partials(pcdgpu_ctx* ctx, int pairing, const void* p1, const void* p2, int world, int n1, int n2,
                          void* out1, void* out2);
 int groth16_straus(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, void* sums1);      // T = s g_a + r g1_b

@@ -13,10 +13,10 @@
 //   4. msm_accumulate one thread per bucket walks its entries with XYZZ mixed additions
 //                     (8M + 2S); buckets beyond HEAVY entries (e.g. the "scalar == 1" bucket of a
 //                     real witness) are left to msm_accumulate_heavy, one CTA each;
-//   5. msm_reduce_seg per window sum_b (b+1) B_b: every thread takes L consecutive buckets with the
-//                     running-sum trick and adds [t L] * (its plain sum); msm_sum folds the threads'
-//                     contributions (CTA tree sums);
-//   6. msm_combine    the 2^c Horner chain over the window sums (one window with precomputed tables).
+//   5. wec_reduce     per window sum_b (b+1) B_b: every GROUP of lanes (wec.cuh) takes L consecutive buckets
+//                     with the running-sum trick and adds [t L] * (its plain sum); the groups of a CTA and then
+//                     wec_sum fold the contributions;
+//   6. wec_combine    the 2^c Horner chain over the window sums (one window with precomputed tables).
 //
 // With precomputed bases (pcdgpu_bases_upload(..., precompute = 1)) the table holds 2^(c j) P for
 // every window j, all windows share ONE bucket set and step 6's doubling chain disappears.
@@ -28,14 +28,15 @@
 
 #include "common.cuh"
 #include "vecio.cuh"
+#include "wec.cuh"
 
 static constexpr int MSM_SCALAR_BITS = 298;
 static constexpr int MSM_HEAVY = 1024;      // upper limit of the entries one thread may walk (see heavy_thr)
 static constexpr int MSM_HEAVY_THREADS = 128;
 static constexpr int MSM_MAX_HEAVY = 16384;  // size of the heavy-bucket list
 static constexpr int MSM_HEAVY_CHUNK = 1024;  // entries of a heavy bucket summed by one CTA at a time
-static constexpr int MSM_SUM_PER_CTA = 256;   // points folded by one CTA of msm_sum_kernel (two per thread + tree)
-static constexpr int MSM_REDUCE_LOGL = 3;     // bucket reduction: 2^3 buckets per thread
+static constexpr int MSM_REDUCE_LOGL = 3;     // bucket reduction: 2^3 buckets per group of lanes
+static constexpr int MSM_SUM_PER_GROUP = 4;   // wec_sum_kernel: points added serially by a group before the CTA tree
 static constexpr int MSM_MAX_SPLIT = 4;       // parts a bucket's entry list may be cut into (msm_accumulate_kernel)
 
 // Window layout.  Plain MSMs use windows of c bits from bit 0 up.  With precomputed tables all windows
@@ -137,12 +138,11 @@ static __global__ void msm_sizekey_kernel(const u32* __restrict__ counts, size_t
 // Persistent warps pull 32 buckets at a time from a global queue (dynamic scheduling): with one thread per
 // bucket and a plain grid the kernel ran in a few "waves" of equally long threads, and its time was
 // the wave count rounded up (c = 18 at 2^20: 2.3 waves cost 3).
-// PRE: the bases are a precomputed window table, stored in the radix-2^30 form already (precompute_kernel);
-// otherwise they are ABI points and are converted as they are loaded (two extra products per addition).
+// PRE: the bases are a precomputed window table (same point encoding; kept as a template parameter because the two
+// kernels are tuned and profiled separately)
 template <class C, bool PRE>
-__device__ __forceinline__ AffinePoint<typename C::Fast::F> ld_base(const void* bases, size_t idx) {
-  if constexpr (PRE) return ld_vec<AffinePoint<typename C::Fast::F>>(bases, idx);
-  else return fast_affine<C>(ld_vec<AffinePoint<typename C::F>>(bases, idx));
+__device__ __forceinline__ AffinePoint<typename C::F> ld_base(const void* bases, size_t idx) {
+  return ld_vec<AffinePoint<typename C::F>>(bases, idx);
 }
 
 // `split` > 1: every bucket's entry list is cut into `split` equal parts walked by different threads (their sums land in
@@ -158,7 +158,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
                                                              u32* __restrict__ queue, u32 heavy_thr, u32 split,
                                                              u32* __restrict__ hflag) {
   typedef typename C::F F;
-  typedef typename C::Fast CF;    // the radix-2^30 twin of a G1 curve (ec.cuh); C itself for G2
+  typedef C CF;
   typedef typename CF::F FF;
   const unsigned lane = threadIdx.x & 31;
   const size_t nitems = nbuckets * split;
@@ -183,7 +183,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
       }
       // list full: fall through and do it serially (correct, slow); the other parts stay infinity
       if (split > 1) {
-        for (u32 q = 1; q < split; q++) st_vec(buckets, g * split + q, slow_xyzz<C>(acc));
+        for (u32 q = 1; q < split; q++) st_vec(buckets, g * split + q, acc);
       }
     } else if (split > 1) {
       const u32 len = hi - lo;
@@ -197,7 +197,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
       if (ent >> 31) p.y = p.y.neg();
       acc.madd_impl(p);  // inline even for the G2 curves: one call level less in the hottest loop
     }
-    st_vec(buckets, g * split + part, slow_xyzz<C>(acc));
+    st_vec(buckets, g * split + part, acc);
   }
 }
 // buckets[g] = sum of the `split` partial sums of bucket g (unless the heavy path owns the bucket)
@@ -246,14 +246,14 @@ __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_accumulate_heavy_kernel
       if (job % gridDim.x != blockIdx.x) continue;
       u32 e0 = lo + ch * MSM_HEAVY_CHUNK;
       u32 e1 = e0 + MSM_HEAVY_CHUNK < hi ? e0 + MSM_HEAVY_CHUNK : hi;
-      XYZZ<typename C::Fast> acc = XYZZ<typename C::Fast>::inf();
+      XYZZ<C> acc = XYZZ<C>::inf();
       for (u32 e = e0 + threadIdx.x; e < e1; e += MSM_HEAVY_THREADS) {
         u32 ent = entries[e];
-        AffinePoint<typename C::Fast::F> p = ld_base<C, PRE>(bases, ent & 0x7fffffffu);
+        AffinePoint<typename C::F> p = ld_base<C, PRE>(bases, ent & 0x7fffffffu);
         if (ent >> 31) p.y = p.y.neg();
         acc.madd(p);  // out of line for G2 (inlining it here as well takes msm_c3.cu from 80 s to 5 min of ptxas)
       }
-      cta_tree_sum<C>(sm, slow_xyzz<C>(acc));
+      cta_tree_sum<C>(sm, acc);
       if (threadIdx.x == 0) {
         u32 slot = atomicAdd(hp_count, 1u);
         hp_id[slot] = h;
@@ -282,61 +282,7 @@ __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_heavy_finish_kernel(
   }
 }
 
-// ---- 5. bucket reduction ----------------------------------------------------------------------
-// S = sum_b (b + 1) B_b per window.  Thread t of a window takes the L = 2^logL buckets [tL, tL + L) from
-// the top down with the running-sum trick (2 L general additions):
-//   run = sum_j B_{tL+j},  acc = sum_j (j + 1) B_{tL+j},  contribution = acc + [t L] run
-// ([t L] run by double-and-add, t L < 2^c); the T = B / L contributions of a window are then folded by
-// msm_sum_kernel.  Short dependent chains and three launches: this phase is latency-bound.
-template <class C>
-__global__ void __launch_bounds__(128, 4) msm_reduce_seg_kernel(const void* __restrict__ buckets, size_t B, int logL,
-                                                             int nwin, void* __restrict__ seg) {
-  const size_t L = (size_t)1 << logL;
-  const size_t T = (B + L - 1) >> logL;
-  size_t gid = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (gid >= T * nwin) return;
-  size_t w = gid / T, t = gid - w * T;
-  size_t base = w * B + t * L;
-  size_t lim = B - t * L < L ? B - t * L : L;
-  XYZZ<C> run = XYZZ<C>::inf(), acc = XYZZ<C>::inf();
-  for (size_t j = lim; j-- > 0;) {
-    XYZZ<C> p = ld_vec_rw<XYZZ<C>>(buckets, base + j);
-    run.add(p);
-    acc.add(run);
-  }
-  u32 k = (u32)(t * L);
-  if (k != 0 && !run.is_inf()) acc.add(XYZZ<C>::mul(run, &k, 1));
-  st_vec(seg, gid, acc);
-}
-
-// out[w * out_pitch + blockIdx.x'] = sum of up to MSM_SUM_PER_CTA consecutive points of window w
-template <class C>
-__global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_sum_kernel(const void* __restrict__ in, size_t in_pitch,
-                                                                    size_t count, void* __restrict__ out,
-                                                                    size_t out_pitch, size_t ctas_per_win) {
-  extern __shared__ uint4 sm4[];
-  XYZZ<C>* sm = reinterpret_cast<XYZZ<C>*>(sm4);
-  size_t w = blockIdx.x / ctas_per_win, k = blockIdx.x - w * ctas_per_win;
-  size_t lo = k * MSM_SUM_PER_CTA;
-  size_t hi = lo + MSM_SUM_PER_CTA < count ? lo + MSM_SUM_PER_CTA : count;
-  XYZZ<C> acc = XYZZ<C>::inf();
-  for (size_t i = lo + threadIdx.x; i < hi; i += MSM_HEAVY_THREADS) acc.add(ld_vec_rw<XYZZ<C>>(in, w * in_pitch + i));
-  cta_tree_sum<C>(sm, acc);
-  if (threadIdx.x == 0) st_vec(out, w * out_pitch + k, sm[0]);
-}
-
-// ---- 6. combine windows ---------------------------------------------------------------------------
-// result = sum_w 2^(c w) wsum[w] by Horner (one thread; nwin = 1 with precomputed tables)
-template <class C>
-__global__ void msm_combine_kernel(const void* __restrict__ wsum, int c, int nwin, void* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<C> total = ld_vec_rw<XYZZ<C>>(wsum, nwin - 1);
-  for (int ww = nwin - 2; ww >= 0; ww--) {
-    for (int i = 0; i < c; i++) total = total.dbl();
-    total.add(ld_vec_rw<XYZZ<C>>(wsum, ww));
-  }
-  st_vec(out, 0, total);
-}
+// ---- 5. / 6. bucket reduction and window combination: wec.cuh (lane-cooperative group law) -------------------------
 
 // ---- helpers: normalisation, fixed-base multiplication, table precomputation ---------------------
 template <class C>
@@ -345,18 +291,6 @@ __global__ void xyzz_to_affine_kernel(const void* __restrict__ in, size_t n, voi
   if (i >= n) return;
   XYZZ<C> p = ld_vec_rw<XYZZ<C>>(in, i);
   st_vec(out, i, p.to_affine());
-}
-
-// sum of n xyzz points -> affine (single thread; n is a handful of per-GPU partials)
-template <class C>
-__global__ void xyzz_sum_kernel(const void* __restrict__ in, size_t n, void* __restrict__ out) {
-  if (threadIdx.x != 0 || blockIdx.x != 0) return;
-  XYZZ<C> acc = XYZZ<C>::inf();
-  for (size_t i = 0; i < n; i++) {
-    XYZZ<C> p = ld_vec_rw<XYZZ<C>>(in, i);
-    acc.add(p);
-  }
-  st_vec(out, 0, acc.to_affine());
 }
 
 // table[j * 15 + (d - 1)] = d * 16^j * base, j < 75, d in 1..15 (4-bit fixed windows), affine
@@ -399,8 +333,6 @@ __global__ void __launch_bounds__(128) fixed_mul_kernel(const void* __restrict__
 }
 
 // pre[j * n + i] = 2^(start_j) * bases[i]  (affine), j < nwin, start_j = msm_win_start(j, c, nwin, balanced).
-// For the G1 curves the table is written in the radix-2^30 form the accumulate kernels compute in (same 40
-// bytes per coordinate): it is read by msm_accumulate*<C, true> only.
 template <class C>
 __global__ void __launch_bounds__(128) precompute_kernel(const void* __restrict__ bases, size_t n, int c, int nwin,
                                                          void* __restrict__ pre) {
@@ -408,13 +340,13 @@ __global__ void __launch_bounds__(128) precompute_kernel(const void* __restrict_
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   AffinePoint<F> a = ld_vec_rw<AffinePoint<F>>(bases, i);  // pre may alias bases (row 0 in place)
-  st_vec(pre, i, fast_affine<C>(a));
+  st_vec(pre, i, a);
   XYZZ<C> p = XYZZ<C>::from_affine(a);
   for (int j = 1; j < nwin; j++) {
     int nd = msm_win_start(j, c, nwin, 1) - msm_win_start(j - 1, c, nwin, 1);
     for (int b = 0; b < nd; b++) p = p.dbl();
     a = p.to_affine();
-    st_vec(pre, (size_t)j * n + i, fast_affine<C>(a));
+    st_vec(pre, (size_t)j * n + i, a);
     p = XYZZ<C>::from_affine(a);
   }
 }
@@ -465,8 +397,8 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   PCD_CUDA(ctx, cudaMemsetAsync(queue, 0, 4, st));
   const int acc_slot = sizeof(typename C::F) > 40 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1;
   int ps = ctx->prof_begin(PROF_MSM_SORT, (double)n * nwin);
-  ctx->launches += 6 + 2;  // digits, scatter, accumulate, heavy x2, combine + cub's scan (init, scan); the
-                           // reduction levels count themselves
+  ctx->launches += 5 + 2;  // digits, scatter, accumulate, heavy x2 + cub's scan (init, scan); the reduction and
+                           // combination count themselves
   msm_digits_kernel<SP><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const u32*)d_scalars, scalars_mont, n_main,
                                                                     (const u32*)d_extra, n, c, nwin,
                                                                     shared, (int*)dig, counts);
@@ -545,7 +477,6 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                                      (int)heavy_smem));
   PCD_CUDA(ctx, cudaFuncSetAttribute(msm_heavy_finish_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                      (int)heavy_smem));
-  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_sum_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)heavy_smem));
   if (shared)
     msm_accumulate_heavy_kernel<C, true><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
         d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
@@ -557,41 +488,52 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   ps = ctx->prof_begin(PROF_MSM_REDUCE, (double)nbuckets);
-  // seg layout, in points: contributions [rwin][T] | partial sums 2 x [rwin][T / SUM + 2] | wsum [rwin]
-  const int logL = MSM_REDUCE_LOGL;
+  // seg layout, in points: CTA partial sums [rwin][ctas] | sum levels 2 x [rwin][pitch] | wsum [rwin]
+  typedef Wec<C> WG;
+  static const int logL_env = getenv("PCDGPU_REDUCE_LOGL") ? atoi(getenv("PCDGPU_REDUCE_LOGL")) : 0;  // development aid
+  const int logL = logL_env > 0 ? logL_env : MSM_REDUCE_LOGL;
   const size_t L = (size_t)1 << logL;
   const size_t T = (B + L - 1) >> logL;
-  const size_t part_pitch = T / MSM_SUM_PER_CTA + 2;
+  const size_t GPC = WEC_THREADS / WG::G;
+  const size_t ctas = (T + GPC - 1) / GPC;
+  const size_t per_cta = GPC * MSM_SUM_PER_GROUP;
+  const size_t pitch = (ctas + per_cta - 1) / per_cta + 1;
   const size_t PB = sizeof(XYZZ<C>);
-  PCD_TRY(ctx->scratch(SLOT_MSM_SEG, ((size_t)rwin * T + 2 * rwin * part_pitch + rwin + 8) * PB, &seg));
+  PCD_TRY(ctx->scratch(SLOT_MSM_SEG, ((size_t)rwin * ctas + 2 * rwin * pitch + rwin + 8) * PB, &seg));
   char* sp = (char*)seg;
-  void* part_buf[2] = {sp + (size_t)rwin * T * PB, sp + ((size_t)rwin * T + rwin * part_pitch) * PB};
-  void* wsum = (char*)part_buf[1] + (size_t)rwin * part_pitch * PB;
-  msm_reduce_seg_kernel<C><<<(unsigned)((T * rwin + 127) / 128), 128, 0, st>>>(bkt, B, logL, rwin, seg);
+  void* lvl[2] = {sp + (size_t)rwin * ctas * PB, sp + ((size_t)rwin * ctas + rwin * pitch) * PB};
+  void* wsum = (char*)lvl[1] + (size_t)rwin * pitch * PB;
+  void* fin = rwin == 1 ? d_out : wsum;  // one window (precomputed tables): its sum IS the result
+  const size_t red_smem = wec_smem_bytes<C>(WEC_THREADS, 4), sum_smem = wec_smem_bytes<C>(WEC_THREADS, 2);
+  PCD_CUDA(ctx, cudaFuncSetAttribute(wec_reduce_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+  PCD_CUDA(ctx, cudaFuncSetAttribute(wec_sum_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
+  wec_reduce_kernel<C><<<dim3((unsigned)ctas, (unsigned)rwin), WEC_THREADS, red_smem, st>>>(bkt, B, logL,
+                                                                                         ctas == 1 ? fin : seg);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
-  const void* fin = seg;
-  size_t fpitch = T, fcount = T;
+  const void* in = seg;
+  size_t in_pitch = ctas, count = ctas;
   int pp = 0;
-  for (;;) {
-    size_t ctas = (fcount + MSM_SUM_PER_CTA - 1) / MSM_SUM_PER_CTA;
-    bool last = ctas == 1;
-    void* fout = last ? wsum : part_buf[pp];
-    size_t opitch = last ? 1 : part_pitch;
-    msm_sum_kernel<C><<<(unsigned)(ctas * rwin), MSM_HEAVY_THREADS, heavy_smem, st>>>(fin, fpitch, fcount, fout, opitch,
-                                                                                   ctas);
+  while (count > 1) {
+    size_t nct = (count + per_cta - 1) / per_cta;
+    void* out = nct == 1 ? fin : lvl[pp];
+    size_t out_pitch = nct == 1 ? 1 : pitch;
+    wec_sum_kernel<C><<<dim3((unsigned)nct, (unsigned)rwin), WEC_THREADS, sum_smem, st>>>(in, in_pitch, count, out, out_pitch,
+                                                                                       MSM_SUM_PER_GROUP);
     PCD_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
-    if (last) break;
-    fin = fout;
-    fpitch = part_pitch;
-    fcount = ctas;
+    in = out;
+    in_pitch = out_pitch;
+    count = nct;
     pp ^= 1;
   }
   ctx->prof_end(ps);
-  ps = ctx->prof_begin(PROF_MSM_TAIL, (double)rwin);
-  msm_combine_kernel<C><<<1, 32, 0, st>>>(wsum, c, rwin, d_out);
-  PCD_CUDA(ctx, cudaGetLastError());
-  ctx->prof_end(ps);
+  if (rwin > 1) {
+    ps = ctx->prof_begin(PROF_MSM_TAIL, (double)rwin);
+    wec_combine_kernel<C><<<1, 32, 0, st>>>(wsum, c, rwin, d_out);
+    PCD_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    ctx->prof_end(ps);
+  }
   return 0;
 }

@@ -16,10 +16,30 @@ int to_affine_(pcdgpu_ctx* ctx, const void* in, size_t n, void* out) {
   PCD_CUDA(ctx, cudaGetLastError());
   return 0;
 }
-int xyzz_sum_(pcdgpu_ctx* ctx, const void* in, size_t n, void* out) {
-  xyzz_sum_kernel<CV><<<1, 32, 0, ctx->stream>>>(in, n, out);
+int to_affine_at_(pcdgpu_ctx* ctx, const void* in, size_t idx, void* out) {
+  wec_to_affine_kernel<CV><<<1, 32, 0, ctx->cur()>>>(in, idx, out);
   PCD_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
   return 0;
+}
+int sum_points_(pcdgpu_ctx* ctx, const void* in, size_t first, size_t stride, int n, void* out_xyzz, size_t out_idx,
+                void* out_affine) {
+  wec_sum_affine_kernel<CV><<<1, 32, 0, ctx->cur()>>>(in, first, stride, n, out_xyzz, out_idx, out_affine);
+  PCD_CUDA(ctx, cudaGetLastError());
+  ctx->launches += 1;
+  return 0;
+}
+int multi_mul_(pcdgpu_ctx* ctx, const void* pts, size_t idx0, size_t idx1, const void* k, int npairs, void* out,
+               size_t out_idx) {
+  if constexpr (Wec<CV>::G <= 16 && Wec<CV>::K == 1) {
+    wec_multi_mul_kernel<CV><<<1, 32, 0, ctx->cur()>>>(pts, idx0, idx1, (const u32*)k, npairs, out, out_idx);
+    PCD_CUDA(ctx, cudaGetLastError());
+    ctx->launches += 1;
+    return 0;
+  } else {
+    ctx->set_error("multi_mul is a G1 operation");
+    return PCDGPU_E_ARG;
+  }
 }
 int fixed_table_(pcdgpu_ctx* ctx, const void* base, void* table) {
   fixed_table_kernel<CV><<<3, 32, 0, ctx->stream>>>(base, table);
@@ -41,5 +61,5 @@ int precompute_(pcdgpu_ctx* ctx, const void* bases, size_t n, int c, int nwin, v
 }  // namespace
 
 const MsmOps PCD_OPS_NAME = {sizeof(AffinePoint<CV::F>), sizeof(XYZZ<CV>), CV::ScalarParams::ID, run_,
-                             to_affine_,                 xyzz_sum_,        fixed_table_,         fixed_mul_,
-                             precompute_};
+                             to_affine_,                 to_affine_at_,    sum_points_,          multi_mul_,
+                             fixed_table_,               fixed_mul_,       precompute_};

@@ -16,7 +16,16 @@ struct MsmOps {
   int (*run)(pcdgpu_ctx*, const void* d_bases, const void* d_scalars, int mont, size_t n, const void* d_extra,
              size_t n_extra, MsmPlanC plan, void* d_out);
   int (*to_affine)(pcdgpu_ctx*, const void* d_in, size_t n, void* d_out);
-  int (*xyzz_sum)(pcdgpu_ctx*, const void* d_in, size_t n, void* d_out_affine);
+  // the proof / MSM tails, lane-cooperative (wec.cuh), on the context's CURRENT lane (ctx->cur()):
+  //   to_affine_at  d_out_affine <- xyzz point idx of d_in
+  //   sum_points    sum of the n points d_in[first + i * stride] -> xyzz at d_out_xyzz[out_idx] and / or affine (null: skip)
+  //   multi_mul     d_out[out_idx] <- sum_{j < npairs} [k_j] d_pts[idx_j]; k_j ten plain words at d_k + 10 j (G1 curves
+  //                 only; npairs <= 2)
+  int (*to_affine_at)(pcdgpu_ctx*, const void* d_in, size_t idx, void* d_out_affine);
+  int (*sum_points)(pcdgpu_ctx*, const void* d_in, size_t first, size_t stride, int n, void* d_out_xyzz, size_t out_idx,
+                    void* d_out_affine);
+  int (*multi_mul)(pcdgpu_ctx*, const void* d_pts, size_t idx0, size_t idx1, const void* d_k, int npairs, void* d_out,
+                   size_t out_idx);
   // d_table: 75 * 15 affine points (built from d_base by fixed_table); out[i] = scalars[i] * base
   int (*fixed_table)(pcdgpu_ctx*, const void* d_base, void* d_table);
   int (*fixed_mul)(pcdgpu_ctx*, const void* d_table, const void* d_scalars, size_t n, void* d_out);

@@ -226,7 +226,7 @@ int pcdgpu_kzg_commit(pcdgpu_ctx* ctx, const pcdgpu_bases* powers_of_g, const vo
   int count = 0;
   PCD_TRY(kzg_commit_xyzz(ctx, powers_of_g, dc, n, powers_of_gamma_g, dr, n_rand, misc, &count));
   void* d_aff = (char*)misc + 2 * ops->xyzz_bytes;
-  PCD_TRY(ops->xyzz_sum(ctx, misc, count, d_aff));
+  PCD_TRY(ops->sum_points(ctx, misc, 0, 1, count, nullptr, 0, d_aff));
   PCD_CUDA(ctx, cudaMemcpyAsync(out_affine, d_aff, ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
@@ -268,7 +268,7 @@ int pcdgpu_kzg_open(pcdgpu_ctx* ctx, const pcdgpu_bases* powers_of_g, const void
   PCD_TRY(kzg_commit_xyzz(ctx, powers_of_g, dq, n - 1, hiding ? powers_of_gamma_g : nullptr, drq,
                           hiding ? n_rand - 1 : 0, misc, &count));
   void* d_aff = (char*)misc + 2 * ops->xyzz_bytes;
-  PCD_TRY(ops->xyzz_sum(ctx, misc, count, d_aff));
+  PCD_TRY(ops->sum_points(ctx, misc, 0, 1, count, nullptr, 0, d_aff));
   PCD_CUDA(ctx, cudaMemcpyAsync(out_w_affine, d_aff, ops->affine_bytes, cudaMemcpyDeviceToHost, st));
   if (out_value) PCD_CUDA(ctx, cudaMemcpyAsync(out_value, de, 40, cudaMemcpyDeviceToHost, st));
   if (hiding) PCD_CUDA(ctx, cudaMemcpyAsync(out_random_v, dre, 40, cudaMemcpyDeviceToHost, st));

@@ -25,7 +25,7 @@ static void fp_op(int op, const u32* a, const u32* b, u32* out) {
     case 9: r = x.template mul_small<11>(); break;
     case 10: r = x.dbl(); break;
     case 11: r = F::zero(); r.l[0] = x.lexicographically_largest(); break;
-    case 12: r = F::mul_sc(x, y); break;
+    case 12: r = x.inverse_fermat(); break;
     default: r = F::zero();
   }
   st(out, r);
@@ -86,42 +86,4 @@ extern "C" void emu_ec_op(int curve, int op, const u32* p, const u32* q, const u
     case 2: ec_op<CurveMnt6G1>(op, p, q, k, klimbs, out); break;
     default: ec_op<CurveMnt6G2>(op, p, q, k, klimbs, out); break;
   }
-}
-
-// ---- radix-2^30 field and its G1 twins (fp30.cuh, ec.cuh: fast_affine / slow_xyzz) ---------------------
-template <class P, class P30>
-static void fp30_op(int op, const u32* a, const u32* b, u32* out) {
-  Fp<P> x = ld<Fp<P>>(a), y = ld<Fp<P>>(b);
-  Fp30<P30> fx = to_fast<P30>(x), fy = to_fast<P30>(y), r;
-  switch (op) {
-    case 0: r = fx + fy; break;
-    case 1: r = fx - fy; break;
-    case 2: r = fx * fy; break;
-    case 3: r = fx.sqr(); break;
-    case 5: r = fx.neg(); break;
-    case 10: r = fx.dbl(); break;
-    case 13: r = Fp30<P30>::zero(); r.l[0] = (fx == fy) ? 1 : 0; break;  // equality across representatives
-    default: r = fx;
-  }
-  if (op == 13) { memcpy(out, r.l, 40); return; }
-  st(out, from_fast<P>(r));
-}
-extern "C" void emu_fp30_op(int field, int op, const u32* a, const u32* b, u32* out) {
-  if (field == 0) fp30_op<ParamsR4, Params30R4>(op, a, b, out); else fp30_op<ParamsQ4, Params30Q4>(op, a, b, out);
-}
-// buckets as the accumulate kernels build them: inf, then madd of the n given affine points (sign bit in
-// signs[i] negates y), in the radix-2^30 twin; returned through slow_xyzz as an affine ABI point
-template <class C>
-static void ec_fast_acc(const u32* pts, const int* signs, int n, u32* out) {
-  typedef typename C::F F;
-  XYZZ<typename C::Fast> acc = XYZZ<typename C::Fast>::inf();
-  for (int i = 0; i < n; i++) {
-    AffinePoint<typename C::Fast::F> p = fast_affine<C>(ldx<AffinePoint<F>>(pts + (size_t)i * (sizeof(AffinePoint<F>) / 4)));
-    if (signs[i]) p.y = p.y.neg();
-    acc.madd(p);
-  }
-  stx(out, slow_xyzz<C>(acc).to_affine());
-}
-extern "C" void emu_ec_fast_acc(int curve, const u32* pts, const int* signs, int n, u32* out) {
-  if (curve == 0) ec_fast_acc<CurveMnt4G1>(pts, signs, n, out); else ec_fast_acc<CurveMnt6G1>(pts, signs, n, out);
 }
