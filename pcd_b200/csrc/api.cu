@@ -1,5 +1,7 @@
 // api.cu -- the extern "C" surface of libpcdgpu.so (include/pcdgpu.h).  Host-pointer entry points
 // stage through device scratch; _dev entry points are asynchronous on the context's stream.
+#include <cstdlib>
+
 #include "groth16.cuh"
 #include "msm_ops.cuh"
 #include "ntt.cuh"
@@ -85,14 +87,24 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
   pcdgpu_ctx* ctx = new pcdgpu_ctx();
   ctx->device = device;
   ctx->sm_count = prop.multiProcessorCount;
-  if (cudaStreamCreateWithFlags(&ctx->own_stream, cudaStreamNonBlocking) != cudaSuccess) {
+  // Stream priorities: lane 0 carries the witness map and the MSM over h -- a chain of short kernels (CSR product,
+  // NTT passes) that the other lanes' accumulation kernels would otherwise starve (measured at 2^18: seven NTTs that
+  // take 0.1 ms each alone stretched over 6 ms, delaying the h MSM to the very end of the proof); lanes 2 and 3 (a,
+  // b_g1) feed the double-scalar multiplication and come next; the G2 and l MSMs fill the rest.
+  int prio_least = 0, prio_greatest = 0;
+  cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
+  static const bool no_prio = getenv("PCDGPU_NO_PRIORITIES") != nullptr;  // development aid (A/B runs)
+  if (no_prio) prio_greatest = prio_least;
+  const int prio_mid = prio_greatest < prio_least ? prio_greatest + 1 : prio_least;
+  if (cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
     delete ctx;
     return PCDGPU_E_CUDA;
   }
   ctx->stream = ctx->own_stream;
   bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   for (int l = 1; l < pcdgpu_ctx::NLANE && ok; l++)
-    ok = cudaStreamCreateWithFlags(&ctx->lane_stream[l], cudaStreamNonBlocking) == cudaSuccess &&
+    ok = cudaStreamCreateWithPriority(&ctx->lane_stream[l], cudaStreamNonBlocking,
+                                      (l == 2 || l == 3) ? prio_mid : prio_least) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     delete ctx;
@@ -265,13 +277,16 @@ int pcdgpu_bases_upload(pcdgpu_ctx* ctx, int curve, const void* bases, size_t n,
   b->table = nullptr;
   size_t rows = 1;
   if (precompute && n > 0) {
-    // key queries (ctx->key_upload): the five MSMs of a proof run side by side, so the latency-bound bucket
-    // reduction competes with the other lanes' accumulation for issue slots and a window one bit smaller (half
-    // the buckets) wins even though the accumulation grows: measured with the full proof at 2^20, c = 18: 26.5 ms,
-    // 19: 29.4, 20: 35.8; at 2^18, c = 17: 9.8 ms, 18: 11.6, 16: 10.2 (a lone MSM still prefers the larger window)
-    // (at 2^16 the larger window still wins: 5.1 vs 6.0 ms; at 2^17 they tie -- hence only from 2^18 up)
+    // key queries (ctx->key_upload): the five MSMs of a proof run side by side, so the latency-bound bucket reduction
+    // (cost ~ 2^(c-1) buckets) competes with the other lanes' accumulation (cost ~ 299 / c additions per point) and a
+    // smaller window than a lone MSM's wins.  Measured with the whole proof (tools/probe_pcd.py, round 2, lane-cooperative
+    // reduction): 2^18 main proof c = 15: 8.41 ms, 16: 8.34, 17: 8.90, 18: 10.1; 2^16 helper proof (G2 over Fq3) c = 14:
+    // 9.4 ms, 15: 6.27, 16: 7.50, 17: 8.4 (below c = 15 the accumulation runs out of buckets to spread over the SMs).
     b->c = ctx->msm_window > 0 ? ctx->msm_window : msm_auto_window_c(n, 1);
-    if (ctx->msm_window <= 0 && ctx->key_upload && b->c >= 18) b->c -= 1;
+    if (ctx->msm_window <= 0 && ctx->key_upload) {
+      if (b->c >= 18) b->c -= 2;
+      else if (b->c >= 16) b->c -= 1;
+    }
     b->nwin = msm_num_windows_c(b->c);
     rows = b->nwin;
   }

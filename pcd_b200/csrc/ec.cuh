@@ -9,6 +9,7 @@
 #pragma once
 #include <type_traits>
 
+#include "fp3s.cuh"
 #include "fpx.cuh"
 
 template <class F>
@@ -46,6 +47,23 @@ struct CurveMnt6G2 {  // twist over Fq3: a' = (0, 0, 11) = 11 u^2;  u^3 = 5
     return r;
   }
 };
+
+#if defined(__CUDACC__)
+// CurveMnt6G2 with its coordinates sliced over three lanes (fp3s.cuh): the bucket-accumulation kernels' twin.
+// Memory layout of points is CurveMnt6G2's; lane l of a group reads / writes coefficient l of every coordinate.
+struct CurveMnt6G2S {
+  typedef Fq3S F; typedef ParamsQ4 ScalarParams; static constexpr int ID = 3;
+  static constexpr bool OUTLINE = false;
+  __device__ __forceinline__ static F mul_a(const F& v) {  // a' = 11 u^2: (55 v1, 55 v2, 11 v0)
+    const int l = F::li();
+    const int base = (int)(threadIdx.x & 31u) - l;
+    const FpR4 t = F::shfl(v.c, base + (l == 2 ? 0 : l + 1)).template mul_small<11>();
+    F r;
+    r.c = F::sel(l == 2, t, t.template mul_small<5>());
+    return r;
+  }
+};
+#endif
 
 template <class C>
 struct XYZZ {

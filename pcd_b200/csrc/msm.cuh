@@ -200,6 +200,127 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
     st_vec(buckets, g * split + part, acc);
   }
 }
+// ---- the same walk with the point sliced over the three lanes of a group (Fq3: fp3s.cuh) -----------------------------
+// Lane l of a group holds coefficient l of every coordinate: a group walks one work item, a warp ten (lanes 30, 31
+// idle).  Registers per lane drop to a third of the one-thread form, so nothing spills and every product is inline.
+template <class CS>
+__device__ __forceinline__ AffinePoint<typename CS::F> ld_base_sliced(const void* bases, size_t idx, int l) {
+  AffinePoint<typename CS::F> p;
+  const char* src = reinterpret_cast<const char*>(bases) + idx * (size_t)240;
+  const uint2* px = reinterpret_cast<const uint2*>(src + 40 * l);
+  const uint2* py = reinterpret_cast<const uint2*>(src + 120 + 40 * l);
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    uint2 a = __ldg(px + i), b = __ldg(py + i);
+    p.x.c.l[2 * i] = a.x;
+    p.x.c.l[2 * i + 1] = a.y;
+    p.y.c.l[2 * i] = b.x;
+    p.y.c.l[2 * i + 1] = b.y;
+  }
+  return p;
+}
+template <class CS>
+__device__ __forceinline__ void st_xyzz_sliced(void* buckets, size_t idx, const XYZZ<CS>& a, int l) {
+  char* dst = reinterpret_cast<char*>(buckets) + idx * (size_t)480 + 40 * l;
+  const FpR4* co[4] = {&a.x.c, &a.y.c, &a.zz.c, &a.zzz.c};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    uint2* d = reinterpret_cast<uint2*>(dst + 120 * q);
+#pragma unroll
+    for (int i = 0; i < 5; i++) d[i] = make_uint2(co[q]->l[2 * i], co[q]->l[2 * i + 1]);
+  }
+}
+template <class CS>
+__device__ __forceinline__ XYZZ<CS> ld_xyzz_sliced(const void* buckets, size_t idx, int l) {
+  XYZZ<CS> a;
+  const char* src = reinterpret_cast<const char*>(buckets) + idx * (size_t)480 + 40 * l;
+  FpR4* co[4] = {&a.x.c, &a.y.c, &a.zz.c, &a.zzz.c};
+#pragma unroll
+  for (int q = 0; q < 4; q++) {
+    const uint2* d = reinterpret_cast<const uint2*>(src + 120 * q);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      uint2 v = d[i];
+      co[q]->l[2 * i] = v.x;
+      co[q]->l[2 * i + 1] = v.y;
+    }
+  }
+  return a;
+}
+
+#ifndef PCD_SLICED_MIN_CTAS
+#define PCD_SLICED_MIN_CTAS 3
+#endif
+template <class CS, bool PRE>
+__global__ void __launch_bounds__(128, PCD_SLICED_MIN_CTAS) msm_accumulate_sliced_kernel(const void* __restrict__ bases,
+                                                                    const u32* __restrict__ offsets,
+                                                                    const u32* __restrict__ entries,
+                                                                    const u32* __restrict__ perm, size_t nbuckets,
+                                                                    void* __restrict__ buckets, u32* __restrict__ heavy,
+                                                                    u32* __restrict__ queue, u32 heavy_thr, u32 split,
+                                                                    u32* __restrict__ hflag) {
+  typedef typename CS::F FF;
+  const unsigned lane = threadIdx.x & 31;
+  const int l = (int)(lane % 3u);
+  const unsigned grp = lane / 3u;  // 0..9 (10: the two idle lanes)
+  const size_t nitems = nbuckets * split;
+  for (;;) {
+    u32 first = 0;
+    if (lane == 0) first = atomicAdd(queue, 10u);
+    first = __shfl_sync(0xffffffffu, first, 0);
+    if (first >= nitems) break;
+    if (grp >= 10) continue;
+    size_t t = (size_t)first + grp;
+    if (t >= nitems) continue;
+    const u32 part = (u32)(t % split);
+    size_t g = perm[t / split];
+    u32 lo = offsets[g], hi = offsets[g + 1];
+    XYZZ<CS> acc = XYZZ<CS>::inf();
+    if (hi - lo > heavy_thr) {
+      if (part != 0) continue;  // part 0 speaks for the whole bucket
+      u32 slot = 0;
+      if (l == 0) slot = atomicAdd(&heavy[0], 1u);
+      slot = __shfl_sync(FF::gmask(), slot, (int)(lane - l));
+      if (slot < (u32)MSM_MAX_HEAVY) {
+        if (l == 0) {
+          heavy[1 + slot] = (u32)g;
+          hflag[g] = 0xffffffffu;
+        }
+        continue;
+      }
+      if (split > 1) {  // list full: walk it here (correct, slow); the other parts stay infinity
+        for (u32 q = 1; q < split; q++) st_xyzz_sliced<CS>(buckets, g * split + q, acc, l);
+      }
+    } else if (split > 1) {
+      const u32 len = hi - lo;
+      const u32 a = lo + (u32)(((unsigned long long)len * part) / split);
+      hi = lo + (u32)(((unsigned long long)len * (part + 1)) / split);
+      lo = a;
+    }
+    for (u32 e = lo; e < hi; e++) {
+      u32 ent = entries[e];
+      AffinePoint<FF> p = ld_base_sliced<CS>(bases, ent & 0x7fffffffu, l);
+      if (ent >> 31) p.y = p.y.neg();
+      acc.madd_impl(p);
+    }
+    st_xyzz_sliced<CS>(buckets, g * split + part, acc, l);
+  }
+}
+// fold of the bucket parts, sliced (three lanes per bucket)
+template <class CS>
+__global__ void __launch_bounds__(96) msm_fold_parts_sliced_kernel(const void* __restrict__ partials, size_t nbuckets, u32 split,
+                                                                   const u32* __restrict__ hflag, void* __restrict__ buckets) {
+  // 96 threads = 3 warps of 10 groups: group index from the warp, so that a group never straddles two warps
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  if (lane >= 30) return;
+  const int l = (int)(lane % 3u);
+  size_t g = ((size_t)blockIdx.x * 3 + warp) * 10 + lane / 3u;
+  if (g >= nbuckets || hflag[g] == 0xffffffffu) return;
+  XYZZ<CS> acc = ld_xyzz_sliced<CS>(partials, g * split, l);
+  for (u32 q = 1; q < split; q++) acc.add_impl(ld_xyzz_sliced<CS>(partials, g * split + q, l));
+  st_xyzz_sliced<CS>(buckets, g, acc, l);
+}
+
 // buckets[g] = sum of the `split` partial sums of bucket g (unless the heavy path owns the bucket)
 template <class C>
 __global__ void __launch_bounds__(128) msm_fold_parts_kernel(const void* __restrict__ partials, size_t nbuckets, u32 split,
@@ -352,6 +473,11 @@ __global__ void __launch_bounds__(128) precompute_kernel(const void* __restrict_
 }
 
 // ---- host driver --------------------------------------------------------------------------------
+// curves whose accumulation runs sliced over three lanes (fp3s.cuh)
+template <class C> struct MsmSliced { static constexpr bool value = false; typedef C type; };
+#if defined(__CUDACC__)
+template <> struct MsmSliced<CurveMnt6G2> { static constexpr bool value = true; typedef CurveMnt6G2S type; };
+#endif
 struct MsmPlan {
   int c, nwin, shared;
   size_t stride, offset;  // shared (precomputed) tables: row pitch in points and first point used
@@ -428,15 +554,22 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     ctx->spans[ps].units_pinned = ps;
     cudaMemcpyAsync(ctx->prof_pinned + ps, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st);
   }
+  constexpr bool SLICED = MsmSliced<C>::value;      // three lanes per work item (Fq3)
+  constexpr size_t ITEMS_PER_CTA = SLICED ? 40 : 128;  // work items a CTA of 128 threads holds at a time
   int acc_ctas = 0;
-  if (shared) PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, true>, 128, 0));
-  else PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, false>, 128, 0));
+  if constexpr (SLICED) {
+    if (shared) PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, true>, 128, 0));
+    else PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, false>, 128, 0));
+  } else {
+    if (shared) PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, true>, 128, 0));
+    else PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, false>, 128, 0));
+  }
   if (acc_ctas < 1) acc_ctas = 1;
   // CTAs per SM (measured, bench.py): side by side with the other lanes of a proof two CTAs (8 warps) are best -- the
   // registers left free let the latency-bound kernels (reduction, sorting, tails) run beside this one; a lone MSM
   // gains 4 % from a third CTA (5.99 -> 5.77 ms at 2^20); a fourth, forced to 128 registers, is slower.
   static const int acc_cap_env = getenv("PCDGPU_ACC_CTAS") ? atoi(getenv("PCDGPU_ACC_CTAS")) : 0;  // development aid
-  const int acc_cap = acc_cap_env > 0 ? acc_cap_env : (ctx->concurrent && ctx->in_proof ? 2 : 3);
+  const int acc_cap = acc_cap_env > 0 ? acc_cap_env : (SLICED ? 4 : (ctx->concurrent && ctx->in_proof ? 2 : 3));
   if (acc_ctas > acc_cap) acc_ctas = acc_cap;
   size_t acc_grid = (size_t)acc_ctas * ctx->sm_count;
   // One thread walks a bucket only up to 4 x the average size.  Real witnesses repeat values (0, 1, 2, -1,
@@ -446,19 +579,32 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   u32 heavy_thr = (u32)(4 * avg_entries < 64 ? 64 : (4 * avg_entries > (size_t)MSM_HEAVY ? (size_t)MSM_HEAVY : 4 * avg_entries));
   // bucket parts: at least ~6 waves of work items, at least 8 entries per part
   u32 split = 1;
-  while (split < (u32)MSM_MAX_SPLIT && nbuckets * split < 6 * acc_grid * 128 && avg_entries / (2 * split) >= 8) split *= 2;
-  if (acc_grid > (nbuckets * split + 127) / 128) acc_grid = (nbuckets * split + 127) / 128;
+  while (split < (u32)MSM_MAX_SPLIT && nbuckets * split < 6 * acc_grid * ITEMS_PER_CTA && avg_entries / (2 * split) >= 8) split *= 2;
+  if (acc_grid > (nbuckets * split + ITEMS_PER_CTA - 1) / ITEMS_PER_CTA) acc_grid = (nbuckets * split + ITEMS_PER_CTA - 1) / ITEMS_PER_CTA;
   PCD_TRY(ctx->scratch(SLOT_MSM_BKT, nbuckets * sizeof(XYZZ<C>) * (split > 1 ? 1 + split : 1), &bkt));  // buckets | parts
   void* acc_out = split > 1 ? (void*)((char*)bkt + nbuckets * sizeof(XYZZ<C>)) : bkt;
-  if (shared)
-    msm_accumulate_kernel<C, true><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                     acc_out, heavy, queue, heavy_thr, split, cursor);
-  else
-    msm_accumulate_kernel<C, false><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                      acc_out, heavy, queue, heavy_thr, split, cursor);
+  if constexpr (SLICED) {
+    if (shared)
+      msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, true><<<(unsigned)acc_grid, 128, 0, st>>>(
+          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor);
+    else
+      msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, false><<<(unsigned)acc_grid, 128, 0, st>>>(
+          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor);
+  } else {
+    if (shared)
+      msm_accumulate_kernel<C, true><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
+                                                                       acc_out, heavy, queue, heavy_thr, split, cursor);
+    else
+      msm_accumulate_kernel<C, false><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
+                                                                        acc_out, heavy, queue, heavy_thr, split, cursor);
+  }
   PCD_CUDA(ctx, cudaGetLastError());
   if (split > 1) {
-    msm_fold_parts_kernel<C><<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(acc_out, nbuckets, split, cursor, bkt);
+    if constexpr (SLICED)
+      msm_fold_parts_sliced_kernel<typename MsmSliced<C>::type><<<(unsigned)((nbuckets + 29) / 30), 96, 0, st>>>(
+          acc_out, nbuckets, split, cursor, bkt);
+    else
+      msm_fold_parts_kernel<C><<<(unsigned)((nbuckets + 127) / 128), 128, 0, st>>>(acc_out, nbuckets, split, cursor, bkt);
     PCD_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
   }

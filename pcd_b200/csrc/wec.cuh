@@ -71,8 +71,10 @@ __device__ __forceinline__ u32* wec_slot(u32 s, u32* xb, u32* yb, u32* tb) {
 template <class B, int G>
 __device__ __noinline__ void wec_exec(const u32* __restrict__ prog, int rows, int gl, unsigned gmask, u32* xb, u32* yb,
                                       u32* tb) {
+  u32 wn = __ldg(prog + gl);
   for (int r = 0; r < rows; r++) {
-    const u32 w = __ldg(prog + r * G + gl);
+    const u32 w = wn;
+    if (r + 1 < rows) wn = __ldg(prog + (r + 1) * G + gl);  // the next row's word travels while this row computes
     const u32 op = (w >> 24) & 127u;
     if (op != WEC_NOP) {
       u32* d = wec_slot((w >> 16) & 255u, xb, yb, tb);

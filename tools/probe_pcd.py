@@ -19,7 +19,7 @@ from pcd_b200 import synthetic  # noqa: E402
 NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble"]
 ctx = pcd_b200.Context(0)
 dev = torch.device("cuda:0")
-stream = torch.cuda.Stream(device=dev)
+stream = torch.cuda.Stream(device=dev, priority=-1 if not os.environ.get("PCDGPU_NO_PRIORITIES") else 0)
 torch.cuda.set_stream(stream)
 ctx.set_stream(stream.cuda_stream)
 out = {}
@@ -48,7 +48,10 @@ def one(pairing, log_n, precompute, label, reps=5):
     pk = pcd_b200.ProvingKey(pairing=pairing, **inst["pk"])
     cm = pcd_b200.ConstraintMatrices(pairing, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"])
     t0 = time.perf_counter()
+    if os.environ.get("PCD_MSM_WINDOW"):
+        ctx.set_msm_window(int(os.environ["PCD_MSM_WINDOW"]))
     idx = g.index(pk, cm, precompute=precompute)
+    ctx.set_msm_window(0)
     ctx.sync()
     t_index = 1e3 * (time.perf_counter() - t0)
     z = torch.from_numpy(inst["z"].view(np.int64)).to(dev)
