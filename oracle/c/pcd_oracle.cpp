@@ -1007,6 +1007,32 @@ void orc_ntt(int field, void* data, int log_n, int inverse, int coset, int threa
   if (field == 0) domain_transform<PR4>((FpR4*)data, log_n, inverse, coset, threads);
   else domain_transform<PQ4>((FpQ4*)data, log_n, inverse, coset, threads);
 }
+// The DEFINITION of the forward transform at a few output indices (ark-poly EvaluationDomain::fft: out[i] =
+// sum_j in[j] (g^c omega^i)^j, c = 1 on the coset): Horner evaluation of the input as a polynomial at the point
+// g^c omega_n^i, n multiplications per index, independent of every FFT code path.  Used to check transforms too large
+// to recompute in full (2^24: the benchmarked size).  out: count elements; idx: count output indices < 2^log_n.
+void orc_dft_at(int field, const void* data, int log_n, int coset, const u64* idx, size_t count, void* out, int threads) {
+  auto run = [&](auto tag) {
+    typedef decltype(tag) P;
+    typedef Fp<P> F;
+    const F* a = (const F*)data;
+    F* o = (F*)out;
+    const size_t n = (size_t)1 << log_n;
+    const F omega = omega_for<P>(log_n);
+    const F g = F::generator();
+    parallel_for(count, threads, [&](size_t lo, size_t hi, int) {
+      for (size_t t = lo; t < hi; t++) {
+        u64 e[1] = {idx[t]};
+        F x = omega.pow(e, 1);
+        if (coset) x = x * g;
+        F acc = a[n - 1];
+        for (size_t j = n - 1; j-- > 0;) acc = acc * x + a[j];
+        o[t] = acc;
+      }
+    });
+  };
+  if (field == 0) run(PR4{}); else run(PQ4{});
+}
 // GeneralEvaluationDomain::new(min_size): size chosen (0 if none), with its 7-adic and 2-adic exponents
 size_t orc_domain_size(int field, size_t min_size, int* a, int* b) {
   DomainShape d;

@@ -72,6 +72,18 @@ def ntt(field: int, data: np.ndarray, inverse: bool, coset: bool, threads: int =
     return d
 
 
+def dft_at(field: int, data: np.ndarray, indices, coset: bool = False, threads: int = 0) -> np.ndarray:
+    """out[t] = sum_j data[j] (g^coset omega_n^indices[t])^j: the transform's definition at a few output indices"""
+    d = np.ascontiguousarray(data, dtype=np.uint64).reshape(-1, 5)
+    n = d.shape[0]
+    log_n = n.bit_length() - 1
+    assert 1 << log_n == n
+    idx = np.ascontiguousarray(indices, dtype=np.uint64)
+    out = np.zeros((len(idx), 5), dtype=np.uint64)
+    lib().orc_dft_at(field, _p(d), log_n, int(coset), _p(idx), ctypes.c_size_t(len(idx)), _p(out), threads or hw_threads())
+    return out
+
+
 def domain_size(field: int, min_size: int):
     """GeneralEvaluationDomain::new(min_size) -> (n, a, b) with n = 7^a 2^b, or None."""
     a, b = ctypes.c_int(), ctypes.c_int()

@@ -238,12 +238,16 @@ def make_groth16_instance(ctx: L.Context, pairing: int, log_n: int, seed: int = 
                 pk=pk, expected_logs=expected_logs, p=p)
 
 
-def expected_proof(ctx: L.Context, inst, r: int, s: int) -> np.ndarray:
-    """A || B || C affine limbs computed from the instance's known discrete logs (GPU fixed-base)."""
+def expected_proof(ctx: L.Context, inst, r: int, s: int, mul=None) -> np.ndarray:
+    """A || B || C affine limbs computed from the instance's known discrete logs: three scalar multiplications of the
+    generators.  `mul(curve, generator_limbs, scalar_limbs) -> points` selects who performs them: the tests and the
+    benchmark's gates pass the CPU oracle's double-and-add (an independent implementation); the default is the GPU's
+    fixed-base kernel (no CPU code is imported by this package)."""
     a_log, b_log, c_log = inst["expected_logs"](r, s)
     g1, g2 = L.G1_OF[inst["pairing"]], L.G2_OF[inst["pairing"]]
-    ac = ctx.fixed_base_mul(g1, generator(g1), _limbs_from_ints([a_log, c_log]))
-    b = ctx.fixed_base_mul(g2, generator(g2), _limbs_from_ints([b_log]))
+    mul = mul or ctx.fixed_base_mul
+    ac = mul(g1, generator(g1), _limbs_from_ints([a_log, c_log]))
+    b = mul(g2, generator(g2), _limbs_from_ints([b_log]))
     return np.concatenate([ac[0], b[0], ac[1]])
 
 
@@ -330,9 +334,11 @@ def make_gm17_instance(ctx: L.Context, pairing: int, num_constraints: int, seed:
                 pk=pk, expected_logs=expected_logs, p=p)
 
 
-def expected_gm17_proof(ctx: L.Context, inst, d1: int, d2: int, r: int) -> np.ndarray:
+def expected_gm17_proof(ctx: L.Context, inst, d1: int, d2: int, r: int, mul=None) -> np.ndarray:
+    """as expected_proof, for GM17 (a proof satisfying the two verification equations in the exponent)"""
     a_log, b_log, c_log = inst["expected_logs"](d1, d2, r)
     g1, g2 = L.G1_OF[inst["pairing"]], L.G2_OF[inst["pairing"]]
-    ac = ctx.fixed_base_mul(g1, generator(g1), _limbs_from_ints([a_log, c_log]))
-    b = ctx.fixed_base_mul(g2, generator(g2), _limbs_from_ints([b_log]))
+    mul = mul or ctx.fixed_base_mul
+    ac = mul(g1, generator(g1), _limbs_from_ints([a_log, c_log]))
+    b = mul(g2, generator(g2), _limbs_from_ints([b_log]))
     return np.concatenate([ac[0], b[0], ac[1]])

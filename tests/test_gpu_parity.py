@@ -281,7 +281,7 @@ def test_groth16_mixed_radix_domain(ctx):
     p = inst["p"]
     r, s = pow(3, 99, p), pow(5, 77, p)
     proof = g.create_proof_with_reduction(idx, inst["z"], codec.int_to_limbs(r), codec.int_to_limbs(s))
-    assert np.array_equal(proof.affine_limbs(), synthetic.expected_proof(ctx, inst, r, s))
+    assert np.array_equal(proof.affine_limbs(), synthetic.expected_proof(ctx, inst, r, s, mul=co.fixed_base_mul))
     h = g.witness_map(idx, inst["z"])
     ref_h = co.witness_map(1, inst["A"], inst["B"], inst["C"], m, inst["num_inputs"], inst["z"], threads=16)
     assert np.array_equal(h, ref_h)
@@ -367,7 +367,7 @@ def test_gm17_mixed_radix_sap_domain(ctx):
     p = inst["p"]
     d1, d2, r = pow(3, 71, p), pow(5, 61, p), pow(7, 51, p)
     proof = g.create_proof(idx, inst["z"], codec.int_to_limbs(d1), codec.int_to_limbs(d2), codec.int_to_limbs(r))
-    assert np.array_equal(proof.affine_limbs(), synthetic.expected_gm17_proof(ctx, inst, d1, d2, r))
+    assert np.array_equal(proof.affine_limbs(), synthetic.expected_gm17_proof(ctx, inst, d1, d2, r, mul=co.fixed_base_mul))
     # the SAP witness map alone against the C++ oracle
     full, h = g.witness_map(idx, inst["z"], codec.int_to_limbs(d1), codec.int_to_limbs(d2))
     rfull, rh = co.sap_witness_map(1, inst["A"], inst["B"], inst["C"], m, inst["num_inputs"], inst["num_witness"], inst["z"],
