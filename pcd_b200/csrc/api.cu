@@ -104,7 +104,7 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
   bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
   for (int l = 1; l < pcdgpu_ctx::NLANE && ok; l++)
     ok = cudaStreamCreateWithPriority(&ctx->lane_stream[l], cudaStreamNonBlocking,
-                                      (l == 2 || l == 3) ? prio_mid : prio_least) == cudaSuccess &&
+                                      (l == 2 || l == 3 || l >= 5) ? prio_mid : prio_least) == cudaSuccess &&
          cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming) == cudaSuccess;
   if (!ok) {
     delete ctx;
@@ -608,6 +608,43 @@ void pcdgpu_pk_free(pcdgpu_pk* pk) {
   delete pk;
 }
 
+}  // extern "C"
+// Assembly state of a Groth16 proof in SLOT_MISC (shared by the prover and the multi-GPU assembly calls):
+//   rs (r | s, plain) | extras: 13 plain scalars of the constant pairs | sums1: h, l', T | s g_a, r g1_b, g_a, g1_b
+//   (G1 xyzz) | sum2: g2_b | proof (A || B || C affine)
+struct G16Misc {
+  u32* d_rs;
+  char* extras;
+  void* sums1;
+  void* sum2;
+  char* d_proof;
+  size_t x1, x2, a1, a2;
+};
+static int g16_misc(pcdgpu_ctx* ctx, int pairing, G16Misc* m) {
+  const MsmOps *o1 = msm_ops(pcd_g1_of(pairing)), *o2 = msm_ops(pcd_g2_of(pairing));
+  void* misc;
+  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
+  char* mb = (char*)misc;
+  m->x1 = o1->xyzz_bytes;
+  m->x2 = o2->xyzz_bytes;
+  m->a1 = o1->affine_bytes;
+  m->a2 = o2->affine_bytes;
+  m->d_rs = (u32*)mb;
+  m->extras = mb + 128;  // 13 x 40 B
+  m->sums1 = mb + 1024;
+  m->sum2 = (char*)m->sums1 + 6 * m->x1;
+  m->d_proof = (char*)m->sum2 + m->x2;
+  return 0;
+}
+extern "C" {
+
+// Proofs of at most this many variables compute s g_a + r g1_b as two MORE MSMs (scalars s z and r z over the a and
+// b_g1 queries) instead of a double-scalar multiplication of the finished g_a and g1_b: the two MSMs start with the
+// others, so nothing waits for a 298-doubling chain -- the tiny default-circuit proofs of a PCD step
+// (/root/reference/src/ec_cycle_pcd/data_structures.rs:139-143,343-350) are pure latency.  Above it the extra
+// accumulation work would cost more than the chain, which there hides under the h MSM.
+static const size_t GROTH16_SMALL_NV = (size_t)1 << 13;
+
 int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
                              const void* r, const void* s, void* out_proof) {
   if (!ctx) return PCDGPU_E_ARG;
@@ -618,80 +655,82 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
   InProofGuard in_proof(ctx);
   int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
-  const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
-  size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
-  // misc layout: rs (80 B) | extras: 7 scalars | sums1: h, l', T, g_a, g1_b (G1 xyzz) | sum2: g2_b | proof
-  void* misc;
-  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
-  char* mb = (char*)misc;
-  u32* d_rs = (u32*)mb;
-  char* extras = mb + 128;  // r, 1, 1, s, 1, 1, -(r s)
-  void* sums1 = mb + 512;
-  void* sum2 = (char*)sums1 + 5 * x1;
-  char* d_proof = (char*)sum2 + x2;
-  size_t proof_bytes = 2 * o1->affine_bytes + o2->affine_bytes;
-  char* d_A = d_proof;
-  char* d_B = d_proof + o1->affine_bytes;
-  char* d_C = d_proof + o1->affine_bytes + o2->affine_bytes;
+  G16Misc m;
+  PCD_TRY(g16_misc(ctx, pk->pairing, &m));
+  const size_t x1 = m.x1;
+  u32* d_rs = m.d_rs;
+  char* extras = m.extras;
+  void *sums1 = m.sums1, *sum2 = m.sum2;
+  size_t proof_bytes = 2 * m.a1 + m.a2;
+  char* d_A = m.d_proof;
+  char* d_B = m.d_proof + m.a1;
+  char* d_C = m.d_proof + m.a1 + m.a2;
   memcpy(ctx->pinned, r, 40);
   memcpy((char*)ctx->pinned + 40, s, 40);
   PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
   PCD_TRY(groth16_prepare(ctx, pk->pairing, d_rs, (u32*)extras));
   const char* z = (const char*)d_z;
   size_t nv = pk->num_vars, ni = pk->num_inputs;
-  // Fork: the four MSMs over the assignment only need z and the extra scalars, so they start on lanes
-  // 1-4 while lane 0 runs the witness map and then the h MSM (the G2 MSM, the longest, goes first).
-  // Each lane finishes its own piece of the proof: lane 1 normalises B, lane 2 (a) normalises A, lane 3
-  // (b_g1) waits for lane 2 and runs the double-scalar multiplication T = s g_a + r g1_b -- all of it under
-  // the witness map / h MSM, so that after the join only C = T + l' + h is left.
   const bool fork = ctx->concurrent;
+  const bool small = nv <= GROTH16_SMALL_NV;
+  void *d_sz = nullptr, *d_rz = nullptr;
+  if (small) {  // s z and r z (Montgomery), before the fork: both extra lanes read them
+    PCD_TRY(ctx->scratch(SLOT_SAP_FULL, 2 * nv * 40 + 80, &d_sz));
+    d_rz = (char*)d_sz + nv * 40;
+    PCD_TRY(groth16_scale(ctx, pk->pairing, z + 40, nv - 1, d_rs, d_sz, d_rz));
+  }
+  // Fork: the MSMs over the assignment only need z and the extra scalars, so they start on lanes 1-4 (5, 6) while
+  // lane 0 runs the witness map and then the h MSM (the G2 MSM, the longest, goes first).  Each lane finishes its
+  // own piece of the proof: lane 1 normalises B, lane 2 (a) normalises A, lane 3 (b_g1) waits for lane 2 and runs the
+  // double-scalar multiplication T = s g_a + r g1_b (large proofs) -- all of it under the witness map / h MSM, so that
+  // after the join only C = h + l' + T is left.
+  const int nlanes = small ? pcdgpu_ctx::NLANE : pcdgpu_ctx::NLANE_PROOF;
   if (fork) {
     PCD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-    for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
+    for (int l = 1; l < nlanes; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
   }
   struct Job { const pcdgpu_bases* b; const char* sc; size_t n; const char* ex; size_t nex; void* out; };
-  Job jobs[4] = {{pk->b_g2_query, z + 40, nv - 1, extras + 3 * 40, 3, sum2},
-                 {pk->a_query, z + 40, nv - 1, extras, 3, (char*)sums1 + 3 * x1},
-                 {pk->b_g1_query, z + 40, nv - 1, extras + 3 * 40, 3, (char*)sums1 + 4 * x1},
-                 {pk->l_query, z + 40 * ni, nv - ni, extras + 6 * 40, 1, (char*)sums1 + 1 * x1}};
+  Job jobs[6] = {{pk->b_g2_query, z + 40, nv - 1, extras + 3 * 40, 3, sum2},
+                 {pk->a_query, z + 40, nv - 1, extras, 3, (char*)sums1 + 4 * x1},
+                 {pk->b_g1_query, z + 40, nv - 1, extras + 3 * 40, 3, (char*)sums1 + 5 * x1},
+                 {pk->l_query, z + 40 * ni, nv - ni, extras + 6 * 40, 1, (char*)sums1 + 1 * x1},
+                 {pk->a_query, (const char*)d_sz, nv - 1, extras + 7 * 40, 3, (char*)sums1 + 2 * x1},
+                 {pk->b_g1_query, (const char*)d_rz, nv - 1, extras + 10 * 40, 3, (char*)sums1 + 3 * x1}};
   int rc = 0;
-  for (int j = 0; j < 4 && rc == 0; j++) {
+  for (int j = 0; j < nlanes - 1 && rc == 0; j++) {
     ctx->lane = fork ? j + 1 : 0;
     rc = bases_msm(ctx, jobs[j].b, 0, jobs[j].sc, 1, jobs[j].n, jobs[j].ex, jobs[j].nex, jobs[j].out);
     if (rc == 0 && j == 0) rc = point_to_affine(ctx, g2, sum2, 0, d_B);
-    if (rc == 0 && j == 1) {
-      rc = point_to_affine(ctx, g1, sums1, 3, d_A);
-      // lane 3's Straus needs g_a: an event of its own, recorded before lane 2's tail would also do, but the
-      // normalisation is short
-    }
-    if (rc == 0 && j == 2) {
+    if (rc == 0 && j == 1) rc = point_to_affine(ctx, g1, sums1, 4, d_A);
+    if (rc == 0 && j == 2 && !small) {
+      // lane 3's double-scalar multiplication needs g_a from lane 2
       if (fork && cudaStreamWaitEvent(ctx->lane_stream[3], ctx->ev_join[2], 0) != cudaSuccess) rc = PCDGPU_E_CUDA;
       if (rc == 0) rc = groth16_straus(ctx, pk->pairing, d_rs, sums1);
     }
     if (fork && rc == 0 && cudaEventRecord(ctx->ev_join[j + 1], ctx->lane_stream[j + 1]) != cudaSuccess) rc = PCDGPU_E_CUDA;
   }
   ctx->lane = 0;
-  if (rc) {
-    ctx->drain_lanes();
-    return rc;
-  }
-  void* d_h;
-  rc = witness_map_dev(ctx, r1cs, d_z, &d_h);
+  void* d_h = nullptr;
+  if (rc == 0) rc = witness_map_dev(ctx, r1cs, d_z, &d_h);
   // h: n coefficients vs n - 1 query points: truncated to the shorter
   if (rc == 0) rc = bases_msm(ctx, pk->h_query, 0, d_h, 1, r1cs->n, nullptr, 0, (char*)sums1 + 0 * x1);
-  if (rc) {
-    ctx->drain_lanes();
-    return rc;
+  if (rc == 0 && fork)
+    for (int l = 1; l < nlanes && rc == 0; l++)
+      if (cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0) != cudaSuccess) rc = PCDGPU_E_CUDA;
+  if (rc == 0) rc = groth16_finish(ctx, pk->pairing, sums1, d_C, small ? 4 : 3);
+  if (rc == 0 && cudaMemcpyAsync(out_proof, m.d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = PCDGPU_E_CUDA;
+  // every exit, error or not, drains the lanes and the stream: the next call reuses the pinned staging buffer and
+  // the scratch the lanes are working in
+  if (rc) ctx->drain_lanes();
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc == 0 && e != cudaSuccess) {
+    ctx->set_error("cudaStreamSynchronize: %s", cudaGetErrorString(e));
+    rc = PCDGPU_E_CUDA;
   }
-  if (fork)
-    for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
-  PCD_TRY(groth16_finish(ctx, pk->pairing, sums1, d_C));
-  PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));
-  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
-  return 0;
+  return rc;
 }
 
-// layout of the assembly state in SLOT_MISC (shared by the two calls below): rs | sums1 (h, l', T, g_a, g1_b) | sum2 | proof
 int pcdgpu_groth16_assemble_begin_dev(pcdgpu_ctx* ctx, int pairing, const void* r, const void* s, int world,
                                       const void* d_partials_ab, const void* d_partials_g2) {
   if (!ctx) return PCDGPU_E_ARG;
@@ -699,23 +738,16 @@ int pcdgpu_groth16_assemble_begin_dev(pcdgpu_ctx* ctx, int pairing, const void* 
   CHECK_ARG(ctx, r && s && d_partials_ab && d_partials_g2 && world >= 1, "bad argument");
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
   int g1 = g1_of(pairing), g2 = g2_of(pairing);
-  const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
-  size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
-  void* misc;
-  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
-  char* mb = (char*)misc;
-  u32* d_rs = (u32*)mb;
-  void* sums1 = mb + 512;
-  void* sum2 = (char*)sums1 + 5 * x1;
-  char* d_proof = (char*)sum2 + x2;
+  G16Misc m;
+  PCD_TRY(g16_misc(ctx, pairing, &m));
   memcpy(ctx->pinned, r, 40);
   memcpy((char*)ctx->pinned + 40, s, 40);
-  PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
-  // g_a, g1_b -> sums1[3], sums1[4]; g2_b -> sum2
-  PCD_TRY(groth16_sum_partials(ctx, pairing, d_partials_ab, d_partials_g2, world, 2, 1, (char*)sums1 + 3 * x1, sum2));
-  PCD_TRY(point_to_affine(ctx, g1, sums1, 3, d_proof));
-  PCD_TRY(point_to_affine(ctx, g2, sum2, 0, d_proof + o1->affine_bytes));
-  return groth16_straus(ctx, pairing, d_rs, sums1);
+  PCD_CUDA(ctx, cudaMemcpyAsync(m.d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
+  // g_a, g1_b -> sums1[4], sums1[5]; g2_b -> sum2
+  PCD_TRY(groth16_sum_partials(ctx, pairing, d_partials_ab, d_partials_g2, world, 2, 1, (char*)m.sums1 + 4 * m.x1, m.sum2));
+  PCD_TRY(point_to_affine(ctx, g1, m.sums1, 4, m.d_proof));
+  PCD_TRY(point_to_affine(ctx, g2, m.sum2, 0, m.d_proof + m.a1));
+  return groth16_straus(ctx, pairing, m.d_rs, m.sums1);
 }
 
 int pcdgpu_groth16_assemble_finish_dev(pcdgpu_ctx* ctx, int pairing, int world, const void* d_partials_hl,
@@ -724,20 +756,12 @@ int pcdgpu_groth16_assemble_finish_dev(pcdgpu_ctx* ctx, int pairing, int world, 
   CHECK_ARG(ctx, pairing == PCDGPU_MNT4_298 || pairing == PCDGPU_MNT6_298, "unknown pairing id");
   CHECK_ARG(ctx, d_partials_hl && out_proof && world >= 1, "bad argument");
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
-  int g1 = g1_of(pairing), g2 = g2_of(pairing);
-  const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
-  size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;
-  void* misc;
-  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &misc));
-  char* mb = (char*)misc;
-  void* sums1 = mb + 512;
-  void* sum2 = (char*)sums1 + 5 * x1;
-  char* d_proof = (char*)sum2 + x2;
-  size_t proof_bytes = 2 * o1->affine_bytes + o2->affine_bytes;
+  G16Misc m;
+  PCD_TRY(g16_misc(ctx, pairing, &m));
   // h, l' -> sums1[0], sums1[1]
-  PCD_TRY(groth16_sum_partials(ctx, pairing, d_partials_hl, nullptr, world, 2, 0, sums1, nullptr));
-  PCD_TRY(groth16_finish(ctx, pairing, sums1, d_proof + o1->affine_bytes + o2->affine_bytes));
-  PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_TRY(groth16_sum_partials(ctx, pairing, d_partials_hl, nullptr, world, 2, 0, m.sums1, nullptr));
+  PCD_TRY(groth16_finish(ctx, pairing, m.sums1, m.d_proof + m.a1 + m.a2));
+  PCD_CUDA(ctx, cudaMemcpyAsync(out_proof, m.d_proof, 2 * m.a1 + m.a2, cudaMemcpyDeviceToHost, ctx->stream));
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   return 0;
 }

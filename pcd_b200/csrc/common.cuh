@@ -68,7 +68,8 @@ struct pcdgpu_ctx {
   // Lanes: the five MSMs of a proof are independent, so each runs on its own stream with its own
   // scratch and their latency-bound phases (bucket reduction, window combination) overlap the
   // other lanes' accumulation.  Lane 0 is the context's (or the caller's) stream.
-  static const int NLANE = 5;
+  static const int NLANE = 7;        // lanes 5, 6: the two extra MSMs of a small Groth16 proof (see pcdgpu_groth16_prove_dev)
+  static const int NLANE_PROOF = 5;  // lanes every prover forks
   static const int SLOTS_PER_LANE = 24;
   int lane = 0;
   bool concurrent = true;

@@ -349,7 +349,7 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
     const char* f = (const char*)d_full;
     if (fork) {
       PCD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
-      for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
+      for (int l = 1; l < pcdgpu_ctx::NLANE_PROOF; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
     }
     struct Job { const pcdgpu_bases* b; const char* sc; size_t n; const char* ex; size_t nex; void* out; };
     Job jobs[4] = {{pk->b_query, f + 40, nsap - 1, extras, 2, sum2},
@@ -385,7 +385,7 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
     return rc;
   }
   if (fork)
-    for (int l = 1; l < pcdgpu_ctx::NLANE; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
+    for (int l = 1; l < pcdgpu_ctx::NLANE_PROOF; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0));
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
   PCD_TRY(o1->sum_points(ctx, sums1, 0, 1, 3, nullptr, 0, d_C));  // C = G' + C1' + [r] C2'
   ctx->prof_end(ps);

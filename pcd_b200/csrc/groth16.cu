@@ -146,7 +146,8 @@ __global__ void groth16_prepare_kernel(const u32* __restrict__ rs, u32* __restri
     r.l[i] = rs[i];
     s.l[i] = rs[10 + i];
   }
-  Fr nrs = (r.to_mont() * s.to_mont()).neg().from_mont();
+  Fr rsm = r.to_mont() * s.to_mont();
+  Fr rs_ = rsm.from_mont(), nrs = rsm.neg().from_mont();
 #pragma unroll
   for (int i = 0; i < 10; i++) {
     u32 one = i == 0 ? 1u : 0u;
@@ -157,7 +158,35 @@ __global__ void groth16_prepare_kernel(const u32* __restrict__ rs, u32* __restri
     extras[4 * 10 + i] = one;
     extras[5 * 10 + i] = one;
     extras[6 * 10 + i] = nrs.l[i];
+    // small proofs: s g_a and r g1_b as MSMs of their own (scalars s z, r z): constant pairs (delta, a[0] / b[0], alpha / beta)
+    extras[7 * 10 + i] = rs_.l[i];
+    extras[8 * 10 + i] = s.l[i];
+    extras[9 * 10 + i] = s.l[i];
+    extras[10 * 10 + i] = rs_.l[i];
+    extras[11 * 10 + i] = r.l[i];
+    extras[12 * 10 + i] = r.l[i];
   }
+}
+// sz[i] = s z[i], rz[i] = r z[i] (Montgomery in, Montgomery out); rs = r | s plain
+template <class F>
+__global__ void __launch_bounds__(128) groth16_scale_kernel(const u32* __restrict__ z, size_t n, const u32* __restrict__ rs,
+                                                            u32* __restrict__ sz, u32* __restrict__ rz) {
+  size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  F r = ld10<F>(rs, 0).to_mont(), s = ld10<F>(rs, 1).to_mont();
+  F v = ld10<F>(z, i);
+  st10<F>(sz, i, s * v);
+  st10<F>(rz, i, r * v);
+}
+int groth16_scale(pcdgpu_ctx* ctx, int pairing, const void* d_z, size_t n, const u32* d_rs, void* d_sz, void* d_rz) {
+  if (n == 0) return 0;
+  ctx->launches += 1;
+  if (pairing == PCDGPU_MNT4_298)
+    groth16_scale_kernel<FpR4><<<(unsigned)((n + 127) / 128), 128, 0, ctx->cur()>>>((const u32*)d_z, n, d_rs, (u32*)d_sz, (u32*)d_rz);
+  else
+    groth16_scale_kernel<FpQ4><<<(unsigned)((n + 127) / 128), 128, 0, ctx->cur()>>>((const u32*)d_z, n, d_rs, (u32*)d_sz, (u32*)d_rz);
+  PCD_CUDA(ctx, cudaGetLastError());
+  return 0;
 }
 
 int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras) {
@@ -174,7 +203,7 @@ int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras
 //   groth16_finish   C = T + l' + h
 // All of it runs on the lane-cooperative group law (wec.cuh, through the per-curve MsmOps entries): round 1's
 // single-thread versions cost 3.5 - 4 ms (Straus), 0.33 - 0.41 ms (each normalisation, Fermat inversion) per proof.
-// sums1 = {h_acc, l', T, g_a, g1_b} (G1 xyzz).
+// sums1 = {h_acc, l', T (or s g_a), r g1_b (small proofs only), g_a, g1_b} (G1 xyzz).
 // multi-GPU prover: out1[k] = sum over ranks of partials1[rank * n1 + k], k < n1 (G1); out2 = sum of partials2 (G2, n2 = 0 / 1)
 int groth16_sum_partials(pcdgpu_ctx* ctx, int pairing, const void* p1, const void* p2, int world, int n1, int n2,
                          void* out1, void* out2) {
@@ -186,8 +215,8 @@ int groth16_sum_partials(pcdgpu_ctx* ctx, int pairing, const void* p1, const voi
 
 int groth16_straus(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, void* sums1) {
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
-  // d_rs = r | s (plain): T = [r] g1_b + [s] g_a -> pairs (sums1[4], r), (sums1[3], s); T -> sums1[2]
-  int rc = msm_ops(pcd_g1_of(pairing))->multi_mul(ctx, sums1, 4, 3, d_rs, 2, sums1, 2);
+  // d_rs = r | s (plain): T = [r] g1_b + [s] g_a -> pairs (sums1[5], r), (sums1[4], s); T -> sums1[2]
+  int rc = msm_ops(pcd_g1_of(pairing))->multi_mul(ctx, sums1, 5, 4, d_rs, 2, sums1, 2);
   ctx->prof_end(ps);
   return rc;
 }
@@ -197,9 +226,10 @@ int point_to_affine(pcdgpu_ctx* ctx, int curve, const void* src, size_t idx, voi
   ctx->prof_end(ps);
   return rc;
 }
-int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_c) {
+int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_c, int nterms) {
   int ps = ctx->prof_begin(PROF_ASSEMBLE, 1.0);
-  int rc = msm_ops(pcd_g1_of(pairing))->sum_points(ctx, sums1, 0, 1, 3, nullptr, 0, d_out_c);  // C = h + l' + T
+  // C = h + l' + T (nterms = 3), or h + l' + s g_a + r g1_b with the last two from MSMs of their own (nterms = 4)
+  int rc = msm_ops(pcd_g1_of(pairing))->sum_points(ctx, sums1, 0, 1, nterms, nullptr, 0, d_out_c);
   ctx->prof_end(ps);
   return rc;
 }

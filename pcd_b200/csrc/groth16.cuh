@@ -79,13 +79,14 @@ int bases_msm(pcdgpu_ctx* ctx, const pcdgpu_bases* b, size_t offset, const void*
 int witness_map_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, const void* d_z, void** d_h);
 int qap_vector_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, int which, const void* d_z, void* d_out);
 int qap_combine_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, void* d_a, const void* d_b, const void* d_c);
-// extras <- {r, 1, 1, s, 1, 1, -(r s) mod p} as plain integers (the scalars of the constant pairs)
+// extras <- {r, 1, 1, s, 1, 1, -(r s) mod p, rs, s, s, rs, r, r} as plain integers (the scalars of the constant pairs)
 int groth16_prepare(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, u32* d_extras);
-// the proof's tail, on the context's current lane (ctx->cur()): sums1 = {h_acc, l_acc - (r s) delta, T, g_a, g1_b}
+// the proof's tail, on the context's current lane (ctx->cur()): sums1 = {h_acc, l_acc - (r s) delta, T | s g_a, r g1_b, g_a, g1_b}
 int groth16_sum_partials(pcdgpu_ctx* ctx, int pairing, const void* p1, const void* p2, int world, int n1, int n2,
                          void* out1, void* out2);
 int groth16_straus(pcdgpu_ctx* ctx, int pairing, const u32* d_rs, void* sums1);      // T = s g_a + r g1_b
 int point_to_affine(pcdgpu_ctx* ctx, int curve, const void* src_xyzz, size_t idx, void* dst_affine);
-int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_c);  // C = T + l' + h, affine
+int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_c, int nterms = 3);  // C = h + l' + T (+ ...), affine
+int groth16_scale(pcdgpu_ctx* ctx, int pairing, const void* d_z, size_t n, const u32* d_rs, void* d_sz, void* d_rz);
 int groth16_serialize(pcdgpu_ctx* ctx, int pairing, const void* d_proof, unsigned char* d_out);
 int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double* ms_out);
