@@ -225,6 +225,36 @@ int pcdgpu_groth16_assemble_begin_dev(pcdgpu_ctx* ctx, int pairing, const void* 
 int pcdgpu_groth16_assemble_finish_dev(pcdgpu_ctx* ctx, int pairing, int world, const void* d_partials_hl,
                                        void* out_proof);
 
+/* ---- multi-GPU inside the library ------------------------------------------------------------
+ * One proof / one MSM over the GPUs of a box, one process (or host thread) and one context per GPU, driven through the
+ * C ABI alone: MSM point ranges are split per GPU and the per-GPU partial sums are combined with ONE gather of
+ * projective points per exchange (NCCL all-gather over NVLink; libnccl.so.2 is resolved at run time, single-GPU users
+ * never load it).
+ *   rank 0: pcdgpu_comm_unique_id(id), ships the PCDGPU_COMM_ID_BYTES bytes to the other ranks by any means;
+ *   every rank: pcdgpu_comm_init(ctx, id, rank, world)                         (collective; world 1 needs no id)
+ *               pcdgpu_pk_upload_sharded(... the WHOLE host key ...)           (uploads this rank's slice of each query)
+ *               pcdgpu_groth16_prove_sharded(ctx, pk, r1cs, z, r, s, out)      (collective; same inputs on every rank;
+ *                                                                               every rank receives the proof)
+ * The proof is bit-identical to pcdgpu_groth16_prove for any number of ranks (affine points are canonical). */
+#define PCDGPU_COMM_ID_BYTES 128
+int pcdgpu_comm_unique_id(void* out_id);
+int pcdgpu_comm_init(pcdgpu_ctx* ctx, const void* id, int rank, int world);
+int pcdgpu_comm_info(const pcdgpu_ctx* ctx, int* rank, int* world);
+void pcdgpu_comm_destroy(pcdgpu_ctx* ctx);
+int pcdgpu_pk_upload_sharded(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_inputs, size_t h_len,
+                             const void* alpha_g1, const void* beta_g1, const void* delta_g1, const void* beta_g2,
+                             const void* delta_g2, const void* a_query, const void* b_g1_query, const void* b_g2_query,
+                             const void* h_query, const void* l_query, int precompute, pcdgpu_pk** out);
+int pcdgpu_groth16_prove_sharded(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* z,
+                                 const void* r, const void* s, void* out_proof);
+int pcdgpu_groth16_prove_sharded_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
+                                     const void* r, const void* s, void* out_proof);
+/* one MSM sharded by point range: `slice` = this rank's points (pcdgpu_bases_upload of the slice), scalars = this
+ * rank's scalars; every rank receives the affine sum.  Collective. */
+int pcdgpu_msm_bases_sharded(pcdgpu_ctx* ctx, const pcdgpu_bases* slice, const void* scalars, size_t n, void* out_affine);
+int pcdgpu_msm_bases_sharded_dev(pcdgpu_ctx* ctx, const pcdgpu_bases* slice, const void* d_scalars, int scalars_mont,
+                                 size_t n, void* d_out_affine);
+
 /* ark-serialize CanonicalSerialize of the proof (compressed points: x with flag bits 7 = "y is the
  * larger root", 6 = infinity on the last byte): 152 B (MNT4) / 190 B (MNT6).  out: >= 190 bytes. */
 int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affine, uint8_t* out, size_t* out_len);

@@ -122,6 +122,7 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
 
 void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx) {
   if (!ctx) return;
+  pcdgpu_comm_destroy(ctx);
   cudaSetDevice(ctx->device);
   cudaDeviceSynchronize();
   for (int i = 0; i < pcdgpu_ctx::NSLOT; i++)
@@ -540,10 +541,16 @@ int pcdgpu_qap_combine_dev(pcdgpu_ctx* ctx, const pcdgpu_r1cs* r, void* d_a, con
 }
 
 // ---- Groth16 ------------------------------------------------------------------------------------------
-int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_inputs, size_t h_len,
+}  // extern "C"
+static void shard_of(size_t n, int world, int rank, size_t* lo, size_t* hi) {  // contiguous, balanced (pcd_b200/sharding.py)
+  size_t base = n / world, extra = n % world;
+  *lo = rank * base + ((size_t)rank < extra ? (size_t)rank : extra);
+  *hi = *lo + base + ((size_t)rank < extra ? 1 : 0);
+}
+static int pk_upload_impl(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_inputs, size_t h_len,
                      const void* alpha_g1, const void* beta_g1, const void* delta_g1, const void* beta_g2,
                      const void* delta_g2, const void* a_query, const void* b_g1_query, const void* b_g2_query,
-                     const void* h_query, const void* l_query, int precompute, pcdgpu_pk** out) {
+                     const void* h_query, const void* l_query, int precompute, int rank, int world, pcdgpu_pk** out) {
   if (!ctx) return PCDGPU_E_ARG;
   CHECK_ARG(ctx, pairing == PCDGPU_MNT4_298 || pairing == PCDGPU_MNT6_298, "unknown pairing id");
   CHECK_ARG(ctx, out && alpha_g1 && beta_g1 && delta_g1 && beta_g2 && delta_g2 && a_query && b_g1_query && b_g2_query,
@@ -560,6 +567,12 @@ int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_i
   pk->num_vars = num_vars;
   pk->num_inputs = num_inputs;
   pk->h_len = h_len;
+  pk->shard_rank = rank;
+  pk->shard_world = world;
+  shard_of(num_vars - 1, world, rank, &pk->v_lo, &pk->v_hi);
+  shard_of(h_len, world, rank, &pk->h_lo, &pk->h_hi);
+  shard_of(num_vars - num_inputs, world, rank, &pk->l_lo, &pk->l_hi);
+  const int nex3 = rank == 0 ? 3 : 0, nex1 = rank == 0 ? 1 : 0;  // the constant points ride with rank 0
   int rc = 0;
   // Element 0 of the a/b queries belongs to the constant 1 and ark-groth16 adds it, the vk elements
   // and r*delta / s*delta outside its MSMs (prover.rs).  Here those pairs ride inside the MSMs: every
@@ -582,13 +595,13 @@ int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_i
   const void* eb1[3] = {delta_g1, b_g1_query, beta_g1};
   const void* eb2[3] = {delta_g2, b_g2_query, beta_g2};
   const void* el[1] = {delta_g1};
-  rc = rc ? rc : upload_ext(g1, a_query, 1, num_vars - 1, ea, 3, &pk->a_query);
-  rc = rc ? rc : upload_ext(g1, b_g1_query, 1, num_vars - 1, eb1, 3, &pk->b_g1_query);
-  rc = rc ? rc : upload_ext(g2, b_g2_query, 1, num_vars - 1, eb2, 3, &pk->b_g2_query);
-  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, h_query, h_len, precompute, &pk->h_query);
-  rc = rc ? rc : upload_ext(g1, l_query, 0, num_vars - num_inputs, el, 1, &pk->l_query);
+  rc = rc ? rc : upload_ext(g1, a_query, 1 + pk->v_lo, pk->v_hi - pk->v_lo, ea, nex3, &pk->a_query);
+  rc = rc ? rc : upload_ext(g1, b_g1_query, 1 + pk->v_lo, pk->v_hi - pk->v_lo, eb1, nex3, &pk->b_g1_query);
+  rc = rc ? rc : upload_ext(g2, b_g2_query, 1 + pk->v_lo, pk->v_hi - pk->v_lo, eb2, nex3, &pk->b_g2_query);
+  rc = rc ? rc : pcdgpu_bases_upload(ctx, g1, h_query ? (const char*)h_query + pk->h_lo * s1 : nullptr,
+                                     pk->h_hi - pk->h_lo, precompute, &pk->h_query);
+  rc = rc ? rc : upload_ext(g1, l_query, pk->l_lo, pk->l_hi - pk->l_lo, el, nex1, &pk->l_query);
   ctx->key_upload = false;
-  (void)s1;
   (void)s2;
   if (rc) {
     pcdgpu_pk_free(pk);
@@ -596,6 +609,26 @@ int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_i
   }
   *out = pk;
   return 0;
+}
+
+extern "C" {
+int pcdgpu_pk_upload(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_inputs, size_t h_len,
+                     const void* alpha_g1, const void* beta_g1, const void* delta_g1, const void* beta_g2,
+                     const void* delta_g2, const void* a_query, const void* b_g1_query, const void* b_g2_query,
+                     const void* h_query, const void* l_query, int precompute, pcdgpu_pk** out) {
+  return pk_upload_impl(ctx, pairing, num_vars, num_inputs, h_len, alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2, a_query,
+                        b_g1_query, b_g2_query, h_query, l_query, precompute, 0, 1, out);
+}
+int pcdgpu_pk_upload_sharded(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t num_inputs, size_t h_len,
+                             const void* alpha_g1, const void* beta_g1, const void* delta_g1, const void* beta_g2,
+                             const void* delta_g2, const void* a_query, const void* b_g1_query, const void* b_g2_query,
+                             const void* h_query, const void* l_query, int precompute, pcdgpu_pk** out) {
+  if (!ctx) return PCDGPU_E_ARG;
+  ctx->in_proof = true;  // window rule of MSMs that run side by side, as in the single-GPU prover
+  int rc = pk_upload_impl(ctx, pairing, num_vars, num_inputs, h_len, alpha_g1, beta_g1, delta_g1, beta_g2, delta_g2, a_query,
+                          b_g1_query, b_g2_query, h_query, l_query, precompute, ctx->comm_rank, ctx->comm_world, out);
+  ctx->in_proof = false;
+  return rc;
 }
 
 void pcdgpu_pk_free(pcdgpu_pk* pk) {
@@ -652,6 +685,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   CHECK_ARG(ctx, pk->pairing == r1cs->pairing, "key and constraint system are over different pairings");
   CHECK_ARG(ctx, pk->num_vars == r1cs->num_inputs + r1cs->num_witness && pk->num_inputs == r1cs->num_inputs,
             "key and constraint system disagree on the variable counts");
+  CHECK_ARG(ctx, pk->shard_world == 1, "sharded key: use pcdgpu_groth16_prove_sharded");
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
   InProofGuard in_proof(ctx);
   int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
@@ -729,6 +763,146 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
     rc = PCDGPU_E_CUDA;
   }
   return rc;
+}
+
+// One proof over the GPUs of a communicator (pcdgpu_comm_init): every rank holds a slice of each query
+// (pcdgpu_pk_upload_sharded), computes the partial sums of the five MSMs over its slice -- the witness map is
+// recomputed on every rank (0.2 - 1 ms; cheaper than moving h) -- and two all-gathers of xyzz points move them:
+// (a, b_g1 | b_g2) as soon as those three MSMs are done, on the b_g1 lane, so that A, B and s g_a + r g1_b are ready
+// before the h MSM ends, then (h, l').  Every rank assembles and returns the proof (bit-identical on all ranks and to
+// the single-GPU proof: affine points are canonical).
+int pcdgpu_groth16_prove_sharded_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
+                                     const void* r, const void* s, void* out_proof) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pk && r1cs && d_z && r && s && out_proof, "null pointer");
+  CHECK_ARG(ctx, pk->pairing == r1cs->pairing, "key and constraint system are over different pairings");
+  CHECK_ARG(ctx, pk->num_vars == r1cs->num_inputs + r1cs->num_witness && pk->num_inputs == r1cs->num_inputs,
+            "key and constraint system disagree on the variable counts");
+  CHECK_ARG(ctx, pk->shard_world == ctx->comm_world && pk->shard_rank == ctx->comm_rank,
+            "the key was sharded for another communicator");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  InProofGuard in_proof(ctx);
+  const int world = ctx->comm_world;
+  int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
+  G16Misc m;
+  PCD_TRY(g16_misc(ctx, pk->pairing, &m));
+  const size_t x1 = m.x1, x2 = m.x2;
+  // comm layout: mine_ab (2 x1) | mine_g2 (x2) | mine_hl (2 x1) | all_ab (world 2 x1) | all_g2 (world x2) | all_hl (world 2 x1)
+  void* comm;
+  PCD_TRY(ctx->scratch(SLOT_COMM, (size_t)(world + 1) * (4 * x1 + x2) + 256, &comm));
+  char* mine_ab = (char*)comm;
+  char* mine_g2 = mine_ab + 2 * x1;
+  char* mine_hl = mine_g2 + x2;
+  char* all_ab = mine_hl + 2 * x1;
+  char* all_g2 = all_ab + (size_t)world * 2 * x1;
+  char* all_hl = all_g2 + (size_t)world * x2;
+  memcpy(ctx->pinned, r, 40);
+  memcpy((char*)ctx->pinned + 40, s, 40);
+  PCD_CUDA(ctx, cudaMemcpyAsync(m.d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(groth16_prepare(ctx, pk->pairing, m.d_rs, (u32*)m.extras));
+  const char* z = (const char*)d_z;
+  const size_t ni = pk->num_inputs;
+  const bool fork = ctx->concurrent;
+  const bool r0 = pk->shard_rank == 0;
+  if (fork) {
+    PCD_CUDA(ctx, cudaEventRecord(ctx->ev_fork, ctx->stream));
+    for (int l = 1; l < pcdgpu_ctx::NLANE_PROOF; l++) PCD_CUDA(ctx, cudaStreamWaitEvent(ctx->lane_stream[l], ctx->ev_fork, 0));
+  }
+  struct Job { const pcdgpu_bases* b; const char* sc; size_t n; const char* ex; size_t nex; void* out; };
+  const size_t nvs = pk->v_hi - pk->v_lo;
+  Job jobs[4] = {{pk->b_g2_query, z + 40 * (1 + pk->v_lo), nvs, m.extras + 3 * 40, r0 ? 3u : 0u, mine_g2},
+                 {pk->a_query, z + 40 * (1 + pk->v_lo), nvs, m.extras, r0 ? 3u : 0u, mine_ab},
+                 {pk->b_g1_query, z + 40 * (1 + pk->v_lo), nvs, m.extras + 3 * 40, r0 ? 3u : 0u, mine_ab + x1},
+                 {pk->l_query, z + 40 * (ni + pk->l_lo), pk->l_hi - pk->l_lo, m.extras + 6 * 40, r0 ? 1u : 0u, mine_hl + x1}};
+  int rc = 0;
+  for (int j = 0; j < 4 && rc == 0; j++) {
+    ctx->lane = fork ? j + 1 : 0;
+    rc = bases_msm(ctx, jobs[j].b, 0, jobs[j].sc, 1, jobs[j].n, jobs[j].ex, jobs[j].nex, jobs[j].out);
+    if (rc == 0 && j == 2) {
+      // first exchange, on this lane: needs the b_g2 and a partial sums of lanes 1 and 2 as well
+      if (fork && (cudaStreamWaitEvent(ctx->lane_stream[3], ctx->ev_join[1], 0) != cudaSuccess ||
+                   cudaStreamWaitEvent(ctx->lane_stream[3], ctx->ev_join[2], 0) != cudaSuccess))
+        rc = PCDGPU_E_CUDA;
+      if (rc == 0) rc = comm_group(ctx, true);
+      if (rc == 0) rc = comm_allgather(ctx, mine_ab, all_ab, 2 * x1, ctx->cur());
+      if (rc == 0) rc = comm_allgather(ctx, mine_g2, all_g2, x2, ctx->cur());
+      if (rc == 0) rc = comm_group(ctx, false);
+      // g_a, g1_b -> sums1[4], sums1[5]; g2_b -> sum2; A, B; T = s g_a + r g1_b
+      if (rc == 0) rc = groth16_sum_partials(ctx, pk->pairing, all_ab, all_g2, world, 2, 1, (char*)m.sums1 + 4 * x1, m.sum2);
+      if (rc == 0) rc = point_to_affine(ctx, g1, m.sums1, 4, m.d_proof);
+      if (rc == 0) rc = point_to_affine(ctx, g2, m.sum2, 0, m.d_proof + m.a1);
+      if (rc == 0) rc = groth16_straus(ctx, pk->pairing, m.d_rs, m.sums1);
+    }
+    if (fork && rc == 0 && cudaEventRecord(ctx->ev_join[j + 1], ctx->lane_stream[j + 1]) != cudaSuccess) rc = PCDGPU_E_CUDA;
+  }
+  ctx->lane = 0;
+  void* d_h = nullptr;
+  if (rc == 0) rc = witness_map_dev(ctx, r1cs, d_z, &d_h);
+  if (rc == 0) {
+    size_t hn = pk->h_hi - pk->h_lo;
+    if (pk->h_lo >= r1cs->n) hn = 0;
+    else if (pk->h_lo + hn > r1cs->n) hn = r1cs->n - pk->h_lo;
+    rc = bases_msm(ctx, pk->h_query, 0, (const char*)d_h + 40 * pk->h_lo, 1, hn, nullptr, 0, mine_hl);
+  }
+  if (rc == 0 && fork)
+    for (int l = 1; l < pcdgpu_ctx::NLANE_PROOF && rc == 0; l++)
+      if (cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0) != cudaSuccess) rc = PCDGPU_E_CUDA;
+  if (rc == 0) rc = comm_allgather(ctx, mine_hl, all_hl, 2 * x1, ctx->stream);
+  if (rc == 0) rc = groth16_sum_partials(ctx, pk->pairing, all_hl, nullptr, world, 2, 0, m.sums1, nullptr);
+  if (rc == 0) rc = groth16_finish(ctx, pk->pairing, m.sums1, m.d_proof + m.a1 + m.a2, 3);
+  if (rc == 0 && cudaMemcpyAsync(out_proof, m.d_proof, 2 * m.a1 + m.a2, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+    rc = PCDGPU_E_CUDA;
+  if (rc) ctx->drain_lanes();
+  cudaError_t e = cudaStreamSynchronize(ctx->stream);
+  if (rc == 0 && e != cudaSuccess) {
+    ctx->set_error("cudaStreamSynchronize: %s", cudaGetErrorString(e));
+    rc = PCDGPU_E_CUDA;
+  }
+  return rc;
+}
+
+int pcdgpu_groth16_prove_sharded(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* z, const void* r,
+                                 const void* s, void* out_proof) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pk && r1cs && z && r && s && out_proof, "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  size_t nv = r1cs->num_inputs + r1cs->num_witness;
+  void* dz;
+  PCD_TRY(ctx->scratch(SLOT_Z, nv * 40, &dz));
+  PCD_CUDA(ctx, cudaMemcpyAsync(dz, z, nv * 40, cudaMemcpyHostToDevice, ctx->stream));
+  return pcdgpu_groth16_prove_sharded_dev(ctx, pk, r1cs, dz, r, s, out_proof);
+}
+
+// One MSM sharded by point range: every rank passes ITS slice of the bases (resident) and of the scalars; the xyzz
+// partial sums are all-gathered (one exchange of 160 - 480 B per rank) and every rank adds them and normalises.
+int pcdgpu_msm_bases_sharded_dev(pcdgpu_ctx* ctx, const pcdgpu_bases* slice, const void* d_scalars, int scalars_mont,
+                                 size_t n, void* d_out_affine) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, slice && d_out_affine && (n == 0 || d_scalars), "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const MsmOps* ops = msm_ops(slice->curve);
+  const int world = ctx->comm_world;
+  void* comm;
+  PCD_TRY(ctx->scratch(SLOT_COMM, (size_t)(world + 1) * ops->xyzz_bytes + 256, &comm));
+  char* mine = (char*)comm;
+  char* all = mine + ops->xyzz_bytes;
+  PCD_TRY(bases_msm(ctx, slice, 0, d_scalars, scalars_mont, n, nullptr, 0, mine));
+  PCD_TRY(comm_allgather(ctx, mine, all, ops->xyzz_bytes, ctx->stream));
+  return ops->sum_points(ctx, all, 0, 1, world, nullptr, 0, d_out_affine);
+}
+int pcdgpu_msm_bases_sharded(pcdgpu_ctx* ctx, const pcdgpu_bases* slice, const void* scalars, size_t n, void* out_affine) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, slice && out_affine && (n == 0 || scalars), "null pointer");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  const MsmOps* ops = msm_ops(slice->curve);
+  void *ds, *dres;
+  PCD_TRY(ctx->scratch(SLOT_IO2, n * 40 + 16, &ds));
+  PCD_TRY(ctx->scratch(SLOT_MISC, 8192, &dres));
+  PCD_CUDA(ctx, cudaMemcpyAsync(ds, scalars, n * 40, cudaMemcpyHostToDevice, ctx->stream));
+  PCD_TRY(pcdgpu_msm_bases_sharded_dev(ctx, slice, ds, 0, n, dres));
+  PCD_CUDA(ctx, cudaMemcpyAsync(out_affine, dres, ops->affine_bytes, cudaMemcpyDeviceToHost, ctx->stream));
+  PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
+  return 0;
 }
 
 int pcdgpu_groth16_assemble_begin_dev(pcdgpu_ctx* ctx, int pairing, const void* r, const void* s, int world,

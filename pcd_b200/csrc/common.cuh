@@ -89,6 +89,9 @@ struct pcdgpu_ctx {
   size_t spans_used = 0;
   unsigned* prof_pinned = nullptr;  // 4096 u32, pinned
   unsigned long long launches = 0;  // kernels launched by this context since the last read
+  // multi-GPU (comm.cu): NCCL communicator of the ranks that share one proof / MSM; world 1 = none
+  void* nccl_comm = nullptr;
+  int comm_rank = 0, comm_world = 1;
 
   int prof_begin(int slot, double units) {
     if (!profiling) return -1;
@@ -171,7 +174,8 @@ enum {
   SLOT_MSM_HP = 14,  // heavy-bucket partial sums
   SLOT_CUB2 = 15,
   SLOT_NTT_MIXED = 16,  // ping-pong buffer of a mixed-radix transform
-  SLOT_SAP_FULL = 17    // GM17: the SAP assignment (z and the extra variables)
+  SLOT_SAP_FULL = 17,   // GM17: the SAP assignment (z and the extra variables); small Groth16 proofs: s z | r z
+  SLOT_COMM = 18        // multi-GPU: this rank's partial sums and the gathered ones
 };
 
 template <class T>

@@ -34,6 +34,12 @@ struct pcdgpu_pk {
   size_t num_vars, num_inputs, h_len;
   // query vectors with their constant points appended (see pcdgpu_pk_upload)
   pcdgpu_bases *a_query, *b_g1_query, *b_g2_query, *h_query, *l_query;
+  // sharded keys (pcdgpu_pk_upload_sharded): this rank holds points [lo, hi) of each query; the constant points ride
+  // with rank 0.  world 1: the whole key.
+  int shard_rank, shard_world;
+  size_t v_lo, v_hi;  // of the num_vars - 1 ordinary points of a / b_g1 / b_g2
+  size_t h_lo, h_hi;  // of h_query
+  size_t l_lo, l_hi;  // of l_query
 };
 
 struct pcdgpu_gm17_pk {
@@ -90,3 +96,6 @@ int groth16_finish(pcdgpu_ctx* ctx, int pairing, const void* sums1, void* d_out_
 int groth16_scale(pcdgpu_ctx* ctx, int pairing, const void* d_z, size_t n, const u32* d_rs, void* d_sz, void* d_rz);
 int groth16_serialize(pcdgpu_ctx* ctx, int pairing, const void* d_proof, unsigned char* d_out);
 int bench_imad(pcdgpu_ctx* ctx, int modmul, int iters, double* ops_per_s, double* ms_out);
+// comm.cu: all-gather `bytes` bytes per rank (rank-major result) on stream st; group brackets (ncclGroupStart / End)
+int comm_allgather(pcdgpu_ctx* ctx, const void* d_send, void* d_recv, size_t bytes, cudaStream_t st);
+int comm_group(pcdgpu_ctx* ctx, bool start);

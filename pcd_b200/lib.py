@@ -39,7 +39,11 @@ EXPORTS = [
     "pcdgpu_gm17_prove", "pcdgpu_gm17_prove_dev",
     "pcdgpu_poly_divide_linear", "pcdgpu_poly_mul", "pcdgpu_kzg_commit", "pcdgpu_kzg_open",
     "pcdgpu_qap_vector_dev", "pcdgpu_qap_combine_dev", "pcdgpu_set_msm_side_by_side", "pcdgpu_groth16_assemble_begin_dev", "pcdgpu_groth16_assemble_finish_dev",
+    "pcdgpu_comm_unique_id", "pcdgpu_comm_init", "pcdgpu_comm_info", "pcdgpu_comm_destroy", "pcdgpu_pk_upload_sharded",
+    "pcdgpu_groth16_prove_sharded", "pcdgpu_groth16_prove_sharded_dev", "pcdgpu_msm_bases_sharded",
+    "pcdgpu_msm_bases_sharded_dev",
 ]
+COMM_ID_BYTES = 128
 
 
 class PcdGpuError(RuntimeError):
@@ -125,6 +129,16 @@ def load():
     lib.pcdgpu_poly_mul.argtypes = [vp, ci, vp, sz, vp, sz, vp]
     lib.pcdgpu_kzg_commit.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp]
     lib.pcdgpu_kzg_open.argtypes = [vp, vp, vp, sz, vp, vp, sz, vp, vp, vp, vp]
+    lib.pcdgpu_comm_unique_id.argtypes = [vp]
+    lib.pcdgpu_comm_init.argtypes = [vp, vp, ci, ci]
+    lib.pcdgpu_comm_info.argtypes = [vp, ctypes.POINTER(ci), ctypes.POINTER(ci)]
+    lib.pcdgpu_comm_destroy.argtypes = [vp]
+    lib.pcdgpu_comm_destroy.restype = None
+    lib.pcdgpu_pk_upload_sharded.argtypes = [vp, ci, sz, sz, sz] + [vp] * 10 + [ci, ctypes.POINTER(vp)]
+    lib.pcdgpu_groth16_prove_sharded.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.pcdgpu_groth16_prove_sharded_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp]
+    lib.pcdgpu_msm_bases_sharded.argtypes = [vp, vp, vp, sz, vp]
+    lib.pcdgpu_msm_bases_sharded_dev.argtypes = [vp, vp, vp, ci, sz, vp]
     _lib = lib
     return lib
 
@@ -245,6 +259,34 @@ class Context:
         self._check(self.lib.pcdgpu_fixed_base_mul_dev(self.h, curve, _p(base), ctypes.c_void_p(d_scalars), n,
                                                        ctypes.c_void_p(d_out)))
 
+    # ---- multi-GPU: the library's own collective (NCCL all-gather of partial sums, comm.cu) ----
+    def comm_unique_id(self) -> bytes:
+        """rank 0: the 128 bytes every rank passes to comm_init (ship them by any means)"""
+        buf = ctypes.create_string_buffer(COMM_ID_BYTES)
+        rc = self.lib.pcdgpu_comm_unique_id(buf)
+        if rc != 0:
+            raise PcdGpuError(rc, "libnccl.so.2 could not be loaded")
+        return buf.raw
+
+    def comm_init(self, uid: bytes, rank: int, world: int):
+        self._check(self.lib.pcdgpu_comm_init(self.h, ctypes.c_char_p(uid) if uid else None, rank, world))
+
+    def comm_init_torch(self, group=None):
+        """comm_init with the id broadcast through an initialised torch.distributed group"""
+        import torch
+        import torch.distributed as dist
+        if not (dist.is_available() and dist.is_initialized()):
+            return self.comm_init(None, 0, 1)
+        rank, world = dist.get_rank(group), dist.get_world_size(group)
+        box = [self.comm_unique_id() if rank == 0 else None]
+        dist.broadcast_object_list(box, src=0, group=group)
+        self.comm_init(box[0], rank, world)
+
+    def comm_info(self):
+        r, w = ctypes.c_int(), ctypes.c_int()
+        self._check(self.lib.pcdgpu_comm_info(self.h, ctypes.byref(r), ctypes.byref(w)))
+        return r.value, w.value
+
     def bench_imad(self, mode: int = 0, iters: int = 2000):
         ops, ms = ctypes.c_double(), ctypes.c_double()
         self._check(self.lib.pcdgpu_bench_imad(self.h, mode, iters, ctypes.byref(ops), ctypes.byref(ms)))
@@ -279,6 +321,17 @@ class Bases:
     def msm_dev(self, d_scalars: int, n: int, d_out: int, offset: int = 0, scalars_mont: bool = False):
         self.ctx._check(self.ctx.lib.pcdgpu_msm_bases_dev(self.ctx.h, self.h, offset, ctypes.c_void_p(d_scalars),
                                                           int(scalars_mont), n, ctypes.c_void_p(d_out)))
+
+    def msm_sharded(self, scalars: np.ndarray) -> np.ndarray:
+        """collective: this Bases holds THIS rank's slice, `scalars` this rank's scalars; every rank gets the sum"""
+        scalars = _u64(scalars, 5)
+        out = np.zeros(AFFINE_LIMBS[self.curve], dtype=np.uint64)
+        self.ctx._check(self.ctx.lib.pcdgpu_msm_bases_sharded(self.ctx.h, self.h, _p(scalars), scalars.shape[0], _p(out)))
+        return out
+
+    def msm_sharded_dev(self, d_scalars: int, n: int, d_out_affine: int, scalars_mont: bool = False):
+        self.ctx._check(self.ctx.lib.pcdgpu_msm_bases_sharded_dev(self.ctx.h, self.h, ctypes.c_void_p(d_scalars),
+                                                                  int(scalars_mont), n, ctypes.c_void_p(d_out_affine)))
 
     def close(self):
         if getattr(self, "h", None) and self.ctx.h:

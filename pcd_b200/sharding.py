@@ -100,166 +100,32 @@ def witness_map_by_vector(vector_fn: Callable[[int], "object"], combine_fn: Call
 
 # ---- one Groth16 proof over several GPUs ------------------------------------------------------------------
 class ShardedGroth16:
-    """Groth16 `create_proof_with_reduction` spread over the GPUs of one box, for when proofs are
-    NOT independent (a PCD chain proves its steps one after the other): every rank keeps points [lo, hi) of each of
-    the five query vectors resident (with window tables), computes the xyzz partial sums of the five MSMs over its
-    range, ONE all_gather moves the partials (4 x 160 + 320 bytes per rank on MNT4-298) and rank 0 adds them and
-    assembles the proof (pcdgpu_groth16_assemble_partials_dev).  The witness map's a / b / c chains run on ranks
-    0 / 1 / 2 (witness_map_by_vector) and h is broadcast.  The constant points (delta, query[0], alpha / beta) ride
-    in rank 0's slices as extra (point, scalar) pairs, as in pcdgpu_pk_upload.  The proof is bit-identical to the
-    single-GPU one for any number of ranks."""
+    """Groth16 `create_proof_with_reduction` spread over the GPUs of one box, for when proofs are NOT
+    independent (a PCD chain proves its steps one after the other).  Everything happens inside libpcdgpu.so
+    (pcdgpu_comm_init / pcdgpu_pk_upload_sharded / pcdgpu_groth16_prove_sharded): every rank keeps points [lo, hi)
+    of each of the five query vectors resident (with window tables), computes the xyzz partial sums of the five MSMs
+    over its range, two NCCL all-gathers of 160 - 480 byte points move them, and every rank assembles the proof.  No
+    host bounce, no torch collective on the data path: torch.distributed is only used (once, at construction) to
+    broadcast the 128-byte NCCL id.  The proof is bit-identical to the single-GPU one for any number of ranks."""
 
-    def __init__(self, ctx, pk, cm, rank: int, world: int, device, precompute: bool = True, group=None):
-        import ctypes
-        from . import lib as L
-        from .synthetic import FIELD_P
-        self.ctx, self.rank, self.world, self.dev, self.group = ctx, rank, world, device, group
-        self.pairing = pk.pairing
-        self.g1, self.g2 = L.G1_OF[pk.pairing], L.G2_OF[pk.pairing]
-        self.ni, self.nv = cm.num_instance_variables, cm.num_instance_variables + cm.num_witness_variables
-        self.p = FIELD_P[L.SCALAR_FIELD_OF[pk.pairing]]
-        self.R = (1 << 320) % self.p
-        keep = []
-
-        def arr(a, dt):
-            a = np.ascontiguousarray(a, dtype=dt)
-            keep.append(a)
-            return ctypes.c_void_p(a.ctypes.data)
-
-        args = []
-        for (ptr, col, val) in (cm.a, cm.b, cm.c):
-            args += [arr(ptr, np.uint32), arr(col, np.uint32), arr(val, np.uint64)]
-        h = ctypes.c_void_p()
-        ctx._check(ctx.lib.pcdgpu_r1cs_upload(ctx.h, pk.pairing, cm.num_constraints, self.ni, cm.num_witness_variables,
-                                              *args, ctypes.byref(h)))
-        self.r1cs = h
-        self.n = ctx.lib.pcdgpu_r1cs_domain_size(h)
-        # the four MSMs over the assignment run on contexts (streams + scratch) of their own, beside the witness map
-        self.side = [L.Context(ctx.device) for _ in range(4)]
-        for c in [ctx] + self.side:  # five MSMs side by side: the prover's window / occupancy rules, not a lone MSM's
-            c._check(c.lib.pcdgpu_set_msm_side_by_side(c.h, 1))
-        import torch
-        self.comm_stream = torch.cuda.Stream(device=device)
-        l1, l2 = L.AFFINE_LIMBS[self.g1], L.AFFINE_LIMBS[self.g2]
-        q = lambda a, w: np.ascontiguousarray(a, dtype=np.uint64).reshape(-1, w)
-        a_q, b1_q, b2_q = q(pk.a_query, l1), q(pk.b_g1_query, l1), q(pk.b_g2_query, l2)
-        l_q, h_q = q(pk.l_query, l1), q(pk.h_query, l1)
-        one = lambda a, w: np.ascontiguousarray(a, dtype=np.uint64).reshape(1, w)
-
-        def part(points, extras, curve):
-            lo, hi = shard_range(points.shape[0], world, rank)
-            pts = points[lo:hi]
-            if rank == 0 and extras:
-                pts = np.concatenate([pts] + extras)
-            return (lo, hi, L.Bases(ctx, curve, pts, precompute))
-
-        self.a = part(a_q[1:], [one(pk.delta_g1, l1), a_q[:1], one(pk.alpha_g1, l1)], self.g1)
-        self.b1 = part(b1_q[1:], [one(pk.delta_g1, l1), b1_q[:1], one(pk.beta_g1, l1)], self.g1)
-        self.b2 = part(b2_q[1:], [one(pk.delta_g2, l2), b2_q[:1], one(pk.beta_g2, l2)], self.g2)
-        self.l = part(l_q, [one(pk.delta_g1, l1)], self.g1)
-        self.h = part(h_q, [], self.g1)
-
-    def _mont(self, vals):
-        import torch
-        b = b"".join(int(v * self.R % self.p).to_bytes(40, "little") for v in vals)
-        return torch.from_numpy(np.frombuffer(b, dtype="<i8").copy().reshape(-1, 5)).to(self.dev)
-
-    def _scalars(self, base, first_row: int, part, extras):
-        """device pointer of the scalars of this rank's slice: rows [first_row + lo, first_row + hi) of `base`, with
-        rank 0's extra scalars appended (a copy only on rank 0)"""
-        import torch
-        lo, hi, bases = part
-        rows = base[first_row + lo:first_row + hi]
-        if self.rank == 0 and extras is not None:
-            rows = torch.cat([rows, extras]).contiguous()
-        return rows, bases.n
+    def __init__(self, ctx, pk, cm, rank: int, world: int, device=None, precompute: bool = True, group=None):
+        from . import snark
+        self.ctx, self.rank, self.world = ctx, rank, world
+        r, w = ctx.comm_info()
+        if w == 1 and world > 1:
+            ctx.comm_init_torch(group)
+        elif (r, w) != (rank, world):
+            raise ValueError("the context's communicator is rank %d of %d, not %d of %d" % (r, w, rank, world))
+        self.g = snark.Groth16(ctx, pk.pairing)
+        self.index = self.g.index(pk, cm, precompute=precompute, sharded=True)
 
     def prove(self, z_dev, r: int, s: int):
-        """z_dev: (num_vars, 5) int64 tensor on this rank's GPU (Montgomery limbs); r, s: plain integers.  Returns the
-        proof's affine limbs on rank 0, None elsewhere."""
-        import ctypes
-        import torch
-        import torch.distributed as dist
-        from . import lib as L
-        ctx, lib, vp = self.ctx, self.ctx.lib, ctypes.c_void_p
-        multi = self.world > 1
-
-        def vector_fn(which):
-            t = torch.empty((self.n, 5), dtype=torch.int64, device=self.dev)
-            ctx._check(lib.pcdgpu_qap_vector_dev(ctx.h, self.r1cs, which, vp(z_dev.data_ptr()), vp(t.data_ptr())))
-            return t
-
-        def combine_fn(a, b, c):
-            ctx._check(lib.pcdgpu_qap_combine_dev(ctx.h, self.r1cs, vp(a.data_ptr()), vp(b.data_ptr()), vp(c.data_ptr())))
-            return a
-
-        p = self.p
-        ex_a = self._mont([r, 1, 1]) if self.rank == 0 else None
-        ex_b = self._mont([s, 1, 1]) if self.rank == 0 else None
-        ex_l = self._mont([(-r * s) % p]) if self.rank == 0 else None
-        x1, x2 = L.XYZZ_LIMBS[self.g1], L.XYZZ_LIMBS[self.g2]
-        pab = torch.zeros((2, x1), dtype=torch.int64, device=self.dev)   # a, b_g1
-        phl = torch.zeros((2, x1), dtype=torch.int64, device=self.dev)   # h, l
-        p2 = torch.zeros((1, x2), dtype=torch.int64, device=self.dev)    # b_g2
-        keep = []
-
-        def launch(c, part, base, first, extras, out):
-            rows, n = self._scalars(base, first, part, extras)
-            keep.append(rows)
-            c._check(c.lib.pcdgpu_msm_bases_dev(c.h, part[2].h, 0, vp(rows.data_ptr()), 1, n, vp(out.data_ptr())))
-
-        def gather(t):
-            if not multi:
-                return t
-            with torch.cuda.stream(self.comm_stream):  # not behind the witness map / h MSM queued on the main stream
-                outs = [torch.empty_like(t) for _ in range(self.world)]
-                dist.all_gather(outs, t, group=self.group)
-                res = torch.stack(outs).contiguous()
-            self.comm_stream.synchronize()
-            return res
-
-        torch.cuda.current_stream().synchronize()  # z, the extras and the zeroed partials are ready for every stream
-        # the G2 MSM first (the longest), then the three G1 MSMs over the assignment, each on its own context ...
-        launch(self.side[0], self.b2, z_dev, 1, ex_b, p2[0])
-        launch(self.side[1], self.a, z_dev, 1, ex_a, pab[0])
-        launch(self.side[2], self.b1, z_dev, 1, ex_b, pab[1])
-        launch(self.side[3], self.l, z_dev, self.ni, ex_l, phl[1])
-        # ... while this context runs the witness map (its three chains on ranks 0, 1, 2) and then the MSM over h
-        h = witness_map_by_vector(vector_fn, combine_fn,
-                                  lambda: torch.empty((self.n, 5), dtype=torch.int64, device=self.dev), group=self.group)
-        if multi:
-            if h is None:
-                h = torch.empty((self.n, 5), dtype=torch.int64, device=self.dev)
-            dist.broadcast(h, src=0, group=self.group)
-        launch(ctx, self.h, h, 0, None, phl[0])
-        # first exchange: a, b_g1, b_g2 -- rank 0 starts s g_a + r g1_b (4 ms of one thread) under the h MSM
-        for c in self.side[:3]:
-            c.sync()
-        gab, g2 = gather(pab), gather(p2)
+        """z_dev: torch tensor (or anything with data_ptr()) holding the assignment on this rank's GPU; r, s: Python
+        integers.  Collective.  Returns the proof's affine limbs (A || B || C) on every rank."""
         lim = lambda v: np.array([(v >> (64 * i)) & 0xFFFFFFFFFFFFFFFF for i in range(5)], dtype=np.uint64)
-        rl, sl = lim(r), lim(s)
-        asm = self.side[0]  # idle by now; holds the assembly state between begin and finish
-        if self.rank == 0:
-            asm._check(lib.pcdgpu_groth16_assemble_begin_dev(asm.h, self.pairing, vp(rl.ctypes.data), vp(sl.ctypes.data),
-                                                             self.world, vp(gab.data_ptr()), vp(g2.data_ptr())))
-        # second exchange: h, l
-        self.side[3].sync()
-        torch.cuda.current_stream().synchronize()
-        ghl = gather(phl)
-        if self.rank != 0:
-            return None
-        out = np.zeros(2 * L.AFFINE_LIMBS[self.g1] + L.AFFINE_LIMBS[self.g2], dtype=np.uint64)
-        asm._check(lib.pcdgpu_groth16_assemble_finish_dev(asm.h, self.pairing, self.world, vp(ghl.data_ptr()),
-                                                          vp(out.ctypes.data)))
-        return out
+        return self.g.create_proof_sharded_dev(self.index, z_dev.data_ptr(), lim(r), lim(s)).affine_limbs()
 
     def close(self):
-        for part in (self.a, self.b1, self.b2, self.l, self.h):
-            part[2].close()
-        for c in self.side:
-            c.close()
-        self.side = []
-        self.ctx.lib.pcdgpu_set_msm_side_by_side(self.ctx.h, 0)
-        if self.r1cs:
-            self.ctx.lib.pcdgpu_r1cs_free(self.r1cs)
-            self.r1cs = None
+        if self.index is not None:
+            self.index.close()
+            self.index = None

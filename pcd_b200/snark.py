@@ -71,7 +71,11 @@ class Proof:
 class ProverIndex:
     """Device-resident proving key + constraint matrices (uploaded once per circuit shape)."""
 
-    def __init__(self, ctx: L.Context, pk: ProvingKey, cm: ConstraintMatrices, precompute: bool = False):
+    def __init__(self, ctx: L.Context, pk: ProvingKey, cm: ConstraintMatrices, precompute: bool = False,
+                 sharded: bool = False):
+        """sharded: the context has a communicator (Context.comm_init): upload only this rank's slice of every query
+        (pcdgpu_pk_upload_sharded); proofs then go through Groth16.create_proof_sharded on every rank."""
+        self.sharded = sharded
         if pk.pairing != cm.pairing:
             raise ValueError("proving key and constraint matrices are over different pairings")
         self.ctx, self.pairing = ctx, pk.pairing
@@ -103,7 +107,7 @@ class ProverIndex:
             raise ValueError("a_query has %d points for %d variables" % (a_q.shape[0], self.num_vars))
         h_q = np.ascontiguousarray(pk.h_query, dtype=np.uint64).reshape(-1, L.AFFINE_LIMBS[g1])
         pkh = ctypes.c_void_p()
-        ctx._check(lib.pcdgpu_pk_upload(
+        ctx._check((lib.pcdgpu_pk_upload_sharded if sharded else lib.pcdgpu_pk_upload)(
             ctx.h, pk.pairing, self.num_vars, self.num_inputs, h_q.shape[0],
             arr(pk.alpha_g1, np.uint64), arr(pk.beta_g1, np.uint64), arr(pk.delta_g1, np.uint64),
             arr(pk.beta_g2, np.uint64), arr(pk.delta_g2, np.uint64), arr(a_q, np.uint64),
@@ -133,8 +137,8 @@ class Groth16:
     def __init__(self, ctx: L.Context, pairing: int):
         self.ctx, self.pairing = ctx, pairing
 
-    def index(self, pk: ProvingKey, cm: ConstraintMatrices, precompute: bool = False) -> ProverIndex:
-        return ProverIndex(self.ctx, pk, cm, precompute)
+    def index(self, pk: ProvingKey, cm: ConstraintMatrices, precompute: bool = False, sharded: bool = False) -> ProverIndex:
+        return ProverIndex(self.ctx, pk, cm, precompute, sharded)
 
     def witness_map(self, index: ProverIndex, z: np.ndarray) -> np.ndarray:
         """R1CStoQAP::witness_map: the n coefficients of h."""
@@ -169,6 +173,18 @@ class Groth16:
         vp = lambda a: ctypes.c_void_p(a.ctypes.data)
         self.ctx._check(self.ctx.lib.pcdgpu_groth16_prove_dev(self.ctx.h, index.pk, index.r1cs, ctypes.c_void_p(d_z),
                                                               vp(r), vp(s), vp(out)))
+        return Proof(self.pairing, out[:g1].copy(), out[g1:g1 + g2].copy(), out[g1 + g2:].copy())
+
+    def create_proof_sharded_dev(self, index: ProverIndex, d_z: int, r: np.ndarray, s: np.ndarray) -> Proof:
+        """One proof over the GPUs of the context's communicator (collective: every rank calls it with the same
+        inputs over its slice of the key, index = g.index(..., sharded=True); every rank receives the proof)."""
+        r = np.ascontiguousarray(r, dtype=np.uint64)
+        s = np.ascontiguousarray(s, dtype=np.uint64)
+        g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
+        out = np.zeros(2 * g1 + g2, dtype=np.uint64)
+        vp = lambda a: ctypes.c_void_p(a.ctypes.data)
+        self.ctx._check(self.ctx.lib.pcdgpu_groth16_prove_sharded_dev(self.ctx.h, index.pk, index.r1cs,
+                                                                      ctypes.c_void_p(d_z), vp(r), vp(s), vp(out)))
         return Proof(self.pairing, out[:g1].copy(), out[g1:g1 + g2].copy(), out[g1 + g2:].copy())
 
     def prove(self, index: ProverIndex, z: np.ndarray, rng: Callable[[int], np.ndarray]) -> Proof:

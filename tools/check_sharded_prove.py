@@ -72,7 +72,47 @@ def main():
             idx.close()
         if world > 1:
             dist.barrier()
+    # one MSM sharded by point range through the library's collective (pcdgpu_msm_bases_sharded_dev)
+    lg = int(os.environ.get("LOG_N_MSM", "18"))
+    n = 1 << lg
+    pts = synthetic.random_points_dev(ctx, 0, n, seed=3).cpu().numpy().view(np.uint64)  # same points on every rank
+    sc_host = synthetic.random_limbs(n, 0, 9)
+    lo, hi = sharding.shard_range(n, world, rank)
+    shard = pcd_b200.Bases(ctx, 0, pts[lo:hi], precompute=True)
+    sc = torch.from_numpy(sc_host[lo:hi].copy().view(np.int64)).to(dev)
+    res = torch.zeros(16, dtype=torch.int64, device=dev)
+    for _ in range(3):
+        shard.msm_sharded_dev(sc.data_ptr(), hi - lo, res.data_ptr())
+    torch.cuda.synchronize()
     if world > 1:
+        dist.barrier()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(stream)
+    for _ in range(10):
+        shard.msm_sharded_dev(sc.data_ptr(), hi - lo, res.data_ptr())
+    e1.record(stream)
+    torch.cuda.synchronize()
+    ms_sh = e0.elapsed_time(e1) / 10
+    got = res.cpu().numpy().view(np.uint64)[:10]
+    shard.close()
+    if rank == 0:
+        full = pcd_b200.Bases(ctx, 0, pts, precompute=True)
+        ref = full.msm(sc_host)
+        scf = torch.from_numpy(sc_host.view(np.int64)).to(dev)
+        for _ in range(3):
+            full.msm_dev(scf.data_ptr(), n, res.data_ptr())
+        e0.record(stream)
+        for _ in range(10):
+            full.msm_dev(scf.data_ptr(), n, res.data_ptr())
+        e1.record(stream)
+        torch.cuda.synchronize()
+        same = bool(np.array_equal(got, ref))
+        out["g1_msm_2^%d" % lg] = {"gpus": world, "matches_single_gpu": same, "ms_sharded": ms_sh,
+                                   "ms_one_gpu": e0.elapsed_time(e1) / 10}
+        ok_all = ok_all and same
+        full.close()
+    if world > 1:
+        dist.barrier()
         dist.destroy_process_group()
     if rank == 0:
         print(json.dumps(out), flush=True)
