@@ -25,6 +25,7 @@
 #include <cstring>
 #include <string>
 #include <utility>
+#include <map>
 #include <vector>
 
 #include "pcdgpu.h"
@@ -96,20 +97,31 @@ struct Proof {
   G1Affine<E> c{};
 };
 
-// one GPU context per host thread (the ABI's rule); shared by every Groth16<E> call on that thread
+// one GPU context per host thread AND device (the ABI's rule: a context is never shared between host threads); shared
+// by every Groth16<E> / GM17<E> call of that thread on that device, destroyed when the thread ends
 class Backend {
+  struct PerThread {
+    std::map<int, pcdgpu_ctx*> by_device;
+    ~PerThread() {
+      for (auto& kv : by_device) pcdgpu_ctx_destroy(kv.second);
+    }
+  };
+
  public:
   static Result<pcdgpu_ctx*> get(int device = 0) {
-    thread_local pcdgpu_ctx* ctx = nullptr;
+    thread_local PerThread mine;
     Result<pcdgpu_ctx*> r;
-    if (!ctx) {
+    auto it = mine.by_device.find(device);
+    if (it == mine.by_device.end()) {
+      pcdgpu_ctx* ctx = nullptr;
       int rc = pcdgpu_ctx_create(device, &ctx);
       if (rc != PCDGPU_OK) {
         r.error = {ErrorKind::Backend, rc, pcdgpu_strerror(rc)};  // no CPU fallback: the error surfaces
         return r;
       }
+      it = mine.by_device.emplace(device, ctx).first;
     }
-    r.value = ctx;
+    r.value = it->second;
     return r;
   }
 };

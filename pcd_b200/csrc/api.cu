@@ -96,25 +96,21 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
   static const bool no_prio = getenv("PCDGPU_NO_PRIORITIES") != nullptr;  // development aid (A/B runs)
   if (no_prio) prio_greatest = prio_least;
   const int prio_mid = prio_greatest < prio_least ? prio_greatest + 1 : prio_least;
-  if (cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) {
-    delete ctx;
-    return PCDGPU_E_CUDA;
-  }
+  // every partial failure goes through pcdgpu_ctx_destroy, which releases whatever was created so far
+  int rc = PCDGPU_OK;
+  if (cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) rc = PCDGPU_E_CUDA;
   ctx->stream = ctx->own_stream;
-  bool ok = cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) == cudaSuccess;
-  for (int l = 1; l < pcdgpu_ctx::NLANE && ok; l++)
-    ok = cudaStreamCreateWithPriority(&ctx->lane_stream[l], cudaStreamNonBlocking,
-                                      (l == 2 || l == 3 || l >= 5) ? prio_mid : prio_least) == cudaSuccess &&
-         cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming) == cudaSuccess;
-  if (!ok) {
-    delete ctx;
-    return PCDGPU_E_CUDA;
-  }
+  if (rc == 0 && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = PCDGPU_E_CUDA;
+  for (int l = 1; l < pcdgpu_ctx::NLANE && rc == 0; l++)
+    if (cudaStreamCreateWithPriority(&ctx->lane_stream[l], cudaStreamNonBlocking,
+                                     (l == 2 || l == 3 || l >= 5) ? prio_mid : prio_least) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming) != cudaSuccess)
+      rc = PCDGPU_E_CUDA;
   ctx->pinned_bytes = 1 << 16;
-  if (cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) {
-    cudaStreamDestroy(ctx->own_stream);
-    delete ctx;
-    return PCDGPU_E_NOMEM;
+  if (rc == 0 && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) rc = PCDGPU_E_NOMEM;
+  if (rc) {
+    pcdgpu_ctx_destroy(ctx);
+    return rc;
   }
   *out = ctx;
   return PCDGPU_OK;
@@ -139,7 +135,7 @@ void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx) {
     cudaEventDestroy(sp.a);
     cudaEventDestroy(sp.b);
   }
-  cudaStreamDestroy(ctx->own_stream);
+  if (ctx->own_stream) cudaStreamDestroy(ctx->own_stream);
   delete ctx;
 }
 
@@ -448,6 +444,9 @@ int pcdgpu_r1cs_upload(pcdgpu_ctx* ctx, int pairing, size_t m, size_t num_inputs
   const void* vals[3] = {a_val, b_val, c_val};
   size_t nnz[3], total = 0, off[9];
   for (int i = 0; i < 3; i++) {
+    // row_ptr must be a monotone prefix array ending at nnz: a bad one would send spmv_kernel out of bounds on the device
+    CHECK_ARG(ctx, ptrs[i][0] == 0, "row_ptr[0] must be 0");
+    for (size_t k = 0; k < m; k++) CHECK_ARG(ctx, ptrs[i][k] <= ptrs[i][k + 1], "row_ptr is not monotone");
     nnz[i] = ptrs[i][m];
     CHECK_ARG(ctx, nnz[i] == 0 || (cols[i] && vals[i]), "null column / value array");
     for (size_t k = 0; k < nnz[i]; k++) CHECK_ARG(ctx, cols[i][k] < num_inputs + num_witness, "column index out of range");

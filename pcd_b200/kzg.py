@@ -58,6 +58,11 @@ class OpeningProof:
     random_v: Optional[np.ndarray]
 
 
+def hiding_blinding_coefficients(hiding_bound: int) -> int:
+    """coefficients of the blinding polynomial of a hiding commitment: degree hiding_bound + 1 -> hiding_bound + 2 draws"""
+    return hiding_bound + 2
+
+
 class KZG10:
     def __init__(self, ctx: L.Context):
         self.ctx = ctx
@@ -65,15 +70,18 @@ class KZG10:
     def commit(self, powers: Powers, polynomial: np.ndarray, hiding_bound: Optional[int] = None,
                rng: Optional[Callable[[int], np.ndarray]] = None):
         """KZG10::commit.  polynomial: (n, 5) Montgomery coefficients, lowest degree first.  With a hiding bound the
-        blinding polynomial has hiding_bound + 1 coefficients drawn from rng(field) (Montgomery limbs each), in order.
-        Returns (commitment affine limbs, Randomness)."""
+        blinding polynomial is `Randomness::rand(hiding_bound, ..)`: degree
+        `calculate_hiding_polynomial_degree(hiding_bound) = hiding_bound + 1`, i.e. hiding_bound + 2 coefficients
+        (`P::rand(d, rng)` draws d + 1), drawn from rng(field) in order, lowest degree first (ark-poly-commit
+        kzg10/data_structures.rs, recalled: upstream is not vendored) -- the draw COUNT matters for byte parity because
+        every later draw of the caller's rng shifts with it.  Returns (commitment affine limbs, Randomness)."""
         poly = np.ascontiguousarray(polynomial, dtype=np.uint64).reshape(-1, 5)
         if poly.shape[0] > powers.size():
             raise ValueError("polynomial has %d coefficients for %d powers" % (poly.shape[0], powers.size()))
         if hiding_bound is not None:
             if rng is None:
                 raise ValueError("a hiding commitment needs an rng")
-            blind = np.stack([rng(powers.field) for _ in range(hiding_bound + 1)]).astype(np.uint64)
+            blind = np.stack([rng(powers.field) for _ in range(hiding_blinding_coefficients(hiding_bound))]).astype(np.uint64)
         else:
             blind = np.zeros((0, 5), dtype=np.uint64)
         out = np.zeros(L.AFFINE_LIMBS[powers.curve], dtype=np.uint64)

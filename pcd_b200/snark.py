@@ -22,6 +22,14 @@ from . import lib as L
 CSR = Tuple[np.ndarray, np.ndarray, np.ndarray]  # (row_ptr u32[m+1], col u32[nnz], val u64[nnz,5] Montgomery)
 
 
+def _scalar(a) -> np.ndarray:
+    """one scalar as five u64 limbs (the C side reads exactly 40 bytes)"""
+    a = np.ascontiguousarray(a, dtype=np.uint64).reshape(-1)
+    if a.size != 5:
+        raise ValueError("a scalar is five 64-bit limbs, got %d" % a.size)
+    return a
+
+
 @dataclass
 class ConstraintMatrices:
     """ark-relations `ConstraintMatrices`: instance variables first (column 0 is the constant 1)."""
@@ -106,6 +114,18 @@ class ProverIndex:
         if a_q.shape[0] != self.num_vars:
             raise ValueError("a_query has %d points for %d variables" % (a_q.shape[0], self.num_vars))
         h_q = np.ascontiguousarray(pk.h_query, dtype=np.uint64).reshape(-1, L.AFFINE_LIMBS[g1])
+        # every query goes to C as a raw pointer and is read num_vars (num_witness) points deep: check the lengths here
+        for name, q, limbs_, want in (("b_g1_query", pk.b_g1_query, L.AFFINE_LIMBS[g1], self.num_vars),
+                                      ("b_g2_query", pk.b_g2_query, L.AFFINE_LIMBS[g2], self.num_vars),
+                                      ("l_query", pk.l_query, L.AFFINE_LIMBS[g1], self.num_witness)):
+            got = np.asarray(q).size // limbs_ if np.asarray(q).size % limbs_ == 0 else -1
+            if got != want:
+                raise ValueError("%s has %d points, expected %d" % (name, got, want))
+        for name, pt, limbs_ in (("alpha_g1", pk.alpha_g1, L.AFFINE_LIMBS[g1]), ("beta_g1", pk.beta_g1, L.AFFINE_LIMBS[g1]),
+                                 ("delta_g1", pk.delta_g1, L.AFFINE_LIMBS[g1]), ("beta_g2", pk.beta_g2, L.AFFINE_LIMBS[g2]),
+                                 ("delta_g2", pk.delta_g2, L.AFFINE_LIMBS[g2])):
+            if np.asarray(pt).size != limbs_:
+                raise ValueError("%s is not one affine point" % name)
         pkh = ctypes.c_void_p()
         ctx._check((lib.pcdgpu_pk_upload_sharded if sharded else lib.pcdgpu_pk_upload)(
             ctx.h, pk.pairing, self.num_vars, self.num_inputs, h_q.shape[0],
@@ -155,8 +175,8 @@ class Groth16:
         z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
         if z.shape[0] != index.num_vars:
             raise ValueError("assignment has %d elements for %d variables" % (z.shape[0], index.num_vars))
-        r = np.ascontiguousarray(r, dtype=np.uint64)
-        s = np.ascontiguousarray(s, dtype=np.uint64)
+        r = _scalar(r)
+        s = _scalar(s)
         g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
         out = np.zeros(2 * g1 + g2, dtype=np.uint64)
         vp = lambda a: ctypes.c_void_p(a.ctypes.data)
@@ -166,8 +186,8 @@ class Groth16:
 
     def create_proof_dev(self, index: ProverIndex, d_z: int, r: np.ndarray, s: np.ndarray) -> Proof:
         """same with the assignment already resident on the GPU (device pointer)."""
-        r = np.ascontiguousarray(r, dtype=np.uint64)
-        s = np.ascontiguousarray(s, dtype=np.uint64)
+        r = _scalar(r)
+        s = _scalar(s)
         g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
         out = np.zeros(2 * g1 + g2, dtype=np.uint64)
         vp = lambda a: ctypes.c_void_p(a.ctypes.data)
@@ -178,8 +198,8 @@ class Groth16:
     def create_proof_sharded_dev(self, index: ProverIndex, d_z: int, r: np.ndarray, s: np.ndarray) -> Proof:
         """One proof over the GPUs of the context's communicator (collective: every rank calls it with the same
         inputs over its slice of the key, index = g.index(..., sharded=True); every rank receives the proof)."""
-        r = np.ascontiguousarray(r, dtype=np.uint64)
-        s = np.ascontiguousarray(s, dtype=np.uint64)
+        r = _scalar(r)
+        s = _scalar(s)
         g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
         out = np.zeros(2 * g1 + g2, dtype=np.uint64)
         vp = lambda a: ctypes.c_void_p(a.ctypes.data)
@@ -306,7 +326,7 @@ class GM17:
         z = np.ascontiguousarray(z, dtype=np.uint64).reshape(-1, 5)
         if z.shape[0] != index.num_vars:
             raise ValueError("assignment has %d elements for %d variables" % (z.shape[0], index.num_vars))
-        d1, d2, r = (np.ascontiguousarray(x, dtype=np.uint64) for x in (d1, d2, r))
+        d1, d2, r = (_scalar(x) for x in (d1, d2, r))
         g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
         out = np.zeros(2 * g1 + g2, dtype=np.uint64)
         vp = lambda a: ctypes.c_void_p(a.ctypes.data)
@@ -315,7 +335,7 @@ class GM17:
         return Proof(self.pairing, out[:g1].copy(), out[g1:g1 + g2].copy(), out[g1 + g2:].copy())
 
     def create_proof_dev(self, index: GM17ProverIndex, d_z: int, d1: np.ndarray, d2: np.ndarray, r: np.ndarray) -> Proof:
-        d1, d2, r = (np.ascontiguousarray(x, dtype=np.uint64) for x in (d1, d2, r))
+        d1, d2, r = (_scalar(x) for x in (d1, d2, r))
         g1, g2 = L.AFFINE_LIMBS[L.G1_OF[self.pairing]], L.AFFINE_LIMBS[L.G2_OF[self.pairing]]
         out = np.zeros(2 * g1 + g2, dtype=np.uint64)
         vp = lambda a: ctypes.c_void_p(a.ctypes.data)

@@ -103,6 +103,15 @@ def test_gpu_poly_mul(ctx, field, na, nb):
         assert len(out) == na + nb - 1
 
 
+def test_hiding_commitment_draw_count():
+    """ark-poly-commit kzg10: Randomness::rand(hiding_bound) draws a polynomial of degree
+    calculate_hiding_polynomial_degree(hiding_bound) = hiding_bound + 1, i.e. hiding_bound + 2 field elements; the mirror
+    must consume exactly that many draws of the caller's rng (every later draw shifts otherwise)"""
+    from pcd_b200 import kzg
+    for hb in (0, 1, 2, 7):
+        assert kzg.hiding_blinding_coefficients(hb) == hb + 2
+
+
 @pytest.mark.gpu
 @pytest.mark.parametrize("pairing,deg,pre", [(0, 300, False), (1, 300, True), (0, 5000, True)])
 def test_gpu_kzg_commit_open(ctx, pairing, deg, pre):
@@ -117,9 +126,11 @@ def test_gpu_kzg_commit_open(ctx, pairing, deg, pre):
     K = kzg.KZG10(ctx)
     for n, hb in ((deg + 1, None), (deg + 1, 2), (deg // 2, 1), (1, None), (7, 0)):
         poly = _rand_poly(n, field, 500 + n)
-        blind_ints = _rand_poly(hb + 1, field, 600 + n) if hb is not None else None
+        blind_ints = _rand_poly(kzg.hiding_blinding_coefficients(hb), field, 600 + n) if hb is not None else None
         draws = iter(_mont(blind_ints, field)) if blind_ints else None
         c, rand = K.commit(powers, _mont(poly, field), hb, (lambda f: next(draws)) if draws else None)
+        if draws is not None:  # every blinding coefficient was consumed, none left over
+            assert next(draws, None) is None and rand.blinding_polynomial.shape[0] == hb + 2
         assert np.array_equal(c, ko.commit(pairing, pg, pgg, poly, blind_ints, 8))
         log = ko.expected_commit_log(p, beta, gamma, poly, blind_ints)
         assert np.array_equal(c, co.fixed_base_mul(g1, G, codec.ints_to_limbs([log]), 1)[0])

@@ -143,6 +143,13 @@ def test_witness_map_by_vector_gloo(world):
     assert all(ret[r] for r in range(world))
 
 
+def _free_port():
+    import socket
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
 @pytest.mark.gpu
 def test_witness_map_by_vector_multi_gpu():
     """real GPUs: needs at least two (skipped on a one-GPU box; the gloo tests above cover the host logic)"""
@@ -154,7 +161,7 @@ def test_witness_map_by_vector_multi_gpu():
     world = 3 if ngpu >= 3 else 2
     env = dict(os.environ, LOG_N="14")
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-                        "--master-addr", "127.0.0.1", "--master-port", "29533",
+                        "--master-addr", "127.0.0.1", "--master-port", str(_free_port()),
                         os.path.join(ROOT, "tools", "check_wm_by_vector.py")], env=env, capture_output=True, text=True,
                        timeout=600)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
@@ -174,6 +181,6 @@ def test_sharded_groth16_prove_multi_gpu():
         cmd = [sys.executable, script]
     else:
         cmd = [sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node", str(world),
-               "--master-addr", "127.0.0.1", "--master-port", "29534", script]
+               "--master-addr", "127.0.0.1", "--master-port", str(_free_port()), script]
     r = subprocess.run(cmd, env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
