@@ -61,3 +61,14 @@ def test_domain_size_rule_matches_oracle():
         for m in (1, 2, 3, 1000, 1 << 16, (1 << 17) - 1, 1 << 17, (1 << 17) + 1, 200704, 200705, 7 << 17, (7 << 17) + 1,
                   49 << 17, (49 << 17) + 1, 1 << 20, (1 << 34) + 1):
             assert L.domain_size(field, m) == co.domain_size(field, m), (field, m)
+
+
+def test_rust_sys_crate_declares_every_header_function():
+    """rust/pcdgpu-sys/src/lib.rs (uncompiled source) is generated from include/pcdgpu.h: every exported function is
+    declared, and the committed file is what tools/gen_rust_sys.py produces"""
+    import subprocess
+    import sys
+    src = open(os.path.join(ROOT, "rust", "pcdgpu-sys", "src", "lib.rs")).read()
+    for n in _header_functions():
+        assert re.search(r"pub fn %s\(" % n, src), n
+    assert subprocess.call([sys.executable, os.path.join(ROOT, "tools", "gen_rust_sys.py"), "--check"]) == 0
