@@ -17,7 +17,7 @@
 #include "ec.cuh"
 #include "wec_programs.cuh"
 
-enum { WEC_NOP = 0, WEC_MUL, WEC_ADD, WEC_SUB, WEC_DBL, WEC_NEG, WEC_CPY, WEC_MULK, WEC_INV, WEC_SUBD };
+enum { WEC_NOP = 0, WEC_MUL, WEC_LIN, WEC_RED, WEC_INV, WEC_CPY };
 
 template <class C>
 struct WecTraits;
@@ -65,45 +65,120 @@ __device__ __forceinline__ u32* wec_slot(u32 s, u32* xb, u32* yb, u32* tb) {
   return s < 16u ? xb + s * 10u : (s < 32u ? yb + (s - 16u) * 10u : tb + (s - 32u) * 10u);
 }
 
-// The interpreter: `rows` rows of G instruction words; lane gl of the group executes word [row * G + gl] and the
-// group synchronises after every row (the generator never lets a row read a slot that another lane of the same
-// row writes).  One copy per base field and group size in a kernel (noinline): it holds the only inlined product.
+// ---- unreduced ("lazy") linear arithmetic on ten-limb integers ---------------------------------------------------
+// The generator (tools/gen_wec.py) tracks for every value a bound m with value < m p < 2^320 and never lets a
+// subtraction underflow, so LIN needs no comparison and no conditional subtraction at all.
+template <class B>
+__device__ __forceinline__ void wec_raw_add(u32* r, const u32* a, const u32* b) {  // r = a + b (no carry out by the bound)
+  r[0] = prims::add_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < FP_LIMBS - 1; i++) r[i] = prims::addc_cc(a[i], b[i]);
+  r[FP_LIMBS - 1] = prims::addc(a[FP_LIMBS - 1], b[FP_LIMBS - 1]);
+}
+template <class B>
+__device__ __forceinline__ void wec_raw_sub(u32* r, const u32* a, const u32* b) {  // r = a - b, a >= b
+  r[0] = prims::sub_cc(a[0], b[0]);
+#pragma unroll
+  for (int i = 1; i < FP_LIMBS - 1; i++) r[i] = prims::subc_cc(a[i], b[i]);
+  r[FP_LIMBS - 1] = prims::subc(a[FP_LIMBS - 1], b[FP_LIMBS - 1]);
+}
+template <class B>
+__device__ __forceinline__ void wec_p_shl(u32* r, u32 j) {  // r = p << j, j < 22
+  typedef typename B::Params P;
+  r[0] = P::mod(0) << j;
+#pragma unroll
+  for (int i = 1; i < FP_LIMBS; i++) r[i] = __funnelshift_l(P::mod(i - 1), P::mod(i), j);
+}
+// d = a + k b (a absent when zero_a); k != 0 small; for k < 0: a + (p << j) - |k| b
+template <class B>
+__device__ __forceinline__ void wec_lin(u32* d, const u32* a, const u32* b, int k, u32 j, bool zero_a) {
+  u32 t[FP_LIMBS], x[FP_LIMBS];
+  const uint2* bq = reinterpret_cast<const uint2*>(b);
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    uint2 v = bq[i];
+    x[2 * i] = v.x;
+    x[2 * i + 1] = v.y;
+  }
+  const u32 ka = (u32)(k < 0 ? -k : k);
+#pragma unroll
+  for (int i = 0; i < FP_LIMBS; i++) t[i] = x[i];
+  for (int bit = 30 - __clz(ka); bit >= 0; bit--) {  // |k| b by double-and-add from the top bit (no iterations for |k| = 1)
+    wec_raw_add<B>(t, t, t);
+    if ((ka >> bit) & 1u) wec_raw_add<B>(t, t, x);
+  }
+  if (k < 0) {
+    wec_p_shl<B>(x, j);
+    wec_raw_sub<B>(t, x, t);
+  }
+  if (!zero_a) {
+    const uint2* aq = reinterpret_cast<const uint2*>(a);
+#pragma unroll
+    for (int i = 0; i < 5; i++) {
+      uint2 v = aq[i];
+      x[2 * i] = v.x;
+      x[2 * i + 1] = v.y;
+    }
+    wec_raw_add<B>(t, t, x);
+  }
+  uint2* dq = reinterpret_cast<uint2*>(d);
+#pragma unroll
+  for (int i = 0; i < 5; i++) dq[i] = make_uint2(t[2 * i], t[2 * i + 1]);
+}
+// d = a mod p for a < 2^m p: conditional subtraction of p << s for s = m - 1 .. 0
+template <class B>
+__device__ __forceinline__ void wec_red(u32* d, const u32* a, u32 m) {
+  u32 v[FP_LIMBS], ps[FP_LIMBS], t[FP_LIMBS];
+  const uint2* aq = reinterpret_cast<const uint2*>(a);
+#pragma unroll
+  for (int i = 0; i < 5; i++) {
+    uint2 w = aq[i];
+    v[2 * i] = w.x;
+    v[2 * i + 1] = w.y;
+  }
+  for (int s = (int)m - 1; s >= 0; s--) {
+    wec_p_shl<B>(ps, (u32)s);
+    t[0] = prims::sub_cc(v[0], ps[0]);
+#pragma unroll
+    for (int i = 1; i < FP_LIMBS; i++) t[i] = prims::subc_cc(v[i], ps[i]);
+    const u32 borrow = prims::subc(0, 0);  // 0xffffffff if v < p << s
+#pragma unroll
+    for (int i = 0; i < FP_LIMBS; i++) v[i] = borrow ? v[i] : t[i];
+  }
+  uint2* dq = reinterpret_cast<uint2*>(d);
+#pragma unroll
+  for (int i = 0; i < 5; i++) dq[i] = make_uint2(v[2 * i], v[2 * i + 1]);
+}
+
+// The interpreter: `rows` rows of G instructions (two words each); lane gl of the group executes instruction
+// [row * G + gl] and the group synchronises after every row (the generator never lets a row read a slot that another
+// lane of the same row writes, and gives all the instructions of a row the same opcode: no divergence inside a row).
+// One copy per base field and group size in a kernel (noinline): it holds the only inlined product.
 template <class B, int G>
 __device__ __noinline__ void wec_exec(const u32* __restrict__ prog, int rows, int gl, unsigned gmask, u32* xb, u32* yb,
                                       u32* tb) {
-  u32 wn = __ldg(prog + gl);
+  const uint2* pr = reinterpret_cast<const uint2*>(prog);
+  uint2 wn = __ldg(pr + gl);
   for (int r = 0; r < rows; r++) {
-    const u32 w = wn;
-    if (r + 1 < rows) wn = __ldg(prog + (r + 1) * G + gl);  // the next row's word travels while this row computes
-    const u32 op = (w >> 24) & 127u;
+    const uint2 w = wn;
+    if (r + 1 < rows) wn = __ldg(pr + (r + 1) * G + gl);  // the next row's words travel while this row computes
+    const u32 op = w.x >> 28;
     if (op != WEC_NOP) {
-      u32* d = wec_slot((w >> 16) & 255u, xb, yb, tb);
-      const B a = wec_ld<B>(wec_slot((w >> 8) & 255u, xb, yb, tb));
-      B res;
-      switch (op) {
-        case WEC_MUL: res = a * wec_ld<B>(wec_slot(w & 255u, xb, yb, tb)); break;
-        case WEC_ADD: res = a + wec_ld<B>(wec_slot(w & 255u, xb, yb, tb)); break;
-        case WEC_SUB: res = a - wec_ld<B>(wec_slot(w & 255u, xb, yb, tb)); break;
-        case WEC_SUBD: {
-          const B b = wec_ld<B>(wec_slot(w & 255u, xb, yb, tb));
-          res = a - b - b;
-          break;
-        }
-        case WEC_DBL: res = a.dbl(); break;
-        case WEC_NEG: res = a.neg(); break;
-        case WEC_MULK: {  // small constant k >= 3: double-and-add from its top bit
-          const u32 k = w & 255u;
-          res = a;
-          for (int bit = 30 - __clz(k); bit >= 0; bit--) {
-            res = res.dbl();
-            if ((k >> bit) & 1u) res = res + a;
-          }
-          break;
-        }
-        case WEC_INV: res = a.inverse(); break;
-        default: res = a; break;  // WEC_CPY
+      u32* d = wec_slot((w.x >> 18) & 511u, xb, yb, tb);
+      u32* a = wec_slot((w.x >> 9) & 511u, xb, yb, tb);
+      u32* b = wec_slot(w.x & 511u, xb, yb, tb);
+      if (op == WEC_MUL) {
+        wec_st<B>(d, wec_ld<B>(a) * wec_ld<B>(b));
+      } else if (op == WEC_LIN) {
+        const int k = (int)(signed char)(w.y & 0xffu);
+        wec_lin<B>(d, a, b, k, (w.y >> 8) & 31u, (w.y >> 18) & 1u);
+      } else if (op == WEC_RED) {
+        wec_red<B>(d, a, (w.y >> 13) & 31u);
+      } else if (op == WEC_INV) {
+        wec_st<B>(d, wec_ld<B>(a).inverse());
+      } else {  // WEC_CPY
+        wec_st<B>(d, wec_ld<B>(a));
       }
-      wec_st<B>(d, res);
     }
     __syncwarp(gmask);
   }

@@ -62,6 +62,32 @@ def test_field_random_vs_oracle(emu):
                 assert np.array_equal(out, co.field_op(field, op, xs[i], ys[i]))
 
 
+def test_product_of_unreduced_operands(emu):
+    """The lane-cooperative group law (wec.cuh) feeds the Montgomery product operands that were never reduced:
+    a + k1 p and b + k2 p with (k1 + 1)(k2 + 1) <= 2^20.  The product must still be the canonical a b / R mod p: the
+    pre-subtraction value is < p (1 + 2^20 p / 2^320) < 2 p, and no row accumulator leaves its ten limbs."""
+    for field in (0, 1):
+        p = codec.FIELD_P[field]
+        xs = codec.random_field_elems(60, field, 41)
+        ys = codec.random_field_elems(60, field, 42)
+        mults = [(0, 0), (1, 0), (1, 1), (1023, 1023), ((1 << 20) - 1, 0), (0, (1 << 20) - 1), (2047, 511), (292, 292),
+                 (54, 2515)]
+        for i in range(60):
+            xi, yi = codec.limbs_to_int(xs[i]), codec.limbs_to_int(ys[i])
+            want = co.field_op(field, 2, xs[i], ys[i])
+            for k1, k2 in mults:
+                a = codec.int_to_limbs(xi + k1 * p)
+                b = codec.int_to_limbs(yi + k2 * p)
+                out = np.zeros(5, dtype=np.uint64)
+                emu.emu_fp_op(field, 2, _p(a), _p(b), _p(out))
+                assert np.array_equal(out, want), (field, i, k1, k2)
+        # extreme operands: the largest values below 2^10 p
+        big = codec.int_to_limbs(1024 * p - 1)
+        out = np.zeros(5, dtype=np.uint64)
+        emu.emu_fp_op(field, 2, _p(big), _p(big), _p(out))
+        assert np.array_equal(out, co.field_op(field, 2, codec.int_to_limbs(p - 1), codec.int_to_limbs(p - 1)))
+
+
 def test_inverse_binary_gcd(emu):
     """Fp::inverse (binary extended Euclid on the Montgomery representative) == Fermat's a^(p-2) == the oracle, on
     edge values (0, 1, 2, p - 1, powers of two, all-ones limbs) and random elements."""

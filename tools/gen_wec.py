@@ -10,12 +10,21 @@ of base-field operations and list-scheduled into steps; in a step every lane exe
 instruction on operands in shared memory (pcd_b200/csrc/wec.cuh interprets the schedule).  A group addition then costs
 its multiplicative DEPTH (4..5 products) instead of its product COUNT.
 
-Instruction word: last << 31 | op << 24 | dst << 16 | a << 8 | b.  A program is a sequence of ROWS of G words (one per
-lane); a lane executes its words in order and the group synchronises after every row whose words carry the `last`
-bit, so that a lane can run a chain of dependent linear instructions on its own results without a barrier in
-between.  Slot byte: 0..15 = X (the point updated in place), 16..31 = Y (the point added), 32.. = T (temporaries; the
-first ones carry values between the two halves of an addition).  One slot = one base-field element (ten u32 words,
-Montgomery form).
+Instruction set (one instruction per lane and ROW, the group synchronises after every row; all the instructions of a
+row have the same opcode, so the lanes of a warp never diverge inside a row):
+  MUL  d = a * b     Montgomery product; operands may be UNREDUCED (< 2^10 p each), the result is canonical (< p)
+  LIN  d = a + k b   k a small signed constant; NO reduction: the generator tracks for every value a bound m (value
+                     < m p) and turns a negative k into + (2^j p - |k| b) with 2^j >= |k| m_b, so nothing ever
+                     underflows or needs a conditional subtraction; a may be the constant 0
+  RED  d = a mod p   canonical representative of a value < 2^m p (m conditional subtractions): only where a value
+                     leaves the program (outputs) or would exceed the product's operand range
+  INV  d = 1 / a     (binary extended Euclid, fp.cuh)
+Additions, subtractions, doublings, negations and multiplications by the small curve / non-residue constants of the
+formulas all lower to LIN, and a `LIN(x, k1 * y)` whose y is itself `k2 * u` is fused into `LIN(x, (k1 k2) u)`.
+Instruction = two u32 words: w0 = op << 28 | dst << 18 | a << 9 | b;  w1 = (k & 0xff) | j << 8 | m << 13 | zero_a << 18.
+Slot: 0..15 = X (the point updated in place), 16..31 = Y (the point added), 32.. = T (temporaries; the first ones
+carry values between the two halves of an addition).  One slot = one base-field element (ten u32 words, Montgomery
+form).
 
   python tools/gen_wec.py            # rewrite pcd_b200/csrc/wec_programs.cuh
   python tools/gen_wec.py --check    # exit 1 if the committed header differs from what this script generates
@@ -31,8 +40,10 @@ import sys
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 OUT = os.path.join(ROOT, "pcd_b200", "csrc", "wec_programs.cuh")
 
-OP_NOP, OP_MUL, OP_ADD, OP_SUB, OP_DBL, OP_NEG, OP_CPY, OP_MULK, OP_INV, OP_SUBD = range(10)
-OP_NAMES = ["nop", "mul", "add", "sub", "dbl", "neg", "cpy", "mulk", "inv", "subd"]
+OP_NOP, OP_MUL, OP_LIN, OP_RED, OP_INV, OP_CPY = range(6)
+OP_NAMES = ["nop", "mul", "lin", "red", "inv", "cpy"]
+MUL_BOUND = 1 << 20   # product of the operands' bounds a Montgomery product accepts (T < p (1 + 2^-2) < 2 p)
+MAX_BOUND = 1 << 21   # a value must stay below 2^21 p < 2^320
 REG_X, REG_Y, REG_T = 0, 1, 2
 MAX_T = 224
 X_BASE, Y_BASE, T_BASE = 0, 16, 32
@@ -140,9 +151,14 @@ class E:
             c1 = (a[0] + a[1]) * (b[0] + b[1]) - v0 - v1
             return E([v0 + v1.mulk(nr), c1], nr)
         v0, v1, v2 = a[0] * b[0], a[1] * b[1], a[2] * b[2]  # Karatsuba, 6 products
-        c0 = v0 + ((a[1] + a[2]) * (b[1] + b[2]) - v1 - v2).mulk(nr)
-        c1 = (a[0] + a[1]) * (b[0] + b[1]) - v0 - v1 + v2.mulk(nr)
-        c2 = (a[0] + a[2]) * (b[0] + b[2]) - v0 - v2 + v1
+        w12, w01, w02 = (a[1] + a[2]) * (b[1] + b[2]), (a[0] + a[1]) * (b[0] + b[1]), (a[0] + a[2]) * (b[0] + b[2])
+        # the same sums as fpx.cuh, associated as balanced trees (two dependent linear rows instead of four):
+        #   c0 = v0 + nr (w12 - v1 - v2) = (v0 - nr v2) + nr (w12 - v1)
+        #   c1 = w01 - v0 - v1 + nr v2   = (w01 - v0) - (v1 - nr v2)
+        #   c2 = w02 - v0 - v2 + v1      = (w02 - v0) + (v1 - v2)
+        c0 = (v0 - v2.mulk(nr)) + (w12 - v1).mulk(nr)
+        c1 = (w01 - v0) - (v1 - v2.mulk(nr))
+        c2 = (w02 - v0) + (v1 - v2)
         return E([c0, c1, c2], nr)
 
     def sqr(self):
@@ -159,7 +175,7 @@ class E:
         s2 = t2 * t2
         s3 = (a[1] * a[2]).dbl()
         s4 = a[2] * a[2]
-        return E([s0 + s3.mulk(nr), s1 + s4.mulk(nr), s1 + s2 + s3 - s0 - s4], nr)
+        return E([s0 + s3.mulk(nr), s1 + s4.mulk(nr), (s1 + s2) + (s3 - (s0 + s4))], nr)
 
     def inv(self):
         a, nr = self.c, self.nr
@@ -282,13 +298,20 @@ def trace(curve, prog):
 PROGRAMS = ["add1", "add2", "madd1", "madd2", "dbl", "toaff"]
 
 
-# ---- scheduling ------------------------------------------------------------------------------------------------
-def schedule(g, outs, G):
-    """List scheduling by dependency level: a step holds up to G mutually independent instructions, all linear or all
-    products / inversions (a product step costs a full Montgomery product whatever the number of lanes that multiply,
-    so products wait until no linear instruction is ready and then go together, deepest remaining chain first).
-    Returns a list of steps (kind, lanes), lanes = list of one-instruction chains."""
-    nodes = g.nodes
+# ---- lowering: formulas -> MUL / LIN / RED / INV with bounds -------------------------------------------------------
+class LNode:
+    __slots__ = ("op", "a", "b", "k", "j", "m", "bound", "id", "pin")
+
+    def __init__(self, lg, op, a=None, b=None, k=0, pin=None):
+        self.op, self.a, self.b, self.k, self.pin = op, a, b, k, pin
+        self.j = self.m = 0
+        self.bound = 1
+        self.id = len(lg)
+        lg.append(self)
+
+
+def lower(g, outs):
+    """traced DAG -> (list of LNode, outputs); only nodes an output depends on are lowered"""
     needed = set()
     stack = [n for n, _ in outs]
     while stack:
@@ -299,111 +322,227 @@ def schedule(g, outs, G):
         for o in (n.a, n.b):
             if o is not None:
                 stack.append(o)
-    users = {i: [] for i in needed}
+    uses = {}
     for i in needed:
-        n = nodes[i]
+        n = g.nodes[i]
         for o in (n.a, n.b):
             if o is not None:
-                users[o.id].append(i)
+                uses[o.id] = uses.get(o.id, 0) + 1
+    for n, _ in outs:
+        uses[n.id] = uses.get(n.id, 0) + 1
+    lg = []
+    m = {}  # traced node id -> LNode
+    scaled = {}  # LNode id -> (source LNode, k): the node is k * source with a == zero
+
+    def lin(a, b, k):
+        """a + k b with b possibly itself a pure scaling used once"""
+        if b.id in scaled and scaled[b.id][2] == 1 and abs(k * scaled[b.id][1]) <= 127:
+            src, k2, _ = scaled[b.id]
+            b, k = src, k * k2
+            # the fused scaling node stays in lg but is no longer needed: pruned by the scheduler's reachability
+        n = LNode(lg, "lin", a, b, k)
+        return n
+
+    for i in sorted(needed):
+        t = g.nodes[i]
+        if t.op == "in":
+            m[i] = LNode(lg, "in", pin=t.pin)
+        elif t.op == "mul":
+            m[i] = LNode(lg, "mul", m[t.a.id], m[t.b.id])
+        elif t.op == "inv":
+            m[i] = LNode(lg, "inv", m[t.a.id])
+        elif t.op == "add":
+            a, b = m[t.a.id], m[t.b.id]
+            if a.id in scaled and scaled[a.id][2] == 1 and b.id not in scaled:
+                a, b = b, a  # put the scaling on the b side so that it fuses
+            m[i] = lin(a, b, 1)
+        elif t.op == "sub":
+            m[i] = lin(m[t.a.id], m[t.b.id], -1)
+        elif t.op == "subd":
+            m[i] = lin(m[t.a.id], m[t.b.id], -2)
+        elif t.op in ("dbl", "neg", "mulk"):
+            k = {"dbl": 2, "neg": -1}.get(t.op, t.k)
+            src = m[t.a.id]
+            if src.id in scaled and scaled[src.id][2] == 1 and abs(k * scaled[src.id][1]) <= 127:
+                k, src = k * scaled[src.id][1], scaled[src.id][0]
+            n = LNode(lg, "lin", None, src, k)
+            scaled[n.id] = (src, k, uses.get(i, 0))
+            m[i] = n
+        else:
+            raise ValueError(t.op)
+    louts = [(m[n.id], slot) for n, slot in outs]
+    return lg, louts
+
+
+def finalize_bounds(lg, louts):
+    """bounds in topological order; RED nodes where a product's operands are too large and on every output that is not
+    canonical already.  Returns (lg, louts) with REDs appended / operands rewired."""
+    red_of = {}
+
+    def red(n):
+        if n.bound <= 1:
+            return n
+        if n.id not in red_of:
+            r = LNode(lg, "red", n)
+            r.m = max(1, (n.bound - 1).bit_length())
+            r.bound = 1
+            red_of[n.id] = r
+        return red_of[n.id]
+
+    for n in list(lg):
+        if n.op == "in":
+            n.bound = 1
+        elif n.op == "mul":
+            while n.a.bound * n.b.bound > MUL_BOUND:
+                if n.a.bound >= n.b.bound:
+                    n.a = red(n.a)
+                else:
+                    n.b = red(n.b)
+            n.bound = 1
+        elif n.op == "inv":
+            n.a = red(n.a)
+            n.bound = 1
+        elif n.op == "lin":
+            kb = abs(n.k) * n.b.bound
+            ab = n.a.bound if n.a is not None else 0
+            if n.k < 0:
+                n.j = max(0, (kb - 1).bit_length())  # 2^j >= |k| m_b
+                n.bound = ab + (1 << n.j)
+            else:
+                n.bound = ab + kb
+            assert n.bound < MAX_BOUND and n.j < 32, "bound overflow"
+    louts = [(red(n), slot) for n, slot in louts]
+    # REDs were appended after their sources but possibly after their users in id order: re-sort topologically
+    order, seen = [], set()
+
+    def visit(n):
+        if n.id in seen:
+            return
+        seen.add(n.id)
+        for o in (n.a, n.b):
+            if o is not None:
+                visit(o)
+        order.append(n)
+
+    for n, _ in louts:
+        visit(n)
+    for k, n in enumerate(order):
+        n.id = k
+    return order, louts
+
+
+# ---- scheduling ------------------------------------------------------------------------------------------------
+KIND = {"mul": "mul", "inv": "inv", "lin": "lin", "red": "red"}
+
+
+def schedule(lg, louts, G):
+    """List scheduling by dependency level.  Every row holds instructions of ONE opcode (no divergence inside a row):
+    ready LIN instructions first, then RED, then products (up to G, deepest remaining chain first), an inversion alone."""
+    users = {n.id: [] for n in lg}
+    for n in lg:
+        for o in (n.a, n.b):
+            if o is not None:
+                users[o.id].append(n.id)
+    by_id = {n.id: n for n in lg}
     height = {}
 
     def h(i):
         if i not in height:
-            n = nodes[i]
+            n = by_id[i]
             w = 10 if n.op in ("mul", "inv") else 1
             height[i] = w + max([h(u) for u in users[i]], default=0)
         return height[i]
 
-    is_prod = lambda i: nodes[i].op in ("mul", "inv")
-    done = {i for i in needed if nodes[i].op == "in"}
-    todo = [i for i in sorted(needed) if nodes[i].op != "in"]
-    steps = []
-    ready = lambda i: all(o is None or o.id in done for o in (nodes[i].a, nodes[i].b))
+    done = {n.id for n in lg if n.op == "in"}
+    todo = [n.id for n in lg if n.op != "in"]
+    ready = lambda i: all(o is None or o.id in done for o in (by_id[i].a, by_id[i].b))
+    rows = []
     while todo:
-        lin = sorted((i for i in todo if not is_prod(i) and ready(i)), key=lambda i: -h(i))
-        if lin:
-            pick, kind = lin[:G], "lin"
-        else:
-            pick, kind = sorted((i for i in todo if is_prod(i) and ready(i)), key=lambda i: -h(i))[:G], "mul"
+        pick = None
+        # reductions that feed a product go as soon as they are ready; the outputs' reductions wait until nothing
+        # else is, so that they share one row
+        for kind, want_users in (("lin", None), ("red", True), ("mul", None), ("inv", None), ("red", False)):
+            cand = sorted((i for i in todo if by_id[i].op == kind and ready(i) and
+                           (want_users is None or bool(users[i]) == want_users)), key=lambda i: -h(i))
+            if cand:
+                pick = cand[:1] if kind == "inv" else cand[:G]
+                rows.append((kind, pick))
+                break
         assert pick, "scheduler stuck"
-        steps.append((kind, [[i] for i in pick]))
         done.update(pick)
         todo = [i for i in todo if i not in done]
-    return steps
+    return rows, by_id
 
 
-def allocate(g, outs, steps, G):
+def allocate(lg, louts, rows, by_id, G):
     """Slots: inputs are pinned; an output goes straight to its slot when the value living there is dead, else to a
-    temporary with a copy at the end; a temporary is reused after the STEP of its last use (a slot is never read and
-    written by different lanes inside one step).  Returns rows: list of (row of G instruction tuples | None, last)."""
-    nodes = g.nodes
+    temporary with a copy row at the end; a temporary is reused after the ROW of its last use (a slot is never read and
+    written by different lanes inside one row)."""
     last_use = {}
-    for s, (_, lanes) in enumerate(steps):
-        for lane in lanes:
-            for i in lane:
-                n = nodes[i]
-                for o in (n.a, n.b):
-                    if o is not None:
-                        last_use[o.id] = s
+    for s, (_, ids) in enumerate(rows):
+        for i in ids:
+            n = by_id[i]
+            for o in (n.a, n.b):
+                if o is not None:
+                    last_use[o.id] = s
     out_of = {}
-    for n, slot in outs:
+    for n, slot in louts:
         out_of.setdefault(n.id, []).append(slot)
-    out_slots = {slot for _, slot in outs}
+    out_slots = {slot for _, slot in louts}
     pinned_until = {}
-    for n in nodes:
+    for n in lg:
         if n.op == "in":
             pinned_until[n.pin] = max(pinned_until.get(n.pin, -1), last_use.get(n.id, -1))
-    loc = {n.id: n.pin for n in nodes if n.op == "in"}
-    t_pinned = {n.pin[1] for n in nodes if n.op == "in" and n.pin[0] == REG_T}
+    loc = {n.id: n.pin for n in lg if n.op == "in"}
+    t_pinned = {n.pin[1] for n in lg if n.op == "in" and n.pin[0] == REG_T}
     t_pinned |= {s[1] for s in out_slots if s[0] == REG_T}
     free_t = [i for i in range(MAX_T) if i not in t_pinned]
     release = {}
     final_copies = []
     max_t = max(t_pinned, default=-1)
-    rows = []
-    for s, (kind, lanes) in enumerate(steps):
-        depth = max(len(lane) for lane in lanes)
-        step_rows = [[None] * G for _ in range(depth)]
-        for li, lane in enumerate(lanes):
-            for ri, i in enumerate(lane):
-                n = nodes[i]
-                dst = None
-                for slot in out_of.get(i, []):
-                    if pinned_until.get(slot, -1) < s and dst is None:
-                        dst = slot
-                        pinned_until[slot] = 10 ** 9
-                if dst is None:
-                    assert free_t, "out of temporaries"
-                    t = free_t.pop(0)
-                    max_t = max(max_t, t)
-                    dst = (REG_T, t)
-                    if i not in out_of:
-                        release.setdefault(last_use.get(i, s), []).append(t)
-                loc[i] = dst
-                for slot in out_of.get(i, []):
-                    if slot != dst:
-                        final_copies.append((slot, i))
-                step_rows[ri][li] = (n.op, dst, loc[n.a.id] if n.a is not None else (0, 0),
-                                     loc[n.b.id] if n.b is not None else (0, 0), n.k)
-        for ri, r in enumerate(step_rows):
-            rows.append((r, ri == depth - 1))
+    out_rows = []
+    for s, (kind, ids) in enumerate(rows):
+        row = []
+        for i in ids:
+            n = by_id[i]
+            dst = None
+            for slot in out_of.get(i, []):
+                if pinned_until.get(slot, -1) < s and dst is None:
+                    dst = slot
+                    pinned_until[slot] = 10 ** 9
+            if dst is None:
+                assert free_t, "out of temporaries"
+                t = free_t.pop(0)
+                max_t = max(max_t, t)
+                dst = (REG_T, t)
+                if i not in out_of:
+                    release.setdefault(last_use.get(i, s), []).append(t)
+            loc[i] = dst
+            for slot in out_of.get(i, []):
+                if slot != dst:
+                    final_copies.append((slot, i))
+            row.append(dict(op=kind, d=dst, a=loc[n.a.id] if n.a is not None else None,
+                            b=loc[n.b.id] if n.b is not None else None, k=n.k, j=n.j, m=n.m))
+        out_rows.append((kind, row))
         for t in release.pop(s, []):
             free_t.append(t)
         free_t.sort()
-    for n, slot in outs:
+    for n, slot in louts:
         if loc[n.id] != slot and (slot, n.id) not in final_copies:
             final_copies.append((slot, n.id))
     if final_copies:
         srcs = {loc[i] for _, i in final_copies}
-        dsts = [s for s, _ in final_copies]
+        dsts = [sl for sl, _ in final_copies]
         assert not (srcs & set(dsts)), "final copies alias"
         for c in range(0, len(final_copies), G):
-            chunk = [("cpy", slot, loc[i], (0, 0), 0) for slot, i in final_copies[c:c + G]]
-            rows.append((chunk + [None] * (G - len(chunk)), True))
-    return rows, max_t + 1
+            out_rows.append(("cpy", [dict(op="cpy", d=slot, a=loc[i], b=None, k=0, j=0, m=0)
+                                     for slot, i in final_copies[c:c + G]]))
+    return out_rows, max_t + 1
 
 
 def enc_slot(s):
+    if s is None:
+        return 0
     base = {REG_X: X_BASE, REG_Y: Y_BASE, REG_T: T_BASE}[s[0]]
     lim = {REG_X: 16, REG_Y: 16, REG_T: MAX_T}[s[0]]
     assert 0 <= s[1] < lim
@@ -411,90 +550,105 @@ def enc_slot(s):
 
 
 def encode(rows, G):
+    """two u32 per lane and row: [row][lane][2]"""
     words = []
     opc = {n: i for i, n in enumerate(OP_NAMES)}
-    for row, last in rows:
-        assert len(row) == G
+    for kind, row in rows:
+        assert len(row) <= G
         for ins in row:
-            w = 0
-            if ins is not None:
-                op, d, a, b, k = ins
-                bb = k if op == "mulk" else enc_slot(b)
-                assert 0 <= bb < 256
-                w = (opc[op] << 24) | (enc_slot(d) << 16) | (enc_slot(a) << 8) | bb
-            words.append(w | (0x80000000 if last else 0))
+            w0 = (opc[ins["op"]] << 28) | (enc_slot(ins["d"]) << 18) | (enc_slot(ins["a"]) << 9) | enc_slot(ins["b"])
+            assert -128 <= ins["k"] <= 127 and 0 <= ins["j"] < 32 and 0 <= ins["m"] < 32
+            zero_a = 1 if (ins["op"] == "lin" and ins["a"] is None) else 0
+            w1 = (ins["k"] & 0xff) | (ins["j"] << 8) | (ins["m"] << 13) | (zero_a << 18)
+            words += [w0, w1]
+        words += [0, 0] * (G - len(row))
     return words
 
 
 def build(curve, prog, G=None):
     G = G or CURVES[curve]["G"]
     g, outs = trace(curve, prog)
-    steps = schedule(g, outs, G)
-    rows, nt = allocate(g, outs, steps, G)
-    return dict(curve=curve, prog=prog, G=G, rows=rows, words=encode(rows, G), nrows=len(rows), ntemps=nt,
-                nsteps=sum(1 for _, last in rows if last),
-                mul_steps=sum(1 for kind, _ in steps if kind == "mul"),
-                lin_rows=sum(max(len(l) for l in lanes) for kind, lanes in steps if kind == "lin"))
+    lg, louts = lower(g, outs)
+    lg, louts = finalize_bounds(lg, louts)
+    rows, by_id = schedule(lg, louts, G)
+    arows, nt = allocate(lg, louts, rows, by_id, G)
+    count = lambda k: sum(1 for kind, _ in arows if kind == k)
+    return dict(curve=curve, prog=prog, G=G, rows=arows, words=encode(arows, G), nrows=len(arows), ntemps=nt,
+                mul_rows=count("mul") + count("inv"), lin_rows=count("lin") + count("cpy"), red_rows=count("red"),
+                max_bound=max(n.bound for n in lg))
 
 
 # ---- Python interpreter (tests) ----------------------------------------------------------------------------------
 def interpret(built, p, X, Y, T=None):
-    """Run a schedule on Python integers mod p.  X, Y, T: lists of ints (modified in place).  Also checks the
-    hazards the GPU interpreter relies on: inside one step (rows up to a `last` row) no slot written by a lane is read
-    or written by another lane."""
+    """Run a schedule on Python integers with the EXACT semantics of the GPU interpreter: LIN does not reduce, RED
+    subtracts 2^s p conditionally for s = m-1 .. 0, MUL takes unreduced operands and returns the canonical product.
+    Checks the invariants the GPU relies on: no LIN underflows, every value stays below 2^320, a product's operands
+    are within its range, RED's input is below 2^m p, and inside a row no slot written by one lane is read or written
+    by another.  X, Y, T: lists of ints (modified in place)."""
     G = built["G"]
     T = T if T is not None else [0] * MAX_T
     X += [0] * (16 - len(X))
     Y += [0] * (16 - len(Y))
     mem = X + Y + T
-
     words = built["words"]
-    step_reads = [set() for _ in range(G)]
-    step_writes = [set() for _ in range(G)]
     for r in range(built["nrows"]):
-        last = False
+        reads = [set() for _ in range(G)]
+        writes = [set() for _ in range(G)]
+        pending = []
+        ops = set()
         for lane in range(G):
-            w = words[r * G + lane]
-            last = bool(w >> 31)
-            op, d, a, b = (w >> 24) & 127, (w >> 16) & 255, (w >> 8) & 255, w & 255
+            w0, w1 = words[2 * (r * G + lane)], words[2 * (r * G + lane) + 1]
+            op, d, a, b = w0 >> 28, (w0 >> 18) & 511, (w0 >> 9) & 511, w0 & 511
             if op == OP_NOP:
                 continue
-            av = mem[a]
-            step_reads[lane].add(a)
-            if op in (OP_MUL, OP_ADD, OP_SUB, OP_SUBD):
-                bv = mem[b]
-                step_reads[lane].add(b)
+            ops.add(op)
+            k = w1 & 0xff
+            k = k - 256 if k >= 128 else k
+            j, m, zero_a = (w1 >> 8) & 31, (w1 >> 13) & 31, (w1 >> 18) & 1
             if op == OP_MUL:
+                av, bv = mem[a], mem[b]
+                reads[lane] |= {a, b}
+                assert av * bv < (MUL_BOUND << 2) * p * p, "product operands out of range"
                 res = av * bv % p
-            elif op == OP_ADD:
-                res = (av + bv) % p
-            elif op == OP_SUB:
-                res = (av - bv) % p
-            elif op == OP_DBL:
-                res = 2 * av % p
-            elif op == OP_NEG:
-                res = (-av) % p
-            elif op == OP_CPY:
-                res = av
-            elif op == OP_MULK:
-                res = av * b % p
+            elif op == OP_LIN:
+                bv = mem[b]
+                reads[lane].add(b)
+                t = abs(k) * bv
+                if k < 0:
+                    t = (p << j) - t
+                    assert t >= 0, "LIN underflow"
+                if not zero_a:
+                    t += mem[a]
+                    reads[lane].add(a)
+                assert t < (1 << 320), "LIN overflow"
+                res = t
+            elif op == OP_RED:
+                v = mem[a]
+                reads[lane].add(a)
+                assert v < (p << m), "RED input too large"
+                for sft in range(m - 1, -1, -1):
+                    if v >= (p << sft):
+                        v -= p << sft
+                assert v < p
+                res = v
             elif op == OP_INV:
-                res = pow(av, p - 2, p)
-            elif op == OP_SUBD:
-                res = (av - 2 * bv) % p
+                reads[lane].add(a)
+                assert mem[a] < p
+                res = pow(mem[a], p - 2, p)
+            elif op == OP_CPY:
+                reads[lane].add(a)
+                res = mem[a]
             else:
                 raise ValueError(op)
-            # lanes run at their own pace inside a step: executing them one after the other is one legal order, and
-            # the hazard check below makes every order equivalent
+            pending.append((d, res))
+            writes[lane].add(d)
+        assert len(ops) <= 1, "mixed opcodes in a row"
+        for l1 in range(G):
+            for l2 in range(G):
+                if l1 != l2:
+                    assert not (writes[l1] & (reads[l2] | writes[l2])), "cross-lane hazard in a row"
+        for d, res in pending:
             mem[d] = res
-            step_writes[lane].add(d)
-        if last:
-            for l1 in range(G):
-                for l2 in range(G):
-                    if l1 != l2:
-                        assert not (step_writes[l1] & (step_reads[l2] | step_writes[l2])), "cross-lane hazard in a step"
-            step_reads = [set() for _ in range(G)]
-            step_writes = [set() for _ in range(G)]
     X[:] = mem[0:16]
     Y[:] = mem[16:32]
     T[:] = mem[32:]
@@ -504,9 +658,9 @@ def interpret(built, p, X, Y, T=None):
 # ---- header ------------------------------------------------------------------------------------------------------
 def header():
     lines = ["// GENERATED by tools/gen_wec.py -- do not edit (python tools/gen_wec.py --check verifies it is current).",
-             "// Lane schedules of the warp-cooperative group law (wec.cuh): one u32 per lane and row,",
-             "// last << 31 | op << 24 | dst << 16 | a << 8 | b; slots 0..15 X, 16..31 Y, 32.. T; ops: " +
-             ", ".join("%d %s" % (i, n) for i, n in enumerate(OP_NAMES)) + ".",
+             "// Lane schedules of the warp-cooperative group law (wec.cuh): two u32 per lane and row,",
+             "// w0 = op << 28 | dst << 18 | a << 9 | b;  w1 = (k & 0xff) | j << 8 | m << 13 | zero_a << 18;",
+             "// slots 0..15 X, 16..31 Y, 32.. T; ops: " + ", ".join("%d %s" % (i, n) for i, n in enumerate(OP_NAMES)) + ".",
              "#pragma once", "#include \"prims.cuh\"", ""]
     summary = []
     for curve in sorted(CURVES):
@@ -516,15 +670,16 @@ def header():
             b = build(curve, prog)
             nt = max(nt, b["ntemps"])
             name = "WEC_%s_%s" % (cv["name"], prog.upper())
-            lines.append("// %s %s: %d rows in %d steps (%d product steps, %d linear rows), %d temporaries, %d lanes" %
-                         (cv["name"], prog, b["nrows"], b["nsteps"], b["mul_steps"], b["lin_rows"], b["ntemps"], b["G"]))
+            lines.append("// %s %s: %d rows (%d product, %d linear, %d reduction), %d temporaries, %d lanes, largest bound %d p" %
+                         (cv["name"], prog, b["nrows"], b["mul_rows"], b["lin_rows"], b["red_rows"], b["ntemps"], b["G"],
+                          b["max_bound"]))
             lines.append("__device__ const u32 %s[%d] = {" % (name, len(b["words"])))
             ws = b["words"]
             for c in range(0, len(ws), 8):
                 lines.append("  " + ", ".join("0x%08xu" % w for w in ws[c:c + 8]) + ",")
             lines.append("};")
             lines.append("static constexpr int %s_ROWS = %d;" % (name, b["nrows"]))
-            summary.append((cv["name"], prog, b["nrows"], b["nsteps"], b["mul_steps"], b["lin_rows"], b["ntemps"]))
+            summary.append((cv["name"], prog, b["nrows"], b["mul_rows"], b["lin_rows"], b["red_rows"], b["ntemps"], b["max_bound"]))
         lines.append("static constexpr int WEC_%s_NTEMPS = %d;" % (cv["name"], nt))
         lines.append("static constexpr int WEC_%s_G = %d;" % (cv["name"], cv["G"]))
         lines.append("")
@@ -542,7 +697,7 @@ def main():
     with open(OUT, "w") as f:
         f.write(text)
     for row in summary:
-        print("%-8s %-6s rows %3d  steps %2d  product steps %2d  linear rows %2d  temps %2d" % row)
+        print("%-8s %-6s rows %3d  product %2d  linear %2d  reduction %2d  temps %3d  max bound %5d p" % row)
 
 
 if __name__ == "__main__":
