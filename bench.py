@@ -39,8 +39,9 @@ MODMUL_IMADS = 210            # 10-limb Montgomery product
 MADD_MODMULS = {1: 10, 2: 28, 3: 58}  # XYZZ mixed add 8M + 2S in Fq / Fq2 (M=3,S=2) / Fq3 (M=6,S=5)
 METRIC = "pcd_step_proofs_per_sec"
 UNIT = "PCD steps/s"
-PROF_NAMES = ["msm_digits_sort", "msm_accumulate_g1", "msm_accumulate_g2", "msm_reduce", "msm_horner", "ntt", "spmv_qap",
-              "assemble"]
+PROF_NAMES = ["msm_digits_sort", "msm_accumulate_g1", "msm_accumulate_g2_fq2", "msm_reduce", "msm_horner", "ntt", "spmv_qap",
+              "assemble", "msm_accumulate_g2_fq3", "msm_accumulate_small"]
+PROF_ACC = {1: 1, 2: 2, 8: 3}  # accumulation classes of the large MSMs -> extension degree of the coordinates
 
 
 def workload_config(args):
@@ -410,18 +411,13 @@ def run_gpu(args, rank, local_rank, world):
     # ---- roofline of the dominant kernel class ----------------------------------------------------------------
     total_ms = sum(prof["ms"]) or 1.0
     shares = {PROF_NAMES[i]: round(prof["ms"][i] / total_ms, 4) for i in range(NC)}
-    dom = max((1, 2), key=lambda i: prof["ms"][i])
-    # products per bucket entry of the dominant class: G1 always Fq (10); the G2 class mixes Fq2 (main) and Fq3 (helper)
-    # entries -- weighted by the entries each proof contributed is not available per curve, so the G2 class is quoted
-    # with the Fq2 figure for the main-proof share and the Fq3 figure for the helper share through their unit counts
-    if dom == 1:
-        imads = prof["units"][1] * MADD_MODMULS[1] * MODMUL_IMADS
-        work = "bucket entries x 10 Montgomery products (XYZZ mixed addition 8M + 2S over Fq) x 210 IMAD"
-    else:
-        e2, e3 = g2_entry_split(step_plan(args), prof["units"][2])
-        imads = (e2 * MADD_MODMULS[2] + e3 * MADD_MODMULS[3]) * MODMUL_IMADS
-        work = ("bucket entries x (28 products over Fq2 [MNT4 G2] | 58 over Fq3 [MNT6 G2], split by the proofs' point "
-                "counts) x 210 IMAD")
+    # the dominant kernel: bucket accumulation of the large MSMs, per coordinate field (the default-circuit proofs'
+    # MSMs of ~10^3 points are a latency-bound regime of their own and are reported as their own class)
+    dom = max(PROF_ACC, key=lambda i: prof["ms"][i])
+    deg = PROF_ACC[dom]
+    imads = prof["units"][dom] * MADD_MODMULS[deg] * MODMUL_IMADS
+    work = "bucket entries x %d Montgomery products (XYZZ mixed addition 8M + 2S over %s) x %d IMAD" % (
+        MADD_MODMULS[deg], {1: "Fq", 2: "Fq2", 3: "Fq3"}[deg], MODMUL_IMADS)
     achieved = imads / (prof["ms"][dom] * 1e-3) / 1e12 if prof["ms"][dom] > 0 else 0.0
     hbm_peak, hbm_src = load_peaks()
     traffic = None
@@ -430,6 +426,9 @@ def run_gpu(args, rank, local_rank, world):
             traffic = json.load(f).get(PROF_NAMES[dom], {}).get("bytes_per_launch")
     except Exception:
         pass
+    others = {PROF_NAMES[i]: {"frac": (prof["units"][i] * MADD_MODMULS[PROF_ACC[i]] * MODMUL_IMADS / (prof["ms"][i] * 1e-3)
+                                        / imad_peak) if prof["ms"][i] > 0 else None,
+                               "ms_per_step": prof["ms"][i] / args.steps} for i in PROF_ACC if i != dom}
     roofline = {
         "kernel": PROF_NAMES[dom], "bound": "imad", "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
         "frac": achieved / (imad_peak / 1e12), "traffic": traffic,
@@ -438,6 +437,7 @@ def run_gpu(args, rank, local_rank, world):
         "peak_source": "measured live: IMAD.WIDE.U32 issue rate of the fmaheavy pipe (32 lanes/clk/SM), max of the "
                        "independent accumulate form (%.2f T/s) and the carry-chain form (%.2f T/s)" % (imad_indep / 1e12, imad_chain / 1e12),
         "launch_ms_avg": prof["ms"][dom] / max(prof["spans"][dom], 1), "work": work,
+        "other_accumulation_classes": others,
     }
     value = world * args.steps / (ms_dev * 1e-3)
     e2e_value = world * args.steps / (ms_e2e * 1e-3)
@@ -469,13 +469,6 @@ def run_gpu(args, rank, local_rank, world):
     if cpu_baseline:
         line["cpu_baseline"] = cpu_baseline
     emit(line)
-
-
-def g2_entry_split(plan, total_entries):
-    """split the G2 accumulation's bucket entries between the MNT4 (Fq2) and MNT6 (Fq3) proofs by their point counts"""
-    w2 = sum(1 << lg for _, pairing, lg in plan if pairing == 0)
-    w3 = sum(1 << lg for _, pairing, lg in plan if pairing == 1)
-    return total_entries * w2 / (w2 + w3), total_entries * w3 / (w2 + w3)
 
 
 def tree_figure(args, ctx, step, stream, rank, world, barrier, max_over_ranks, log):

@@ -261,12 +261,13 @@ int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affin
 
 /* ---- profiling ----------------------------------------------------------------------------------
  * CUDA-event spans around the library's kernel groups, on the context's stream.  Classes (array
- * index): 0 MSM digit/sort, 1 MSM bucket accumulation G1, 2 same G2, 3 MSM bucket reduction,
+ * index): 0 MSM digit/sort, 1 MSM bucket accumulation G1, 2 same G2 over Fq2, 3 MSM bucket reduction,
  * 4 MSM window Horner, 5 NTT (all passes of a transform), 6 CSR mat-vec + QAP combine, 7 proof
- * assembly.  read() synchronises, returns per class the summed milliseconds, algorithmic units
+ * assembly, 8 MSM bucket accumulation G2 over Fq3, 9 bucket accumulation of MSMs below 2^14 points (any curve).
+ * read() synchronises, returns per class the summed milliseconds, algorithmic units
  * (bucket entries, butterflies, matrix rows, ...) and span count since the last read / enable, the
  * number of kernels launched, and resets.  Arrays hold PCDGPU_PROF_CLASSES entries. */
-#define PCDGPU_PROF_CLASSES 8
+#define PCDGPU_PROF_CLASSES 10
 int pcdgpu_profile_enable(pcdgpu_ctx* ctx, int on);
 int pcdgpu_profile_read(pcdgpu_ctx* ctx, double* ms, double* units, uint64_t* spans, uint64_t* launches);
 /* start / end (ms after the first span's start) and class of every span recorded since the last read:

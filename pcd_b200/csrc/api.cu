@@ -33,6 +33,10 @@ int msm_auto_window_c(size_t n, int shared) {
     // additions and needs >= ~2 * 10^5 buckets to give every SM its threads; the reduction costs ~ 2^(c-1)
     // buckets at ~14 x a mixed addition.  Measured optimum (tools/probe_msm.py): c = lg up to 2^18, 19 at 2^20.
     c = lg <= 18 ? lg : lg - 1;
+    // ~10^3 points (the default-circuit proofs of a PCD step): the walk of one thread per bucket has nothing to
+    // parallelise over, so use FEW buckets and let every bucket go down the chunked (CTA tree sum) path: measured on
+    // the whole 2^10 proof c = 10: 1.78 / 2.10 ms (MNT4 / MNT6), 7: 1.37 / 1.70, 6: 1.32 / 1.79, 4: 1.31 / 2.11
+    if (lg <= 12) c = 7;
     if (c < 6) c = 6;
     if (c > 21) c = 21;
   } else {

@@ -40,12 +40,14 @@ struct NttTables {
 enum {
   PROF_MSM_SORT = 0,  // digits + histogram, scan, scatter
   PROF_MSM_ACC_G1,    // bucket accumulation (msm_accumulate + heavy), G1 curves
-  PROF_MSM_ACC_G2,    // same, G2 curves
+  PROF_MSM_ACC_G2,    // same, G2 over Fq2 (MNT4)
   PROF_MSM_REDUCE,    // bucket reduction, per-window tree sum
   PROF_MSM_TAIL,      // Horner over windows
   PROF_NTT,           // all passes of one transform
   PROF_SPMV,          // CSR mat-vec + pointwise QAP combine
   PROF_ASSEMBLE,      // proof assembly (scalar multiplications, normalisation)
+  PROF_MSM_ACC_G2Q3,  // bucket accumulation over Fq3 (MNT6 G2), kept apart from Fq2 so that the work per entry is exact
+  PROF_MSM_ACC_SMALL, // bucket accumulation of MSMs below 2^14 points (default-circuit proofs): latency-bound regime
   PROF_NSLOT
 };
 

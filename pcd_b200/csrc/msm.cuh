@@ -521,7 +521,9 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   PCD_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
   u32* queue = heavy + MSM_MAX_HEAVY + 2;
   PCD_CUDA(ctx, cudaMemsetAsync(queue, 0, 4, st));
-  const int acc_slot = sizeof(typename C::F) > 40 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1;
+  const int acc_slot = n < ((size_t)1 << 14) ? PROF_MSM_ACC_SMALL
+                       : (sizeof(typename C::F) > 80 ? PROF_MSM_ACC_G2Q3
+                                                     : (sizeof(typename C::F) > 40 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1));
   int ps = ctx->prof_begin(PROF_MSM_SORT, (double)n * nwin);
   ctx->launches += 5 + 2;  // digits, scatter, accumulate, heavy x2 + cub's scan (init, scan); the reduction and
                            // combination count themselves
@@ -577,6 +579,15 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   // one thread (7 ms) would set the kernel's duration; such buckets go to the CTA-parallel heavy path.
   size_t avg_entries = total / nbuckets;
   u32 heavy_thr = (u32)(4 * avg_entries < 64 ? 64 : (4 * avg_entries > (size_t)MSM_HEAVY ? (size_t)MSM_HEAVY : 4 * avg_entries));
+  // ... and never longer than a few times the entries a resident thread would get if the work were spread evenly: with
+  // few buckets (small MSMs: 2^3 .. 2^9 buckets for ~10^3 points) "4 x the average" is thousands of entries, and a
+  // bucket just below it was walked by ONE thread for milliseconds (measured: 2^9-point MSM at c = 4, 6.3 ms) while
+  // the chunked path does the same bucket in 0.2 ms
+  {
+    size_t resident = acc_grid * 128;
+    size_t even = 4 * (total / (resident ? resident : 1)) + 32;
+    if (nbuckets * 8 < resident && even < heavy_thr) heavy_thr = (u32)even;
+  }
   // bucket parts: at least ~6 waves of work items, at least 8 entries per part
   u32 split = 1;
   while (split < (u32)MSM_MAX_SPLIT && nbuckets * split < 6 * acc_grid * ITEMS_PER_CTA && avg_entries / (2 * split) >= 8) split *= 2;

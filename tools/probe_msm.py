@@ -23,9 +23,9 @@ def profile(fn, reps=3):
     ctx.lib.pcdgpu_profile_enable(ctx.h, 1)
     for _ in range(reps):
         fn()
-    ms = (ctypes.c_double * 8)()
-    units = (ctypes.c_double * 8)()
-    spans = (ctypes.c_uint64 * 8)()
+    ms = (ctypes.c_double * 10)()
+    units = (ctypes.c_double * 10)()
+    spans = (ctypes.c_uint64 * 10)()
     launches = ctypes.c_uint64()
     ctx._check(ctx.lib.pcdgpu_profile_read(ctx.h, ms, units, spans, ctypes.byref(launches)))
     ctx.lib.pcdgpu_profile_enable(ctx.h, 0)
