@@ -14,6 +14,25 @@
 
 #define FP_LIMBS 10
 
+// The modulus limbs and -p^-1 mod 2^32 of r4 as the Montgomery REDUCTION rows see them: read from constant memory, so
+// that ptxas cannot see their values.  r4 has p[0] = 1 and -p^-1 = 0xffffffff; given those as immediates ptxas
+// rewrites the quotient digit as a negation and the rows' mad.lo.cc / madc.hi.cc pairs no longer fuse into
+// IMAD.WIDE.U32.X: every pair becomes IMAD.X + IMAD.HI.U32.X, two instructions on the fmaheavy pipe instead of one
+// (cuobjdump, round 2: ntt_pass_kernel<FpR4> 81 IMAD.WIDE.X + 80 IMAD.X + 80 IMAD.HI.X per product against 161 + 0 + 0
+// for q4) -- a third more multiply issue slots on every kernel over r4 (the main proof's NTTs, MNT6 G1 and G2).
+#if defined(__CUDACC__)
+static __constant__ u32 pcd_modc_r4[FP_LIMBS + 2] = {
+    ParamsR4::mod(0), ParamsR4::mod(1), ParamsR4::mod(2), ParamsR4::mod(3), ParamsR4::mod(4), ParamsR4::mod(5),
+    ParamsR4::mod(6), ParamsR4::mod(7), ParamsR4::mod(8), ParamsR4::mod(9), ParamsR4::INV, 0};
+#endif
+template <class P>
+PCD_HD u32 fp_mod_opaque(int i) {  // i = FP_LIMBS: -p^-1 mod 2^32
+#if defined(__CUDA_ARCH__)
+  if (P::ID == 0) return pcd_modc_r4[i];
+#endif
+  return i < FP_LIMBS ? P::mod(i) : P::INV;
+}
+
 template <class P>
 struct Fp {
   u32 l[FP_LIMBS];
@@ -120,12 +139,12 @@ struct Fp {
   // same with the modulus (compile-time limbs, offset off = 0 or 1)
   template <int OFF>
   PCD_HD static void cmad_mod(u32* acc, u32 m) {
-    acc[0] = prims::mad_lo_cc(P::mod(OFF), m, acc[0]);
-    acc[1] = prims::madc_hi_cc(P::mod(OFF), m, acc[1]);
+    acc[0] = prims::mad_lo_cc(fp_mod_opaque<P>(OFF), m, acc[0]);
+    acc[1] = prims::madc_hi_cc(fp_mod_opaque<P>(OFF), m, acc[1]);
 #pragma unroll
     for (int j = 2; j < FP_LIMBS; j += 2) {
-      acc[j] = prims::madc_lo_cc(P::mod(OFF + j), m, acc[j]);
-      acc[j + 1] = prims::madc_hi_cc(P::mod(OFF + j), m, acc[j + 1]);
+      acc[j] = prims::madc_lo_cc(fp_mod_opaque<P>(OFF + j), m, acc[j]);
+      acc[j + 1] = prims::madc_hi_cc(fp_mod_opaque<P>(OFF + j), m, acc[j + 1]);
     }
   }
   // odd = (odd >> 64) + sum_j a[j] * bi * 2^(32 j) + CC, j = 0, 2, ... (a already offset by one)
@@ -149,7 +168,7 @@ struct Fp {
       cmad_n(even, a, bi);
       odd[FP_LIMBS - 1] = prims::addc(odd[FP_LIMBS - 1], 0);
     }
-    u32 m = prims::mul_lo(even[0], P::INV);
+    u32 m = prims::mul_lo(even[0], fp_mod_opaque<P>(FP_LIMBS));
     cmad_mod<1>(odd, m);
     cmad_mod<0>(even, m);
     odd[FP_LIMBS - 1] = prims::addc(odd[FP_LIMBS - 1], 0);

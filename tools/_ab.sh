@@ -1,4 +1,5 @@
-for c in 0 4 5 6 7 8; do
-  echo "== WINDOW $c"
-  PCD_MSM_WINDOW=$c PROBE=tiny python tools/probe_pcd.py 2>&1 | grep -E "^== tinypre"
+for ctas in 2 3; do
+echo "=== ACC_CTAS $ctas"
+PCDGPU_ACC_CTAS=$ctas PROBE=main,help python tools/probe_pcd.py 2>&1 | grep -E "^=="  | cut -c1-110
+PCDGPU_ACC_CTAS=$ctas PROBE=main,help python tools/probe_pcd.py 2>&1 | grep -E "^=="  | cut -c1-110
 done

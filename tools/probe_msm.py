@@ -13,8 +13,10 @@ import pcd_b200  # noqa: E402
 from pcd_b200 import synthetic  # noqa: E402
 
 ctx = pcd_b200.Context(0)
+if os.environ.get("SIDE_BY_SIDE"):
+    ctx.lib.pcdgpu_set_msm_side_by_side(ctx.h, 1)
 dev = torch.device("cuda:0")
-NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble"]
+NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small"]
 
 
 def profile(fn, reps=3):
@@ -29,7 +31,10 @@ def profile(fn, reps=3):
     launches = ctypes.c_uint64()
     ctx._check(ctx.lib.pcdgpu_profile_read(ctx.h, ms, units, spans, ctypes.byref(launches)))
     ctx.lib.pcdgpu_profile_enable(ctx.h, 0)
-    return {NAMES[i]: round(ms[i] / reps, 3) for i in range(8) if ms[i] > 0}
+    out = {NAMES[i]: round(ms[i] / reps, 3) for i in range(10) if ms[i] > 0}
+    ent = sum(units[i] for i in (1, 2, 8, 9)) / reps
+    out['entries'] = int(ent)
+    return out
 
 
 curves = [int(x) for x in os.environ.get("PROBE_CURVES", "0").split(",")]
@@ -50,6 +55,10 @@ for curve in curves:
             for name, sc in (("U", sc_u), ("W", sc_w)):
                 d = torch.from_numpy(sc.view(np.int64)).to(dev)
                 p = profile(lambda: b.msm_dev(d.data_ptr(), n, res.data_ptr()))
-                print("curve %d 2^%d c=%d %s total %.3f ms" % (curve, log_n, c, name, sum(p.values())), p, flush=True)
+                acc = sum(v for k, v in p.items() if k.startswith("acc"))
+                prod = {0: 10, 1: 28, 2: 10, 3: 58}[curve]
+                print("curve %d 2^%d c=%d %s acc %.3f ms = %.2f TIMAD/s (%.2f of 9.15)" % (
+                    curve, log_n, c, name, acc, p["entries"] * prod * 210 / (acc * 1e-3) / 1e12,
+                    p["entries"] * prod * 210 / (acc * 1e-3) / 9.15e12), p, flush=True)
             b.close()
         ctx.set_msm_window(0)
