@@ -1,0 +1,160 @@
+"""Marlin (/root/reference/tests/mnt4_marlin.rs:53-94): the oracle's prover against the AHP verifier
+identities and a known-trapdoor SRS on the CPU; the GPU prover (pcd_b200.marlin over the C ABI) against the oracle byte
+for byte."""
+import numpy as np
+import pytest
+
+import c_oracle as co
+import codec
+import kzg_oracle as ko
+import marlin_oracle as mo
+import pcd_oracle as o
+import synth
+
+FP_OF = {0: o.FR4, 1: o.FQ4}  # scalar field of the pairing
+CF_OF = {0: o.FQ4, 1: o.FR4}  # base field of its G1 = the sponge field
+
+
+class Draws:
+    """the caller's rng: one F::rand per call (SplitMix64-based; the real rng stays on the Rust side)"""
+
+    def __init__(self, fp, seed):
+        self.fp, self.rng, self.count = fp, o.SplitMix64(seed), 0
+
+    def __call__(self):
+        self.count += 1
+        return self.rng.field(self.fp.p)
+
+
+def _coords_of(pairing):
+    cf = CF_OF[pairing]
+    Rinv = pow(cf.R, -1, cf.p)
+
+    def coords(pt):
+        pt = np.asarray(pt, dtype=np.uint64).reshape(2, 5)
+        x, y = (codec.limbs_to_int(pt[0]) * Rinv % cf.p, codec.limbs_to_int(pt[1]) * Rinv % cf.p)
+        inf = 1 if not pt.any() else 0
+        return [x, y, inf]
+    return coords
+
+
+def marlin_setup(pairing, m, seed=5, num_inputs=3):
+    fp = FP_OF[pairing]
+    r1cs, z = o.synthetic_r1cs(fp, m, num_inputs, seed, 0.3)
+    idx = mo.index(r1cs)
+    max_degree = max(3 * idx.H.size, 4 * idx.K.size)
+    p = fp.p
+    beta, gamma = pow(3, 1001, p), pow(5, 777, p)
+    g1 = codec.G1_OF[pairing]
+    G = synth.generator_limbs(g1)
+    pg, pgg = ko.setup(pairing, max_degree, beta, gamma, G, 0)
+    return dict(pairing=pairing, fp=fp, r1cs=r1cs, z=z, idx=idx, max_degree=max_degree, beta=beta, gamma=gamma, G=G,
+                pg=pg, pgg=pgg, g1=g1)
+
+
+def oracle_group(S):
+    def group(coeffs, shift, blinding):
+        assert shift + len(coeffs) <= S["pg"].shape[0]
+        parts = []
+        if coeffs:
+            parts.append(co.msm(S["g1"], S["pg"][shift:shift + len(coeffs)], codec.ints_to_limbs(coeffs), 0))
+        if blinding:
+            parts.append(co.msm(S["g1"], S["pgg"][:len(blinding)], codec.ints_to_limbs(blinding), 0))
+        if not parts:
+            return np.zeros(10, dtype=np.uint64)
+        return co.point_sum(S["g1"], np.stack(parts))
+    return group
+
+
+def index_comm_coords(S):
+    """the index commitments (12 polynomials, no hiding, no bounds), flattened to sponge elements"""
+    group, coords = oracle_group(S), _coords_of(S["pairing"])
+    comms = [group(c, 0, []) for _, c in S["idx"].index_polys()]
+    return comms, [e for c in comms for e in coords(c)]
+
+
+def oracle_prove(S, seed=99):
+    comms, flat = index_comm_coords(S)
+    draws = Draws(S["fp"], seed)
+    proof, trace = mo.prove(S["idx"], flat, CF_OF[S["pairing"]], S["z"], draws, S["max_degree"], oracle_group(S),
+                            _coords_of(S["pairing"]))
+    return proof, trace, flat, draws.count
+
+
+def test_chacha20_block_zero_key():
+    """RFC 7539 style known answer: key = 0, counter = 0, nonce = 0 -> first keystream words of ChaCha20"""
+    rng = mo.ChaCha20Rng(bytes(32))
+    first = b"".join(rng.next_u32().to_bytes(4, "little") for _ in range(8))
+    assert first.hex() == "76b8e0ada0f13d90405d6ae55386bd28bdd219b8a08ded1aa836efcc8b770dc7"
+
+
+def test_poseidon_sponge_shape():
+    for fp in (o.FR4, o.FQ4):
+        ark = mo.poseidon_ark(fp)
+        assert len(ark) == 39 and all(len(r) == 3 and all(0 <= x < fp.p for x in r) for r in ark)
+        s1, s2 = mo.PoseidonSponge(fp), mo.PoseidonSponge(fp)
+        s1.absorb([1, 2, 3, 4, 5])
+        s2.absorb([1, 2])
+        s2.absorb([3, 4, 5])
+        assert s1.squeeze(3) == s2.squeeze(3)  # absorbing in pieces is the same stream
+        s3 = mo.PoseidonSponge(fp)
+        s3.absorb([1, 2, 3, 4, 6])
+        assert s3.squeeze(1) != mo_squeeze_again([1, 2, 3, 4, 5], fp)
+
+
+def mo_squeeze_again(elems, fp):
+    s = mo.PoseidonSponge(fp)
+    s.absorb(elems)
+    return s.squeeze(1)
+
+
+def test_reindex_is_a_permutation():
+    for h, x in ((8, 2), (16, 4), (64, 1), (32, 16)):
+        if x == h:
+            continue
+        if h // x == 1:
+            continue
+        img = [mo.reindex_by_subdomain(h, x, i) for i in range(h)]
+        assert sorted(img) == list(range(h))
+        assert img[:x] == [i * (h // x) for i in range(x)]
+
+
+def test_divide_by_vanishing():
+    p = o.R4
+    a = [pow(3, i + 1, p) for i in range(37)]
+    for n in (4, 8, 16, 64):
+        q, r = mo.p_div_vanishing(p, a, n)
+        back = mo.p_add(p, mo.p_mul(p, q, [p - 1] + [0] * (n - 1) + [1]), r)
+        assert mo.p_trim(back) == a and len(r) <= n
+
+
+@pytest.mark.parametrize("pairing,m", [(0, 20), (1, 13)])
+def test_oracle_marlin_complete(pairing, m):
+    """the oracle's proof passes the AHP verifier identities and every KZG check in the exponent; changing an
+    evaluation, a challenge-bearing commitment or the witness breaks it"""
+    S = marlin_setup(pairing, m)
+    assert S["r1cs"].is_satisfied(S["z"])
+    proof, trace, flat, ndraws = oracle_prove(S)
+    idx, p = S["idx"], S["fp"].p
+    # rng draws: 3 blinding coefficients, mask polynomial, hiding polynomials of w, z_a, z_b, mask_poly, g_1 (+ shifted)
+    assert ndraws == 3 + 3 * idx.H.size + 4 * 3 + 2 * 3
+    coords = _coords_of(pairing)
+
+    def point_of_log(v):
+        return co.fixed_base_mul(S["g1"], S["G"], codec.ints_to_limbs([v]), 1)[0]
+
+    args = (idx, flat, CF_OF[pairing], S["z"][:S["r1cs"].num_inputs])
+    assert mo.check_proof(*args, proof, trace, S["max_degree"], S["beta"], S["gamma"], point_of_log, coords)
+    bad = mo.Proof(proof.commitments, [(l, (v + (l == "t")) % p) for l, v in proof.evaluations], proof.pc_proof)
+    assert not mo.check_proof(*args, bad, trace, S["max_degree"], S["beta"], S["gamma"], point_of_log, coords)
+    # both sumcheck LCs really evaluate to zero at the challenge points (the AHP verifier's equations)
+    ev = dict(proof.evaluations)
+    x_at_beta = mo.p_eval(p, o.domain_ifft(idx.X, mo.format_assignment(idx, S["z"])[0]), trace.challenges["beta"])
+    for label, pl, terms in mo.linear_combinations(idx, trace.challenges, ev, x_at_beta):
+        val = sum(c * (mo.p_eval(p, trace.polys[l].poly, trace.challenges[pl]) if l else 1) for c, l in terms) % p
+        assert val == (0 if label in mo.LC_WITH_ZERO_EVAL else ev[label]), label
+    # an unsatisfying assignment cannot be proven (the outer sumcheck remainder has a constant term)
+    zbad = list(S["z"])
+    zbad[-1] = (zbad[-1] + 1) % p
+    with pytest.raises(AssertionError):
+        mo.prove(idx, flat, CF_OF[pairing], zbad, Draws(S["fp"], 1), S["max_degree"], oracle_group(S), coords)
