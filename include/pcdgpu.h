@@ -205,6 +205,57 @@ int pcdgpu_kzg_open(pcdgpu_ctx* ctx, const pcdgpu_bases* powers_of_g, const void
                     const pcdgpu_bases* powers_of_gamma_g, const void* rand_coeffs, size_t n_rand, const void* z,
                     void* out_w_affine, void* out_value, void* out_random_v);
 
+/* ---- device-resident polynomials: what ark-marlin's AHP prover does between its FFTs and its commitments ------------
+ * Replaces, under `MarlinSNARK::prove` as the reference binds it (/root/reference/tests/mnt4_marlin.rs:72-75, reached
+ * through /root/reference/src/ec_cycle_pcd/mod.rs:171,179): ark-poly `DensePolynomial` / `EvaluationsOnDomain`
+ * arithmetic (add, sub, pointwise mul, scalar mul, `evaluate`, `divide_by_vanishing_poly`, division by X - z),
+ * ark-ff `batch_inversion`, `EvaluationDomain::elements`, the sparse matrix products of ark-marlin's
+ * prover_first_round / prover_second_round, and `KZG10::commit` over powers_of_g[shift..] (MarlinKZG10's shifted
+ * commitments).  Vectors live in device memory (Montgomery elements, 40 B each) between calls so that a prover round is
+ * a sequence of kernels on the context's stream with no host copies; scalars (challenges) are 40-byte HOST values
+ * passed by value into the kernels.  The AHP round logic and the Fiat-Shamir sponge are host code above these calls
+ * (pcd_b200/marlin.py mirrors ark-marlin's; INTEGRATION.md shows where the Rust side would call them). */
+typedef struct pcdgpu_csr pcdgpu_csr; /* device-resident sparse matrix (CSR) */
+int pcdgpu_dev_alloc(pcdgpu_ctx* ctx, size_t bytes, void** d_out); /* stream-ordered (cudaMallocAsync) */
+int pcdgpu_dev_free(pcdgpu_ctx* ctx, void* d);
+int pcdgpu_dev_upload(pcdgpu_ctx* ctx, void* d_dst, const void* src, size_t bytes);   /* returns when copied */
+int pcdgpu_dev_download(pcdgpu_ctx* ctx, void* dst, const void* d_src, size_t bytes); /* returns when copied */
+int pcdgpu_dev_copy(pcdgpu_ctx* ctx, void* d_dst, const void* d_src, size_t bytes);
+int pcdgpu_dev_zero(pcdgpu_ctx* ctx, void* d, size_t bytes);
+enum { PCDGPU_VEC_ADD = 0, PCDGPU_VEC_SUB = 1, PCDGPU_VEC_MUL = 2, PCDGPU_VEC_RSUB = 3 /* b - a */ };
+/* out[i] = a[i] op b[i]; out may alias a or b */
+int pcdgpu_vec_binary_dev(pcdgpu_ctx* ctx, int field, int op, void* d_out, const void* d_a, const void* d_b, size_t n);
+/* out[i] = a[i] op scalar */
+int pcdgpu_vec_scalar_dev(pcdgpu_ctx* ctx, int field, int op, void* d_out, const void* d_a, const void* scalar, size_t n);
+/* y[i] += scalar * x[i] */
+int pcdgpu_vec_axpy_dev(pcdgpu_ctx* ctx, int field, void* d_y, const void* scalar, const void* d_x, size_t n);
+/* ark-ff batch_inversion in place (zeros stay zero) */
+int pcdgpu_vec_inverse_dev(pcdgpu_ctx* ctx, int field, void* d_data, size_t n);
+/* out[i] = scale * base^i (EvaluationDomain::elements with base = group_gen, scale = 1) */
+int pcdgpu_vec_powers_dev(pcdgpu_ctx* ctx, int field, void* d_out, const void* base, const void* scale, size_t n);
+/* out[i] = src[index[i]], index 0xffffffff gives 0 (d_index: device u32) */
+int pcdgpu_vec_gather_dev(pcdgpu_ctx* ctx, int field, void* d_out, const void* d_src, const uint32_t* d_index, size_t n);
+/* DensePolynomial::evaluate: out (host) = p(z) */
+int pcdgpu_poly_eval_dev(pcdgpu_ctx* ctx, int field, const void* d_coeffs, size_t n, const void* z, void* out);
+/* DensePolynomial::divide_by_vanishing_poly for the domain of size domain_n: p = q (X^N - 1) + r; q: n - N coefficients
+ * (untouched when n <= N), r: N coefficients */
+int pcdgpu_poly_divide_vanishing_dev(pcdgpu_ctx* ctx, int field, const void* d_p, size_t n, size_t domain_n, void* d_q,
+                                     void* d_r);
+/* (p - p(z)) / (X - z) on device coefficients; out_eval (host, may be NULL: then the call stays asynchronous) = p(z) */
+int pcdgpu_poly_divide_linear_dev(pcdgpu_ctx* ctx, int field, const void* d_p, size_t n, const void* z, void* d_q,
+                                  void* out_eval);
+/* pcdgpu_ntt_general on device memory */
+int pcdgpu_ntt_general_dev(pcdgpu_ctx* ctx, int field, void* d_data, int pow7, int pow2, int inverse, int coset);
+/* sparse matrix (CSR: row_ptr[m + 1], col[nnz] < ncols, val[nnz] Montgomery) resident on the GPU; out[row] = M[row] . x */
+int pcdgpu_csr_upload(pcdgpu_ctx* ctx, int field, size_t m, size_t ncols, const uint32_t* row_ptr, const uint32_t* col,
+                      const void* val, pcdgpu_csr** out);
+void pcdgpu_csr_free(pcdgpu_csr* c);
+int pcdgpu_csr_matvec_dev(pcdgpu_ctx* ctx, const pcdgpu_csr* c, const void* d_x, void* d_out);
+/* KZG10::commit of device-resident coefficients over powers_of_g[shift .. shift + n) (+ the blinding polynomial over
+ * powers_of_gamma_g[0 .. n_rand)); out_affine: host */
+int pcdgpu_kzg_commit_dev(pcdgpu_ctx* ctx, const pcdgpu_bases* powers_of_g, size_t shift, const void* d_coeffs, size_t n,
+                          const pcdgpu_bases* powers_of_gamma_g, const void* d_rand, size_t n_rand, void* out_affine);
+
 /* Launch heuristics for callers that run several MSMs side by side on contexts of their own (the multi-GPU prover):
  * on != 0 selects, for bases uploaded and MSMs launched through this context afterwards, the window and occupancy
  * rules the single-GPU prover uses for its five concurrent MSMs (one bit smaller window from 2^18 points up, two

@@ -42,6 +42,11 @@ EXPORTS = [
     "pcdgpu_comm_unique_id", "pcdgpu_comm_init", "pcdgpu_comm_info", "pcdgpu_comm_destroy", "pcdgpu_pk_upload_sharded",
     "pcdgpu_groth16_prove_sharded", "pcdgpu_groth16_prove_sharded_dev", "pcdgpu_msm_bases_sharded",
     "pcdgpu_msm_bases_sharded_dev",
+    "pcdgpu_dev_alloc", "pcdgpu_dev_free", "pcdgpu_dev_upload", "pcdgpu_dev_download", "pcdgpu_dev_copy", "pcdgpu_dev_zero",
+    "pcdgpu_vec_binary_dev", "pcdgpu_vec_scalar_dev", "pcdgpu_vec_axpy_dev", "pcdgpu_vec_inverse_dev",
+    "pcdgpu_vec_powers_dev", "pcdgpu_vec_gather_dev", "pcdgpu_poly_eval_dev", "pcdgpu_poly_divide_vanishing_dev",
+    "pcdgpu_poly_divide_linear_dev", "pcdgpu_ntt_general_dev", "pcdgpu_csr_upload", "pcdgpu_csr_free",
+    "pcdgpu_csr_matvec_dev", "pcdgpu_kzg_commit_dev",
 ]
 COMM_ID_BYTES = 128
 
@@ -139,6 +144,27 @@ def load():
     lib.pcdgpu_groth16_prove_sharded_dev.argtypes = [vp, vp, vp, vp, vp, vp, vp]
     lib.pcdgpu_msm_bases_sharded.argtypes = [vp, vp, vp, sz, vp]
     lib.pcdgpu_msm_bases_sharded_dev.argtypes = [vp, vp, vp, ci, sz, vp]
+    lib.pcdgpu_dev_alloc.argtypes = [vp, sz, ctypes.POINTER(vp)]
+    lib.pcdgpu_dev_free.argtypes = [vp, vp]
+    lib.pcdgpu_dev_upload.argtypes = [vp, vp, vp, sz]
+    lib.pcdgpu_dev_download.argtypes = [vp, vp, vp, sz]
+    lib.pcdgpu_dev_copy.argtypes = [vp, vp, vp, sz]
+    lib.pcdgpu_dev_zero.argtypes = [vp, vp, sz]
+    lib.pcdgpu_vec_binary_dev.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    lib.pcdgpu_vec_scalar_dev.argtypes = [vp, ci, ci, vp, vp, vp, sz]
+    lib.pcdgpu_vec_axpy_dev.argtypes = [vp, ci, vp, vp, vp, sz]
+    lib.pcdgpu_vec_inverse_dev.argtypes = [vp, ci, vp, sz]
+    lib.pcdgpu_vec_powers_dev.argtypes = [vp, ci, vp, vp, vp, sz]
+    lib.pcdgpu_vec_gather_dev.argtypes = [vp, ci, vp, vp, vp, sz]
+    lib.pcdgpu_poly_eval_dev.argtypes = [vp, ci, vp, sz, vp, vp]
+    lib.pcdgpu_poly_divide_vanishing_dev.argtypes = [vp, ci, vp, sz, sz, vp, vp]
+    lib.pcdgpu_poly_divide_linear_dev.argtypes = [vp, ci, vp, sz, vp, vp, vp]
+    lib.pcdgpu_ntt_general_dev.argtypes = [vp, ci, vp, ci, ci, ci, ci]
+    lib.pcdgpu_csr_upload.argtypes = [vp, ci, sz, sz, vp, vp, vp, ctypes.POINTER(vp)]
+    lib.pcdgpu_csr_free.argtypes = [vp]
+    lib.pcdgpu_csr_free.restype = None
+    lib.pcdgpu_csr_matvec_dev.argtypes = [vp, vp, vp, vp]
+    lib.pcdgpu_kzg_commit_dev.argtypes = [vp, vp, sz, vp, sz, vp, vp, sz, vp]
     _lib = lib
     return lib
 

@@ -11,6 +11,7 @@ use std::os::raw::{c_char, c_int, c_void};
 #[repr(C)] pub struct pcdgpu_r1cs { _p: [u8; 0] }
 #[repr(C)] pub struct pcdgpu_pk { _p: [u8; 0] }
 #[repr(C)] pub struct pcdgpu_gm17_pk { _p: [u8; 0] }
+#[repr(C)] pub struct pcdgpu_csr { _p: [u8; 0] }
 
 pub const PCDGPU_OK: c_int = 0;
 pub const PCDGPU_E_ARG: c_int = -1;
@@ -74,6 +75,26 @@ extern "C" {
     pub fn pcdgpu_poly_mul(ctx: *mut pcdgpu_ctx, field: c_int, a: *const c_void, na: usize, b: *const c_void, nb: usize, out: *mut c_void) -> c_int;
     pub fn pcdgpu_kzg_commit(ctx: *mut pcdgpu_ctx, powers_of_g: *const pcdgpu_bases, coeffs: *const c_void, n: usize, powers_of_gamma_g: *const pcdgpu_bases, rand_coeffs: *const c_void, n_rand: usize, out_affine: *mut c_void) -> c_int;
     pub fn pcdgpu_kzg_open(ctx: *mut pcdgpu_ctx, powers_of_g: *const pcdgpu_bases, coeffs: *const c_void, n: usize, powers_of_gamma_g: *const pcdgpu_bases, rand_coeffs: *const c_void, n_rand: usize, z: *const c_void, out_w_affine: *mut c_void, out_value: *mut c_void, out_random_v: *mut c_void) -> c_int;
+    pub fn pcdgpu_dev_alloc(ctx: *mut pcdgpu_ctx, bytes: usize, d_out: *mut *mut c_void) -> c_int;
+    pub fn pcdgpu_dev_free(ctx: *mut pcdgpu_ctx, d: *mut c_void) -> c_int;
+    pub fn pcdgpu_dev_upload(ctx: *mut pcdgpu_ctx, d_dst: *mut c_void, src: *const c_void, bytes: usize) -> c_int;
+    pub fn pcdgpu_dev_download(ctx: *mut pcdgpu_ctx, dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
+    pub fn pcdgpu_dev_copy(ctx: *mut pcdgpu_ctx, d_dst: *mut c_void, d_src: *const c_void, bytes: usize) -> c_int;
+    pub fn pcdgpu_dev_zero(ctx: *mut pcdgpu_ctx, d: *mut c_void, bytes: usize) -> c_int;
+    pub fn pcdgpu_vec_binary_dev(ctx: *mut pcdgpu_ctx, field: c_int, op: c_int, d_out: *mut c_void, d_a: *const c_void, d_b: *const c_void, n: usize) -> c_int;
+    pub fn pcdgpu_vec_scalar_dev(ctx: *mut pcdgpu_ctx, field: c_int, op: c_int, d_out: *mut c_void, d_a: *const c_void, scalar: *const c_void, n: usize) -> c_int;
+    pub fn pcdgpu_vec_axpy_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_y: *mut c_void, scalar: *const c_void, d_x: *const c_void, n: usize) -> c_int;
+    pub fn pcdgpu_vec_inverse_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_data: *mut c_void, n: usize) -> c_int;
+    pub fn pcdgpu_vec_powers_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_out: *mut c_void, base: *const c_void, scale: *const c_void, n: usize) -> c_int;
+    pub fn pcdgpu_vec_gather_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_out: *mut c_void, d_src: *const c_void, d_index: *const u32, n: usize) -> c_int;
+    pub fn pcdgpu_poly_eval_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_coeffs: *const c_void, n: usize, z: *const c_void, out: *mut c_void) -> c_int;
+    pub fn pcdgpu_poly_divide_vanishing_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_p: *const c_void, n: usize, domain_n: usize, d_q: *mut c_void, d_r: *mut c_void) -> c_int;
+    pub fn pcdgpu_poly_divide_linear_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_p: *const c_void, n: usize, z: *const c_void, d_q: *mut c_void, out_eval: *mut c_void) -> c_int;
+    pub fn pcdgpu_ntt_general_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_data: *mut c_void, pow7: c_int, pow2: c_int, inverse: c_int, coset: c_int) -> c_int;
+    pub fn pcdgpu_csr_upload(ctx: *mut pcdgpu_ctx, field: c_int, m: usize, ncols: usize, row_ptr: *const u32, col: *const u32, val: *const c_void, out: *mut *mut pcdgpu_csr) -> c_int;
+    pub fn pcdgpu_csr_free(c: *mut pcdgpu_csr);
+    pub fn pcdgpu_csr_matvec_dev(ctx: *mut pcdgpu_ctx, c: *const pcdgpu_csr, d_x: *const c_void, d_out: *mut c_void) -> c_int;
+    pub fn pcdgpu_kzg_commit_dev(ctx: *mut pcdgpu_ctx, powers_of_g: *const pcdgpu_bases, shift: usize, d_coeffs: *const c_void, n: usize, powers_of_gamma_g: *const pcdgpu_bases, d_rand: *const c_void, n_rand: usize, out_affine: *mut c_void) -> c_int;
     pub fn pcdgpu_set_msm_side_by_side(ctx: *mut pcdgpu_ctx, on: c_int) -> c_int;
     pub fn pcdgpu_groth16_assemble_begin_dev(ctx: *mut pcdgpu_ctx, pairing: c_int, r: *const c_void, s: *const c_void, world: c_int, d_partials_ab: *const c_void, d_partials_g2: *const c_void) -> c_int;
     pub fn pcdgpu_groth16_assemble_finish_dev(ctx: *mut pcdgpu_ctx, pairing: c_int, world: c_int, d_partials_hl: *const c_void, out_proof: *mut c_void) -> c_int;

@@ -158,3 +158,81 @@ def test_oracle_marlin_complete(pairing, m):
     zbad[-1] = (zbad[-1] + 1) % p
     with pytest.raises(AssertionError):
         mo.prove(idx, flat, CF_OF[pairing], zbad, Draws(S["fp"], 1), S["max_degree"], oracle_group(S), coords)
+
+
+def test_product_sponge_matches_oracle():
+    """pcd_b200/fiat_shamir.py (the product's host-side transcript) against the oracle's restatement"""
+    from pcd_b200 import fiat_shamir as fsm
+    for field, (f, cf) in enumerate(((o.FR4, o.FQ4), (o.FQ4, o.FR4))):
+        a, b = mo.FiatShamirRng(f, cf), fsm.FiatShamirAlgebraicSpongeRng(field, 1 - field)
+        assert mo.poseidon_ark(cf) == fsm.PoseidonSponge(1 - field).ark
+        for rng in (a, b):
+            rng.absorb_bytes(b"MARLIN-2019") if rng is a else rng.absorb_bytes(b"MARLIN-2019")
+        a.absorb_native([5, 6, 7]); b.absorb_native_field_elements([5, 6, 7])
+        a.absorb_nonnative([f.p - 1, 12345, 1 << 200]); b.absorb_nonnative_field_elements([f.p - 1, 12345, 1 << 200])
+        assert a.squeeze_nonnative(4) == b.squeeze_nonnative_field_elements(4)
+        a.absorb_native([9]); b.absorb_native_field_elements([9])
+        assert a.squeeze_128_bits_nonnative(7) == b.squeeze_128_bits_nonnative_field_elements(7)
+        assert a.squeeze_native(3) == b.squeeze_native_field_elements(3)
+
+
+# ---- GPU ------------------------------------------------------------------------------------------------------
+@pytest.fixture(scope="module")
+def ctx():
+    import pcd_b200
+    c = pcd_b200.Context(0)
+    yield c
+    c.close()
+
+
+def gpu_prove(ctx, S, seed=99, precompute=False):
+    from pcd_b200 import kzg, marlin
+    import pcd_b200
+    fp = S["fp"]
+    A, B, C = synth.r1cs_to_csr(S["r1cs"])
+    cm = pcd_b200.ConstraintMatrices(S["pairing"], S["r1cs"].num_inputs, S["r1cs"].num_witness, A, B, C)
+    powers = kzg.Powers(ctx, S["pairing"], S["pg"], S["pgg"], precompute=precompute)
+    snark = marlin.MarlinSNARK(ctx, S["pairing"])
+    ipk = snark.index(cm, powers, S["max_degree"])
+    draws = Draws(fp, seed)
+    rng = lambda field: synth.mont_limbs([draws()], fp)[0]
+    proof = snark.prove(ipk, synth.mont_limbs(S["z"], fp), rng)
+    return proof, ipk, snark, draws.count
+
+
+def assert_same_proof(gpu, orc):
+    for rg, ro in zip(gpu.commitments, orc.commitments):
+        assert [c.label for c in rg] == [l for l, _, _ in ro]
+        for c, (label, comm, shifted) in zip(rg, ro):
+            assert np.array_equal(c.comm, comm), label
+            assert (c.shifted_comm is None) == (shifted is None), label
+            if shifted is not None:
+                assert np.array_equal(c.shifted_comm, shifted), label + " (shifted)"
+    assert gpu.evaluations == orc.evaluations
+    assert len(gpu.pc_proof) == len(orc.pc_proof)
+    for (pl, w, rv), (plo, wo, rvo) in zip(gpu.pc_proof, orc.pc_proof):
+        assert pl == plo and np.array_equal(w, wo) and rv == rvo, pl
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pairing,m,pre", [(0, 20, False), (1, 13, False), (0, 300, True), (1, 200, False)])
+def test_gpu_marlin_matches_oracle(ctx, pairing, m, pre):
+    """the GPU prover's commitments, evaluations and opening proofs equal the oracle's byte for byte; the oracle's proof
+    passes the AHP verifier identities and the KZG checks in the exponent (so the GPU's does)"""
+    S = marlin_setup(pairing, m)
+    proof, trace, flat, ndraws = oracle_prove(S)
+    gproof, ipk, snark, gdraws = gpu_prove(ctx, S, precompute=pre)
+    assert gdraws == ndraws
+    comms, _ = index_comm_coords(S)
+    for c, ref in zip(ipk.index_comms, comms):
+        assert np.array_equal(c.comm, ref), c.label
+    assert snark.last_trace["challenges"] == trace.challenges
+    assert snark.last_trace["opening_challenges"] == trace.opening_challenges
+    assert_same_proof(gproof, proof)
+    coords = _coords_of(pairing)
+    point_of_log = lambda v: co.fixed_base_mul(S["g1"], S["G"], codec.ints_to_limbs([v]), 1)[0]
+    as_oracle = mo.Proof([[(c.label, c.comm, c.shifted_comm) for c in rnd] for rnd in gproof.commitments],
+                         gproof.evaluations, gproof.pc_proof)
+    assert mo.check_proof(S["idx"], flat, CF_OF[pairing], S["z"][:S["r1cs"].num_inputs], as_oracle, trace,
+                          S["max_degree"], S["beta"], S["gamma"], point_of_log, coords)
+    ipk.close()
