@@ -392,6 +392,8 @@ def run_gpu(args, rank, local_rank, world):
         extra["groth16_2^%d" % args.log_n] = proof_figure(args, ctx, dev, stream, co, log)
     if rank == 0 and world == 1 and not args.no_gm17:
         extra["gm17"] = gm17_figure(args, ctx, dev, stream, co, log)
+    if rank == 0 and world == 1 and not args.no_marlin:
+        extra["marlin"] = marlin_figure(args, ctx, co, log)
     cpu_baseline = None
     if rank == 0 and world == 1 and not args.no_cpu_baseline:
         _, cinsts = cpu_step_setup(args, log)
@@ -645,6 +647,68 @@ def gm17_figure(args, ctx, dev, stream, co, log):
             "sap_domain": "2^%d" % k, "note": "SAP witness map (5 NTTs) + 4 G1 MSMs + 1 G2 MSM + assembly; one proof at a time"}
 
 
+def marlin_figure(args, ctx, co, log):
+    """Marlin proofs/s on MNT4-298 (BASELINE config 4; /root/reference/tests/mnt4_marlin.rs:72-75): synthetic R1CS with
+    |H| = 2^k, KZG10 SRS with a known trapdoor built on the GPU.  The proof is checked before it is timed: every
+    commitment against [p(beta) + gamma r(beta)] G by the oracle's scalar multiplication, the AHP verifier's sumcheck
+    identities, and KZG10's equation in the exponent (tests/marlin_check.py).  Timed with the wall clock around the
+    whole prover call: it hands commitments back to the host between rounds (the transcript lives there), so a proof is
+    not one stream-ordered region."""
+    import random
+    import time
+
+    import pcd_b200
+    from pcd_b200 import kzg, marlin, synthetic
+    import marlin_check
+    pairing, field = pcd_b200.MNT4_298, 0
+    p = synthetic.FIELD_P[field]
+    m = (1 << args.marlin_log_h) - 4
+    z, ra, rb, rc = synthetic._synthetic_rows(random.Random(99), p, m, 0.4)
+    cm = pcd_b200.ConstraintMatrices(pairing, 2, len(z) - 2, synthetic._csr(ra, p), synthetic._csr(rb, p),
+                                     synthetic._csr(rc, p))
+    nnz = max(len(c[1]) for c in (cm.a, cm.b, cm.c))
+    h, k = 1 << (len(z) - 1).bit_length(), 1 << (nnz - 1).bit_length()
+    max_degree = max(3 * h, 4 * k)
+    beta, gamma = pow(3, 4004, p), pow(5, 3003, p)
+    pw = [1] * (max_degree + 2)
+    for i in range(1, max_degree + 2):
+        pw[i] = pw[i - 1] * beta % p
+    G = synthetic.generator(0)
+    pg = ctx.fixed_base_mul(0, G, synthetic._limbs_from_ints(pw[:max_degree + 1]))
+    pgg = ctx.fixed_base_mul(0, G, synthetic._limbs_from_ints([gamma * x % p for x in pw]))
+    powers = kzg.Powers(ctx, pairing, pg, pgg, precompute=True)
+    snark = marlin.MarlinSNARK(ctx, pairing)
+    t0 = time.perf_counter()
+    ipk = snark.index(cm, powers, max_degree)
+    ctx.sync()
+    index_s = time.perf_counter() - t0
+    R = (1 << 320) % p
+    zl = synthetic._limbs_from_ints([v * R % p for v in z])
+    blind = synthetic.random_limbs(4 * h + 64, field, 31337)
+
+    def make_rng():
+        it = iter(blind)
+        return lambda f: next(it)
+    proof = snark.prove(ipk, zl, make_rng())
+    marlin_check.check_in_exponent(snark, ipk, proof, beta, gamma, G)
+    if log:
+        log("Marlin proof (|H| = %d, |K| = %d, SRS %d) checked in the exponent" % (h, k, max_degree + 1))
+    snark.prove(ipk, zl, make_rng())
+    ctx.sync()
+    reps = 3
+    t0 = time.perf_counter()
+    for _ in range(reps):
+        snark.prove(ipk, zl, make_rng())
+    ctx.sync()
+    ms = (time.perf_counter() - t0) / reps * 1e3
+    ipk.close()
+    powers.close()
+    return {"proofs_per_s": 1e3 / ms, "ms_per_proof": ms, "pairing": "MNT4-298", "constraints": m, "H": h, "K": k,
+            "srs_points": max_degree + 1, "index_s": index_s, "timing": "host wall clock around MarlinSNARK.prove",
+            "note": "AHP rounds on device vectors (FFTs over H, K, 4K; CSR products; batch inversions), 9 KZG10 "
+                    "commitments + 2 batched openings as MSMs over the resident SRS; host: Poseidon transcript only"}
+
+
 def kernel_figures(args, ctx, dev, stream, imad_peak, co, rank=0, world=1, log=None):
     """G1 MSM Mpts/s at 2^20 (uniform scalars; resident bases with and without the window tables), the other sizes
     BASELINE.json names, and the largest radix-2 NTT (coset FFT over r4), each compared with the oracle once and then
@@ -783,6 +847,8 @@ def main():
     ap.add_argument("--tree-nodes", type=int, default=64)
     ap.add_argument("--gm17-log-n", type=int, default=18, help="SAP domain of the GM17 figure (2^k)")
     ap.add_argument("--no-gm17", action="store_true", help="skip the GM17 figure")
+    ap.add_argument("--no-marlin", action="store_true", help="skip the Marlin figure")
+    ap.add_argument("--marlin-log-h", type=int, default=15, help="|H| of the Marlin figure (2^k)")
     ap.add_argument("--no-proof20", action="store_true", help="skip the 2^20 single-proof figure")
     ap.add_argument("--no-tree", action="store_true")
     ap.add_argument("--no-sharded", action="store_true")

@@ -99,7 +99,9 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
   cudaDeviceGetStreamPriorityRange(&prio_least, &prio_greatest);
   static const bool no_prio = getenv("PCDGPU_NO_PRIORITIES") != nullptr;  // development aid (A/B runs)
   if (no_prio) prio_greatest = prio_least;
-  const int prio_mid = prio_greatest < prio_least ? prio_greatest + 1 : prio_least;
+  // (numerically smaller = more urgent) lane 0 > lanes 2, 3, 5, 6 (a, b_g1 -- the double-scalar multiplication waits for
+  // them -- and the extra MSMs of small proofs) > lane 1 (the G2 MSM) > lane 4 (l)
+  auto prio_at = [&](int k) { return prio_greatest + k < prio_least ? prio_greatest + k : prio_least; };
   // every partial failure goes through pcdgpu_ctx_destroy, which releases whatever was created so far
   int rc = PCDGPU_OK;
   if (cudaStreamCreateWithPriority(&ctx->own_stream, cudaStreamNonBlocking, prio_greatest) != cudaSuccess) rc = PCDGPU_E_CUDA;
@@ -107,9 +109,11 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
   if (rc == 0 && cudaEventCreateWithFlags(&ctx->ev_fork, cudaEventDisableTiming) != cudaSuccess) rc = PCDGPU_E_CUDA;
   for (int l = 1; l < pcdgpu_ctx::NLANE && rc == 0; l++)
     if (cudaStreamCreateWithPriority(&ctx->lane_stream[l], cudaStreamNonBlocking,
-                                     (l == 2 || l == 3 || l >= 5) ? prio_mid : prio_least) != cudaSuccess ||
+                                     (l == 2 || l == 3 || l >= 5) ? prio_at(1) : (l == 1 ? prio_at(2) : prio_least)) != cudaSuccess ||
         cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming) != cudaSuccess)
       rc = PCDGPU_E_CUDA;
+  for (int i = 0; i < 3 && rc == 0; i++)
+    if (cudaEventCreateWithFlags(&ctx->ev_acc[i], cudaEventDisableTiming) != cudaSuccess) rc = PCDGPU_E_CUDA;
   ctx->pinned_bytes = 1 << 16;
   if (rc == 0 && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) rc = PCDGPU_E_NOMEM;
   if (rc) {
@@ -132,6 +136,8 @@ void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx) {
     if (ctx->ev_join[l]) cudaEventDestroy(ctx->ev_join[l]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (int i = 0; i < 3; i++)
+    if (ctx->ev_acc[i]) cudaEventDestroy(ctx->ev_acc[i]);
   for (auto& kv : ctx->ntt_tables) cudaFree(kv.second.twiddles);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->prof_pinned) cudaFreeHost(ctx->prof_pinned);
@@ -734,9 +740,38 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
                  {pk->a_query, (const char*)d_sz, nv - 1, extras + 7 * 40, 3, (char*)sums1 + 2 * x1},
                  {pk->b_g1_query, (const char*)d_rz, nv - 1, extras + 10 * 40, 3, (char*)sums1 + 3 * x1}};
   int rc = 0;
-  for (int j = 0; j < nlanes - 1 && rc == 0; j++) {
+  // the witness map is enqueued FIRST (lane 0, most urgent): its short kernels then start while the GPU is still
+  // empty instead of queueing behind the lanes' accumulation grids; when the lanes are serialised (profiling) it keeps
+  // its place after them so that the scratch it returns stays untouched until the h MSM
+  void* d_h = nullptr;
+  ctx->lane = 0;
+  if (fork) rc = witness_map_dev(ctx, r1cs, d_z, &d_h);
+  // Order of the accumulation grids of a large proof (the throughput-bound part; everything else hides under it): a and
+  // b_g1 first -- the double-scalar multiplication behind them is the longest serial tail (2 - 3 ms on one warp) and
+  // must start early --, then b_g2 (most urgent of the rest: its bucket reduction is the next longest tail), l and h.  Only the accumulate
+  // kernels are ordered (events recorded right after / waited right before their launch): sorting, bucket reduction
+  // and the tails of every lane still overlap freely.  Enqueue order = dependency order (an event must have been
+  // recorded before it is waited for).
+  // MEASURED (2^18 main proof, B200): ordering the grids this way is SLOWER than letting the lanes contend (9.05 vs
+  // 8.15 ms): b_g2's accumulate takes ~5.9 ms whenever it shares the SMs, whatever it shares them with, so delaying
+  // its start delays the proof.  Kept behind PCDGPU_ACC_ORDER for further experiments; off by default.
+  static const bool want_gates = getenv("PCDGPU_ACC_ORDER") != nullptr;
+  const bool gates = fork && !small && want_gates;
+  const int order_gated[6] = {1, 2, 0, 3, 4, 5}, order_plain[6] = {0, 1, 2, 3, 4, 5};
+  const int* order = gates ? order_gated : order_plain;
+  for (int q = 0; q < nlanes - 1 && rc == 0; q++) {
+    const int j = order[q];
     ctx->lane = fork ? j + 1 : 0;
+    if (gates) {
+      if (j == 1 || j == 2) ctx->gate_done = ctx->ev_acc[j - 1];
+      if (j == 0 || j == 3) {
+        ctx->gate_wait[0] = ctx->ev_acc[0];
+        ctx->gate_wait[1] = ctx->ev_acc[1];
+        if (j == 0) ctx->gate_done = ctx->ev_acc[2];
+      }
+    }
     rc = bases_msm(ctx, jobs[j].b, 0, jobs[j].sc, 1, jobs[j].n, jobs[j].ex, jobs[j].nex, jobs[j].out);
+    ctx->gate_wait[0] = ctx->gate_wait[1] = ctx->gate_done = nullptr;
     if (rc == 0 && j == 0) rc = point_to_affine(ctx, g2, sum2, 0, d_B);
     if (rc == 0 && j == 1) rc = point_to_affine(ctx, g1, sums1, 4, d_A);
     if (rc == 0 && j == 2 && !small) {
@@ -747,10 +782,11 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
     if (fork && rc == 0 && cudaEventRecord(ctx->ev_join[j + 1], ctx->lane_stream[j + 1]) != cudaSuccess) rc = PCDGPU_E_CUDA;
   }
   ctx->lane = 0;
-  void* d_h = nullptr;
-  if (rc == 0) rc = witness_map_dev(ctx, r1cs, d_z, &d_h);
+  if (rc == 0 && !fork) rc = witness_map_dev(ctx, r1cs, d_z, &d_h);
   // h: n coefficients vs n - 1 query points: truncated to the shorter
+  if (rc == 0 && gates) ctx->gate_wait[0] = ctx->ev_acc[2];  // h after b_g2's grid: lane 0 is the most urgent stream
   if (rc == 0) rc = bases_msm(ctx, pk->h_query, 0, d_h, 1, r1cs->n, nullptr, 0, (char*)sums1 + 0 * x1);
+  ctx->gate_wait[0] = ctx->gate_wait[1] = ctx->gate_done = nullptr;
   if (rc == 0 && fork)
     for (int l = 1; l < nlanes && rc == 0; l++)
       if (cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0) != cudaSuccess) rc = PCDGPU_E_CUDA;

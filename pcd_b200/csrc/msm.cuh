@@ -156,13 +156,19 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
                                                              const u32* __restrict__ perm, size_t nbuckets,
                                                              void* __restrict__ buckets, u32* __restrict__ heavy,
                                                              u32* __restrict__ queue, u32 heavy_thr, u32 split,
-                                                             u32* __restrict__ hflag) {
+                                                             u32* __restrict__ hflag, u32 quantum, u32 persistent_from) {
   typedef typename C::F F;
   typedef C CF;
   typedef typename CF::F FF;
   const unsigned lane = threadIdx.x & 31;
   const size_t nitems = nbuckets * split;
+  // CTAs below `persistent_from` retire once their warps have walked `quantum` entries per lane: every retirement is a
+  // point where the block scheduler can start a higher-priority lane's kernel (witness map, sorts, the G2 chain); the
+  // last CTAs of the grid stay until the queue is empty, so all the work is always done
+  const bool may_retire = blockIdx.x < persistent_from;
+  u32 walked = 0;
   for (;;) {
+    if (may_retire && __shfl_sync(0xffffffffu, walked, 0) >= quantum) break;
     u32 first = 0;
     if (lane == 0) first = atomicAdd(queue, 32u);
     first = __shfl_sync(0xffffffffu, first, 0);
@@ -191,6 +197,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
       hi = lo + (u32)(((unsigned long long)len * (part + 1)) / split);
       lo = a;
     }
+    walked += hi - lo;
     for (u32 e = lo; e < hi; e++) {
       u32 ent = entries[e];
       AffinePoint<FF> p = ld_base<C, PRE>(bases, ent & 0x7fffffffu);
@@ -258,13 +265,16 @@ __global__ void __launch_bounds__(128, PCD_SLICED_MIN_CTAS) msm_accumulate_slice
                                                                     const u32* __restrict__ perm, size_t nbuckets,
                                                                     void* __restrict__ buckets, u32* __restrict__ heavy,
                                                                     u32* __restrict__ queue, u32 heavy_thr, u32 split,
-                                                                    u32* __restrict__ hflag) {
+                                                                    u32* __restrict__ hflag, u32 quantum, u32 persistent_from) {
   typedef typename CS::F FF;
   const unsigned lane = threadIdx.x & 31;
   const int l = (int)(lane % 3u);
   const unsigned grp = lane / 3u;  // 0..9 (10: the two idle lanes)
   const size_t nitems = nbuckets * split;
+  const bool may_retire = blockIdx.x < persistent_from;  // see msm_accumulate_kernel
+  u32 walked = 0;
   for (;;) {
+    if (may_retire && __shfl_sync(0xffffffffu, walked, 0) >= quantum) break;
     u32 first = 0;
     if (lane == 0) first = atomicAdd(queue, 10u);
     first = __shfl_sync(0xffffffffu, first, 0);
@@ -297,6 +307,7 @@ __global__ void __launch_bounds__(128, PCD_SLICED_MIN_CTAS) msm_accumulate_slice
       hi = lo + (u32)(((unsigned long long)len * (part + 1)) / split);
       lo = a;
     }
+    walked += hi - lo;
     for (u32 e = lo; e < hi; e++) {
       u32 ent = entries[e];
       AffinePoint<FF> p = ld_base_sliced<CS>(bases, ent & 0x7fffffffu, l);
@@ -399,6 +410,102 @@ __global__ void __launch_bounds__(MSM_HEAVY_THREADS) msm_heavy_finish_kernel(
       if (hp_id[s] == h) acc.add(ld_vec_rw<XYZZ<C>>(hp_sum, s));
     cta_tree_sum<C>(sm, acc);
     if (threadIdx.x == 0) st_vec(buckets, heavy[1 + h], sm[0]);
+    __syncthreads();
+  }
+}
+
+// ---- the heavy path with the point sliced over three lanes (Fq3) --------------------------------------------------------
+// One thread per Fq3 point pays 58 - 82 dependent base-field products per group operation (40 - 60 us): the 128-thread
+// form above took 1.2 ms + 0.55 ms for the ONE heavy bucket of the helper proof's witness (the "scalar == 1" bucket) and
+// 1.0 ms of a 1.65 ms default-circuit proof.  Sliced, a group operation is a third as deep, a CTA holds 40 groups, and a
+// chunk is 320 entries (8 per group) followed by a 6-level tree.
+static constexpr int MSM_HEAVY_CHUNK_SLICED = 320;
+static constexpr int MSM_HEAVY_GROUPS = 40;  // 4 warps x 10 groups
+// one out-of-line copy of each group operation for the heavy path (by value: see ec.cuh on nvcc's stack colouring):
+// inlined into the three kernels below they took ptxas from 80 s to 9 min on this file
+template <class CS>
+__device__ __noinline__ XYZZ<CS> sliced_add_ni(XYZZ<CS> a, XYZZ<CS> b) {
+  a.add_impl(b);
+  return a;
+}
+template <class CS>
+__device__ __noinline__ XYZZ<CS> sliced_madd_ni(XYZZ<CS> a, AffinePoint<typename CS::F> p) {
+  a.madd_impl(p);
+  return a;
+}
+template <class CS>
+__device__ __forceinline__ void cta_tree_sum_sliced(void* sm, XYZZ<CS>& acc, int G, int l, bool live) {
+  if (live) st_xyzz_sliced<CS>(sm, (size_t)G, acc, l);
+  __syncthreads();
+  for (int s = 32; s > 0; s >>= 1) {
+    if (live && G < s && G + s < MSM_HEAVY_GROUPS) {
+      acc = sliced_add_ni<CS>(acc, ld_xyzz_sliced<CS>(sm, (size_t)(G + s), l));
+      st_xyzz_sliced<CS>(sm, (size_t)G, acc, l);
+    }
+    __syncthreads();
+  }
+}
+template <class CS, bool PRE>
+__global__ void __launch_bounds__(128) msm_accumulate_heavy_sliced_kernel(
+    const void* __restrict__ bases, const u32* __restrict__ offsets, const u32* __restrict__ entries,
+    const u32* __restrict__ heavy, u32* __restrict__ hp_count, u32* __restrict__ hp_id, void* __restrict__ hp_sum) {
+  typedef typename CS::F FF;
+  extern __shared__ uint4 sm4[];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = lane < 30;
+  const int l = (int)(lane % 3u);
+  const int G = (int)(warp * 10 + lane / 3u);
+  u32 nheavy = heavy[0] < (u32)MSM_MAX_HEAVY ? heavy[0] : (u32)MSM_MAX_HEAVY;
+  u32 job = 0;
+  for (u32 h = 0; h < nheavy; h++) {
+    u32 g = heavy[1 + h];
+    u32 lo = offsets[g], hi = offsets[g + 1];
+    u32 nchunks = (hi - lo + MSM_HEAVY_CHUNK_SLICED - 1) / MSM_HEAVY_CHUNK_SLICED;
+    for (u32 ch = 0; ch < nchunks; ch++, job++) {
+      if (job % gridDim.x != blockIdx.x) continue;
+      u32 e0 = lo + ch * MSM_HEAVY_CHUNK_SLICED;
+      u32 e1 = e0 + MSM_HEAVY_CHUNK_SLICED < hi ? e0 + MSM_HEAVY_CHUNK_SLICED : hi;
+      XYZZ<CS> acc = XYZZ<CS>::inf();
+      if (live) {
+        for (u32 e = e0 + (u32)G; e < e1; e += MSM_HEAVY_GROUPS) {
+          u32 ent = entries[e];
+          AffinePoint<FF> p = ld_base_sliced<CS>(bases, ent & 0x7fffffffu, l);
+          if (ent >> 31) p.y = p.y.neg();
+          acc = sliced_madd_ni<CS>(acc, p);
+        }
+      }
+      cta_tree_sum_sliced<CS>(sm4, acc, G, l, live);
+      if (warp == 0 && lane < 3) {
+        u32 slot = 0;
+        if (lane == 0) {
+          slot = atomicAdd(hp_count, 1u);
+          hp_id[slot] = h;
+        }
+        slot = __shfl_sync(7u, slot, 0);
+        st_xyzz_sliced<CS>(hp_sum, slot, acc, l);
+      }
+      __syncthreads();
+    }
+  }
+}
+template <class CS>
+__global__ void __launch_bounds__(128) msm_heavy_finish_sliced_kernel(
+    const u32* __restrict__ heavy, const u32* __restrict__ hp_count, const u32* __restrict__ hp_id,
+    const void* __restrict__ hp_sum, void* __restrict__ buckets) {
+  extern __shared__ uint4 sm4[];
+  const unsigned lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const bool live = lane < 30;
+  const int l = (int)(lane % 3u);
+  const int G = (int)(warp * 10 + lane / 3u);
+  u32 nheavy = heavy[0] < (u32)MSM_MAX_HEAVY ? heavy[0] : (u32)MSM_MAX_HEAVY;
+  u32 np = *hp_count;
+  for (u32 h = blockIdx.x; h < nheavy; h += gridDim.x) {
+    XYZZ<CS> acc = XYZZ<CS>::inf();
+    if (live)
+      for (u32 s = (u32)G; s < np; s += MSM_HEAVY_GROUPS)
+        if (hp_id[s] == h) acc = sliced_add_ni<CS>(acc, ld_xyzz_sliced<CS>(hp_sum, s, l));
+    cta_tree_sum_sliced<CS>(sm4, acc, G, l, live);
+    if (warp == 0 && lane < 3) st_xyzz_sliced<CS>(buckets, heavy[1 + h], acc, l);
     __syncthreads();
   }
 }
@@ -551,6 +658,11 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                                                                       plan.stride, plan.offset, cursor, (u32*)ent);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
+  for (int gi = 0; gi < 2; gi++)  // the prover's order of the accumulation grids (common.cuh: gate_wait / gate_done)
+    if (ctx->gate_wait[gi]) {
+      PCD_CUDA(ctx, cudaStreamWaitEvent(st, ctx->gate_wait[gi], 0));
+      ctx->gate_wait[gi] = nullptr;
+    }
   ps = ctx->prof_begin(acc_slot, (double)n * nwin);
   if (ps >= 0 && ctx->prof_pinned) {  // exact number of bucket entries (non-zero digits) for the roofline
     ctx->spans[ps].units_pinned = ps;
@@ -592,24 +704,45 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   u32 split = 1;
   while (split < (u32)MSM_MAX_SPLIT && nbuckets * split < 6 * acc_grid * ITEMS_PER_CTA && avg_entries / (2 * split) >= 8) split *= 2;
   if (acc_grid > (nbuckets * split + ITEMS_PER_CTA - 1) / ITEMS_PER_CTA) acc_grid = (nbuckets * split + ITEMS_PER_CTA - 1) / ITEMS_PER_CTA;
+  // inside a proof the CTAs retire after ~a quarter of a millisecond of work (quantum entries per lane) so that the
+  // other lanes' kernels are not starved by a persistent grid; a lone MSM keeps the persistent form
+  static const int quantum_env = getenv("PCDGPU_ACC_QUANTUM") ? atoi(getenv("PCDGPU_ACC_QUANTUM")) : -1;  // development aid
+  u32 quantum = 0, persistent_from = 0;
+  {
+    const int prods = SLICED ? 20 : (sizeof(typename C::F) / 40 == 1 ? 10 : 28);
+    int q = quantum_env >= 0 ? quantum_env : (ctx->concurrent && ctx->in_proof ? 320 / prods : 0);
+    if (q > 0) {
+      const size_t resident = acc_grid;
+      const size_t per_cta = (size_t)q * (SLICED ? 40 : 128);
+      size_t extra = (total + per_cta - 1) / per_cta;
+      if (extra > 65535) extra = 65535;
+      quantum = (u32)q;
+      persistent_from = (u32)extra;
+      acc_grid = resident + extra;
+    }
+  }
   PCD_TRY(ctx->scratch(SLOT_MSM_BKT, nbuckets * sizeof(XYZZ<C>) * (split > 1 ? 1 + split : 1), &bkt));  // buckets | parts
   void* acc_out = split > 1 ? (void*)((char*)bkt + nbuckets * sizeof(XYZZ<C>)) : bkt;
   if constexpr (SLICED) {
     if (shared)
       msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, true><<<(unsigned)acc_grid, 128, 0, st>>>(
-          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor);
+          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from);
     else
       msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, false><<<(unsigned)acc_grid, 128, 0, st>>>(
-          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor);
+          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from);
   } else {
     if (shared)
       msm_accumulate_kernel<C, true><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                       acc_out, heavy, queue, heavy_thr, split, cursor);
+                                                                       acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from);
     else
       msm_accumulate_kernel<C, false><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                        acc_out, heavy, queue, heavy_thr, split, cursor);
+                                                                        acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from);
   }
   PCD_CUDA(ctx, cudaGetLastError());
+  if (ctx->gate_done) {
+    PCD_CUDA(ctx, cudaEventRecord(ctx->gate_done, st));
+    ctx->gate_done = nullptr;
+  }
   if (split > 1) {
     if constexpr (SLICED)
       msm_fold_parts_sliced_kernel<typename MsmSliced<C>::type><<<(unsigned)((nbuckets + 29) / 30), 96, 0, st>>>(
@@ -621,27 +754,40 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   }
   size_t heavy_smem = MSM_HEAVY_THREADS * sizeof(XYZZ<C>);
   // heavy-bucket partial list: at most one partial per MSM_HEAVY_CHUNK entries plus one per bucket
-  size_t hp_cap = total / MSM_HEAVY_CHUNK + MSM_MAX_HEAVY + 8;
+  size_t hp_cap = total / (SLICED ? MSM_HEAVY_CHUNK_SLICED : MSM_HEAVY_CHUNK) + MSM_MAX_HEAVY + 8;
   void* hp;
   PCD_TRY(ctx->scratch(SLOT_MSM_HP, hp_cap * (sizeof(XYZZ<C>) + 4) + 64, &hp));
   u32* hp_count = (u32*)hp;
   u32* hp_id = hp_count + 4;
   void* hp_sum = (char*)hp + 64 + ((hp_cap * 4 + 63) & ~(size_t)63);
   PCD_CUDA(ctx, cudaMemsetAsync(hp_count, 0, 4, st));
-  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)heavy_smem));
-  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)heavy_smem));
-  PCD_CUDA(ctx, cudaFuncSetAttribute(msm_heavy_finish_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                     (int)heavy_smem));
-  if (shared)
-    msm_accumulate_heavy_kernel<C, true><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
-        d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
-  else
-    msm_accumulate_heavy_kernel<C, false><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
-        d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
-  PCD_CUDA(ctx, cudaGetLastError());
-  msm_heavy_finish_kernel<C><<<64, MSM_HEAVY_THREADS, heavy_smem, st>>>(heavy, hp_count, hp_id, hp_sum, bkt);
+  if constexpr (SLICED) {
+    typedef typename MsmSliced<C>::type CS;
+    const size_t sl_smem = MSM_HEAVY_GROUPS * sizeof(XYZZ<C>);
+    if (shared)
+      msm_accumulate_heavy_sliced_kernel<CS, true><<<ctx->sm_count * 4, 128, sl_smem, st>>>(
+          d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
+    else
+      msm_accumulate_heavy_sliced_kernel<CS, false><<<ctx->sm_count * 4, 128, sl_smem, st>>>(
+          d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
+    PCD_CUDA(ctx, cudaGetLastError());
+    msm_heavy_finish_sliced_kernel<CS><<<64, 128, sl_smem, st>>>(heavy, hp_count, hp_id, hp_sum, bkt);
+  } else {
+    PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)heavy_smem));
+    PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)heavy_smem));
+    PCD_CUDA(ctx, cudaFuncSetAttribute(msm_heavy_finish_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                       (int)heavy_smem));
+    if (shared)
+      msm_accumulate_heavy_kernel<C, true><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
+          d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
+    else
+      msm_accumulate_heavy_kernel<C, false><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
+          d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
+    PCD_CUDA(ctx, cudaGetLastError());
+    msm_heavy_finish_kernel<C><<<64, MSM_HEAVY_THREADS, heavy_smem, st>>>(heavy, hp_count, hp_id, hp_sum, bkt);
+  }
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
   ps = ctx->prof_begin(PROF_MSM_REDUCE, (double)nbuckets);

@@ -210,7 +210,9 @@ struct Wec {
 #pragma unroll
       for (int i = 0; i < 10; i++) t |= e[gl * 10 + i];
     }
-    return __ballot_sync(gmask, t != 0) == 0;
+    const bool z = __ballot_sync(gmask, t != 0) == 0;
+    sync();  // the vote orders execution, __syncwarp also orders the reads above against the group's later writes
+    return z;
   }
   __device__ bool is_inf(const u32* p) const { return ext_zero(p + 2 * EW); }
   __device__ void copy(u32* dst, const u32* src, int nwords = PW) const {

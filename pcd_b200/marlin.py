@@ -643,8 +643,9 @@ class MarlinSNARK:
         fs.absorb_nonnative_field_elements([e for _, e in evaluations])
         n_open = sum(2 if l in ("g_1", "g_2") else 1 for l, _, _ in lcs)
         opening = fs.squeeze_128_bits_nonnative_field_elements(n_open)
-        pc_proof = self._open_combinations(pk, polys, lcs, ch, opening)
-        self.last_trace = dict(challenges=ch, opening_challenges=opening)
+        pc_proof, combined = self._open_combinations(pk, polys, lcs, ch, opening)
+        # what a checker needs beyond the proof (tests / bench gate): the polynomials behind the commitments
+        self.last_trace = dict(challenges=ch, opening_challenges=opening, polys=polys, lcs=lcs, combined=combined)
         return Proof(self.pairing, [first, second, third], evaluations, pc_proof)
 
     def _open_combinations(self, pk: IndexProverKey, polys, lcs, ch, opening):
@@ -653,7 +654,7 @@ class MarlinSNARK:
         X^(max_degree - bound) under the next challenge; one kzg10::Proof per point"""
         ops, F, ctx, field = pk.ops, pk.ops.F, self.ctx, self.field
         p, D = F.p, pk.pc.max_degree
-        out = []
+        out, combined = [], {}
         for point_label in sorted({pl for _, pl, _ in lcs}):
             zpt = ch[point_label]
             here = sorted((lc for lc in lcs if lc[1] == point_label), key=lambda t: t[0])
@@ -690,7 +691,8 @@ class MarlinSNARK:
             random_v = (_host_eval(p, acc_r, zpt) + _host_eval(p, shifted_r, zpt)) % p if hiding else None
             w = pk.pc._msm(w_poly, 0, F.enc_many(rw) if rw else None)
             out.append((point_label, w, random_v))
-        return out
+            combined[point_label] = (acc, acc_r, shifted_r, w_poly, rw)
+        return out, combined
 
 
 # blinding polynomials are three coefficients long: they live on the host as integers

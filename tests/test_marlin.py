@@ -236,3 +236,34 @@ def test_gpu_marlin_matches_oracle(ctx, pairing, m, pre):
     assert mo.check_proof(S["idx"], flat, CF_OF[pairing], S["z"][:S["r1cs"].num_inputs], as_oracle, trace,
                           S["max_degree"], S["beta"], S["gamma"], point_of_log, coords)
     ipk.close()
+
+
+@pytest.mark.gpu
+@pytest.mark.parametrize("pairing,m", [(0, 3000), (1, 2500)])
+def test_gpu_marlin_larger_trapdoor(ctx, pairing, m):
+    """beyond the Python oracle prover's reach: the GPU proof checked in the exponent (tests/marlin_check.py)"""
+    import marlin_check
+    fp = FP_OF[pairing]
+    r1cs, z = o.synthetic_r1cs(fp, m, 2, 17, 0.3)
+    nnz = max(sum(len(r) for r in M) for M in (r1cs.A, r1cs.B, r1cs.C))
+    h = 1 << (max(r1cs.num_vars, m) - 1).bit_length()
+    k = 1 << (nnz - 1).bit_length()
+    max_degree = max(3 * h, 4 * k)
+    p = fp.p
+    beta, gamma = pow(3, 2002, p), pow(5, 555, p)
+    G = synth.generator_limbs(codec.G1_OF[pairing])
+    pg, pgg = ko.setup(pairing, max_degree, beta, gamma, G, 0)
+    S = dict(pairing=pairing, fp=fp, r1cs=r1cs, z=z, pg=pg, pgg=pgg, max_degree=max_degree)
+    proof, ipk, snark, ndraws = gpu_prove(ctx, S, seed=3, precompute=True)
+    assert ndraws == 3 + 3 * ipk.H.n + 4 * 3 + 2 * 3
+    assert marlin_check.check_in_exponent(snark, ipk, proof, beta, gamma, G)
+    # a corrupted witness must not survive: the outer sumcheck LC no longer vanishes
+    zbad = list(z)
+    j = max(i for i, v in enumerate(z) if v > 1)  # not a boolean variable (0 -> 1 would still satisfy b * b = b)
+    zbad[j] = (zbad[j] + 1) % p
+    assert not r1cs.is_satisfied(zbad)
+    S2 = dict(S, z=zbad)
+    proof2, ipk2, snark2, _ = gpu_prove(ctx, S2, seed=3)
+    with pytest.raises(AssertionError):
+        marlin_check.check_in_exponent(snark2, ipk2, proof2, beta, gamma, G)
+    ipk.close(); ipk2.close()
