@@ -686,9 +686,18 @@ def marlin_figure(args, ctx, co, log):
     zl = synthetic._limbs_from_ints([v * R % p for v in z])
     blind = synthetic.random_limbs(4 * h + 64, field, 31337)
 
-    def make_rng():
-        it = iter(blind)
-        return lambda f: next(it)
+    class BulkRng:  # the caller's rng: consecutive draws from one precomputed stream, handed out in bulk
+        def __init__(self):
+            self.pos = 0
+
+        def many(self, f, n):
+            self.pos += n
+            return blind[self.pos - n:self.pos]
+
+        def __call__(self, f):
+            return self.many(f, 1)[0]
+
+    make_rng = BulkRng
     proof = snark.prove(ipk, zl, make_rng())
     marlin_check.check_in_exponent(snark, ipk, proof, beta, gamma, G)
     if log:

@@ -282,7 +282,7 @@ static int ntt_run_t(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int in
   void* scratch = nullptr;
   if (passes > 1) PCD_TRY(ctx->scratch(SLOT_NTT, (((size_t)40) << log_n) * batch, &scratch));
   int s = 0;
-  int ps = ctx->prof_begin(PROF_NTT, (double)log_n * (double)((size_t)1 << (log_n - 1)));
+  int ps = ctx->prof_begin(PROF_NTT, (double)batch * (double)log_n * (double)((size_t)1 << (log_n - 1)));
   ctx->launches += passes;
   for (int p = 0; p < passes; p++) {
     int r = (log_n - s + (passes - p) - 1) / (passes - p);  // spread stages evenly, larger first
@@ -541,6 +541,13 @@ int ntt_domain_shape(int field, size_t min_size, size_t* n, int* a, int* b) {
   return found ? 0 : PCDGPU_E_DOMAIN;
 }
 
+// `batch` transforms of 2^log_n elements stored back to back, one launch per pass (blockIdx.y = transform)
+int ntt_run_batch(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int inverse, int coset, int batch) {
+  if (field == PCDGPU_FIELD_R4) return ntt_run_t<FpR4>(ctx, field, d_data, log_n, inverse, coset, batch);
+  if (field == PCDGPU_FIELD_Q4) return ntt_run_t<FpQ4>(ctx, field, d_data, log_n, inverse, coset, batch);
+  ctx->set_error("unknown field id %d", field);
+  return PCDGPU_E_ARG;
+}
 int ntt_run(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int inverse, int coset) {
   if (field == PCDGPU_FIELD_R4) return ntt_run_t<FpR4>(ctx, field, d_data, log_n, inverse, coset);
   if (field == PCDGPU_FIELD_Q4) return ntt_run_t<FpQ4>(ctx, field, d_data, log_n, inverse, coset);

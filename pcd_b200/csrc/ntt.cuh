@@ -13,6 +13,7 @@ struct NttTablesDev {
 int ntt_tables(pcdgpu_ctx* ctx, int field, int log_n, NttTablesDev* out);
 // in-place transform of 2^log_n elements at d_data (device), async on ctx->stream
 int ntt_run(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int inverse, int coset);
+int ntt_run_batch(pcdgpu_ctx* ctx, int field, void* d_data, int log_n, int inverse, int coset, int batch);
 // transform on the general domain 7^a 2^b (a > 0 only on q4); in place, async on ctx->stream
 int ntt_run_general(pcdgpu_ctx* ctx, int field, void* d_data, int a, int b, int inverse, int coset);
 // GeneralEvaluationDomain::new(min_size) -> n = 7^a 2^b, or PCDGPU_E_DOMAIN

@@ -254,6 +254,17 @@ class _Ops:
         return v
 
 
+def draw_many(rng, field: int, n: int) -> np.ndarray:
+    """n consecutive `F::rand` draws of the caller's rng as (n, 5) Montgomery limbs.  An rng object may offer
+    `many(field, n)` for bulk draws (the mask polynomial is 3|H| of them); the order is the same either way."""
+    if hasattr(rng, "many"):
+        out = np.ascontiguousarray(rng.many(field, n), dtype=np.uint64).reshape(-1, 5)
+        if out.shape[0] != n:
+            raise ValueError("rng.many returned %d draws, %d were asked for" % (out.shape[0], n))
+        return out
+    return np.stack([rng(field) for _ in range(n)]).astype(np.uint64)
+
+
 # ---- ark-poly-commit marlin_pc ------------------------------------------------------------------------------------
 @dataclass
 class LabeledPolynomial:
@@ -309,9 +320,9 @@ class MarlinKZG10:
             field = lp.polynomial.field
             if lp.hiding_bound is not None:
                 k = kzg.hiding_blinding_coefficients(lp.hiding_bound)
-                lp.rand = np.stack([rng(field) for _ in range(k)]).astype(np.uint64)
+                lp.rand = draw_many(rng, field, k)
                 if lp.degree_bound is not None:
-                    lp.shifted_rand = np.stack([rng(field) for _ in range(k)]).astype(np.uint64)
+                    lp.shifted_rand = draw_many(rng, field, k)
             c = Commitment(lp.label, self._msm(lp.polynomial, 0, lp.rand))
             if lp.degree_bound is not None:
                 if lp.polynomial.n > lp.degree_bound + 1:
@@ -543,15 +554,15 @@ class MarlinSNARK:
         x_masked = ops.gather(x_evals, pk.x_index.ptr, h)
         ops.binary(SUB, w_evals, w_evals, x_masked, h)
         ops.ntt(w_evals, H, True)
-        blind = [F.dec(rng(field)) for _ in range(ZK_BOUND)]
+        blind = [F.dec(x) for x in draw_many(rng, field, ZK_BOUND)]
         w_full = add_vanishing_multiple(w_evals, blind[0])
         w_poly, w_rem = ops.divide_by_vanishing(w_full, x)
         ops.ntt(z_a, H, True)
-        z_a_poly = add_vanishing_multiple(z_a, F.dec(rng(field)))
+        z_a_poly = add_vanishing_multiple(z_a, F.dec(draw_many(rng, field, ZK_BOUND)[0]))
         ops.ntt(z_b, H, True)
-        z_b_poly = add_vanishing_multiple(z_b, F.dec(rng(field)))
+        z_b_poly = add_vanishing_multiple(z_b, F.dec(draw_many(rng, field, ZK_BOUND)[0]))
         mask_len = 3 * h + 2 * ZK_BOUND - 2
-        mask_host = np.stack([rng(field) for _ in range(mask_len)]).astype(np.uint64)
+        mask_host = draw_many(rng, field, mask_len).copy()
         fix = sum(F.dec(mask_host[i]) for i in range(0, mask_len, h)) % p
         mask_host[0] = F.enc(F.dec(mask_host[0]) - fix)  # the mask sums to zero over H
         mask_poly = DVec.from_host(ctx, field, mask_host)
