@@ -363,9 +363,17 @@ def run_gpu(args, rank, local_rank, world):
     ms_serial = e0.elapsed_time(e1)
     launches2 = ctypes.c_uint64()
     ctx._check(ctx.lib.pcdgpu_profile_read(ctx.h, ms, units, spans, ctypes.byref(launches2)))
+    prof = {"ms": list(ms), "units": list(units), "spans": list(spans)}
+    # the same pass proof by proof: the step mixes MSMs of 2^18, 2^16 and 2^10 points in one kernel class, the roofline
+    # is stated for the dominant kernel of the dominant proof
+    prof_parts = {}
+    for part, (r, s) in zip(step.parts, rs[1]):
+        for _ in range(args.steps):
+            part["g"].create_proof_dev(part["idx"], part["z_dev"].data_ptr(), r, s)
+        ctx._check(ctx.lib.pcdgpu_profile_read(ctx.h, ms, units, spans, ctypes.byref(launches2)))
+        prof_parts[part["label"]] = {"ms": list(ms), "units": list(units), "spans": list(spans)}
     ctx.lib.pcdgpu_profile_enable(ctx.h, 0)
     ctx.set_concurrency(True)
-    prof = {"ms": list(ms), "units": list(units), "spans": list(spans)}
     # per-proof latencies of the step (device time of each of the four calls)
     per_proof = {}
     for part, (r, s) in zip(step.parts, rs[1]):
@@ -415,12 +423,19 @@ def run_gpu(args, rank, local_rank, world):
     shares = {PROF_NAMES[i]: round(prof["ms"][i] / total_ms, 4) for i in range(NC)}
     # the dominant kernel: bucket accumulation of the large MSMs, per coordinate field (the default-circuit proofs'
     # MSMs of ~10^3 points are a latency-bound regime of their own and are reported as their own class)
-    dom = max(PROF_ACC, key=lambda i: prof["ms"][i])
+    dom_part, dom = max(((lbl, i) for lbl in prof_parts for i in PROF_ACC), key=lambda t: prof_parts[t[0]]["ms"][t[1]])
+    pp = prof_parts[dom_part]
     deg = PROF_ACC[dom]
-    imads = prof["units"][dom] * MADD_MODMULS[deg] * MODMUL_IMADS
+    imads = pp["units"][dom] * MADD_MODMULS[deg] * MODMUL_IMADS
     work = "bucket entries x %d Montgomery products (XYZZ mixed addition 8M + 2S over %s) x %d IMAD" % (
         MADD_MODMULS[deg], {1: "Fq", 2: "Fq2", 3: "Fq3"}[deg], MODMUL_IMADS)
-    achieved = imads / (prof["ms"][dom] * 1e-3) / 1e12 if prof["ms"][dom] > 0 else 0.0
+    achieved = imads / (pp["ms"][dom] * 1e-3) / 1e12 if pp["ms"][dom] > 0 else 0.0
+    step_frac = (prof["units"][dom] * MADD_MODMULS[deg] * MODMUL_IMADS / (prof["ms"][dom] * 1e-3) / imad_peak
+                 if prof["ms"][dom] > 0 else None)
+    by_proof = {lbl: {PROF_NAMES[i]: {"ms_per_proof": q["ms"][i] / args.steps,
+                                      "frac": (q["units"][i] * MADD_MODMULS[PROF_ACC[i]] * MODMUL_IMADS / (q["ms"][i] * 1e-3)
+                                               / imad_peak)}
+                      for i in PROF_ACC if q["ms"][i] > 0} for lbl, q in prof_parts.items()}
     hbm_peak, hbm_src = load_peaks()
     traffic = None
     try:
@@ -432,13 +447,18 @@ def run_gpu(args, rank, local_rank, world):
                                         / imad_peak) if prof["ms"][i] > 0 else None,
                                "ms_per_step": prof["ms"][i] / args.steps} for i in PROF_ACC if i != dom}
     roofline = {
-        "kernel": PROF_NAMES[dom], "bound": "imad", "achieved": achieved, "peak": imad_peak / 1e12, "unit": "TIMAD/s",
+        "kernel": PROF_NAMES[dom], "proof": dom_part, "bound": "imad", "achieved": achieved, "peak": imad_peak / 1e12,
+        "unit": "TIMAD/s",
         "frac": achieved / (imad_peak / 1e12), "traffic": traffic,
         "traffic_note": "DRAM bytes of one launch from the committed ncu capture (profiles/r02_traffic.json); algorithmic: "
                         "80 / 160 / 240 B per gathered point + 4 B per entry",
         "peak_source": "measured live: IMAD.WIDE.U32 issue rate of the fmaheavy pipe (32 lanes/clk/SM), max of the "
                        "independent accumulate form (%.2f T/s) and the carry-chain form (%.2f T/s)" % (imad_indep / 1e12, imad_chain / 1e12),
-        "launch_ms_avg": prof["ms"][dom] / max(prof["spans"][dom], 1), "work": work,
+        "launch_ms_avg": pp["ms"][dom] / max(pp["spans"][dom], 1), "work": work,
+        "scope": "the accumulation phase (accumulate + part fold + heavy-bucket kernels) of the %s proof's MSMs of this "
+                 "class, lanes serialised; the same class over the whole step (2^18, 2^16 and 2^10-point MSMs mixed): "
+                 "frac %s" % (dom_part, "%.3f" % step_frac if step_frac is not None else "n/a"),
+        "accumulation_by_proof": by_proof,
         "other_accumulation_classes": others,
     }
     value = world * args.steps / (ms_dev * 1e-3)

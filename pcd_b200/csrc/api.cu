@@ -113,7 +113,9 @@ int pcdgpu_ctx_create(int device, pcdgpu_ctx** out) {
         cudaEventCreateWithFlags(&ctx->ev_join[l], cudaEventDisableTiming) != cudaSuccess)
       rc = PCDGPU_E_CUDA;
   for (int i = 0; i < 3 && rc == 0; i++)
-    if (cudaEventCreateWithFlags(&ctx->ev_acc[i], cudaEventDisableTiming) != cudaSuccess) rc = PCDGPU_E_CUDA;
+    if (cudaEventCreateWithFlags(&ctx->ev_acc[i], cudaEventDisableTiming) != cudaSuccess ||
+        cudaEventCreateWithFlags(&ctx->ev_sorted[i], cudaEventDisableTiming) != cudaSuccess)
+      rc = PCDGPU_E_CUDA;
   ctx->pinned_bytes = 1 << 16;
   if (rc == 0 && cudaMallocHost(&ctx->pinned, ctx->pinned_bytes) != cudaSuccess) rc = PCDGPU_E_NOMEM;
   if (rc) {
@@ -136,8 +138,10 @@ void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx) {
     if (ctx->ev_join[l]) cudaEventDestroy(ctx->ev_join[l]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
-  for (int i = 0; i < 3; i++)
+  for (int i = 0; i < 3; i++) {
     if (ctx->ev_acc[i]) cudaEventDestroy(ctx->ev_acc[i]);
+    if (ctx->ev_sorted[i]) cudaEventDestroy(ctx->ev_sorted[i]);
+  }
   for (auto& kv : ctx->ntt_tables) cudaFree(kv.second.twiddles);
   if (ctx->pinned) cudaFreeHost(ctx->pinned);
   if (ctx->prof_pinned) cudaFreeHost(ctx->prof_pinned);
@@ -757,11 +761,23 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   // its start delays the proof.  Kept behind PCDGPU_ACC_ORDER for further experiments; off by default.
   static const bool want_gates = getenv("PCDGPU_ACC_ORDER") != nullptr;
   const bool gates = fork && !small && want_gates;
-  const int order_gated[6] = {1, 2, 0, 3, 4, 5}, order_plain[6] = {0, 1, 2, 3, 4, 5};
-  const int* order = gates ? order_gated : order_plain;
+  // What IS ordered by default (large proofs): b_g2's accumulation grid starts only when the a, b_g1 and l lanes have
+  // finished SORTING.  Its CTAs fill the register file (Fq2: 234 registers, Fq3 sliced: four CTAs per SM) and its first
+  // work items are the largest buckets, so for the first millisecond nothing retires and the other lanes' sort kernels
+  // (0.1 - 0.25 ms each alone) crawled for 0.9 - 1.4 ms, delaying the a / b_g1 accumulation and with it the
+  // double-scalar multiplication.
+  static const bool no_sort_gate = getenv("PCDGPU_NO_SORT_GATE") != nullptr;  // development aid (A/B runs)
+  const bool sort_gate = fork && !small && !gates && !no_sort_gate;
+  const int order_gated[6] = {1, 2, 0, 3, 4, 5}, order_plain[6] = {0, 1, 2, 3, 4, 5}, order_sorted[6] = {1, 2, 3, 0, 4, 5};
+  const int* order = gates ? order_gated : (sort_gate ? order_sorted : order_plain);
   for (int q = 0; q < nlanes - 1 && rc == 0; q++) {
     const int j = order[q];
     ctx->lane = fork ? j + 1 : 0;
+    if (sort_gate) {
+      if (j >= 1 && j <= 3) ctx->sort_done = ctx->ev_sorted[j - 1];
+      if (j == 0)
+        for (int k = 0; k < 3; k++) ctx->gate_wait[k] = ctx->ev_sorted[k];
+    }
     if (gates) {
       if (j == 1 || j == 2) ctx->gate_done = ctx->ev_acc[j - 1];
       if (j == 0 || j == 3) {
@@ -771,7 +787,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
       }
     }
     rc = bases_msm(ctx, jobs[j].b, 0, jobs[j].sc, 1, jobs[j].n, jobs[j].ex, jobs[j].nex, jobs[j].out);
-    ctx->gate_wait[0] = ctx->gate_wait[1] = ctx->gate_done = nullptr;
+    ctx->gate_wait[0] = ctx->gate_wait[1] = ctx->gate_wait[2] = ctx->gate_done = ctx->sort_done = nullptr;
     if (rc == 0 && j == 0) rc = point_to_affine(ctx, g2, sum2, 0, d_B);
     if (rc == 0 && j == 1) rc = point_to_affine(ctx, g1, sums1, 4, d_A);
     if (rc == 0 && j == 2 && !small) {

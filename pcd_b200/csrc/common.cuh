@@ -80,8 +80,11 @@ struct pcdgpu_ctx {
   // Order of the accumulation grids inside a proof (set by the prover before an MSM, consumed by it): the next MSM's
   // accumulate kernel waits for gate_wait[*] and records gate_done right after its launch.  ev_acc: a, b_g1, b_g2.
   cudaEvent_t ev_acc[3] = {nullptr, nullptr, nullptr};
-  cudaEvent_t gate_wait[2] = {nullptr, nullptr};
+  cudaEvent_t gate_wait[3] = {nullptr, nullptr, nullptr};
   cudaEvent_t gate_done = nullptr;
+  // ev_sorted[k]: recorded after the scatter kernel (end of the sorting phase) of the MSM that was given sort_done
+  cudaEvent_t ev_sorted[3] = {nullptr, nullptr, nullptr};
+  cudaEvent_t sort_done = nullptr;
   cudaStream_t cur() const { return lane == 0 ? stream : lane_stream[lane]; }
   // grow-only scratch slots (slot ids are fixed per use and lane so concurrent phases never alias)
   static const int NSLOT = SLOTS_PER_LANE * NLANE;

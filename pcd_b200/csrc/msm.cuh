@@ -658,7 +658,11 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                                                                       plan.stride, plan.offset, cursor, (u32*)ent);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->prof_end(ps);
-  for (int gi = 0; gi < 2; gi++)  // the prover's order of the accumulation grids (common.cuh: gate_wait / gate_done)
+  if (ctx->sort_done) {
+    PCD_CUDA(ctx, cudaEventRecord(ctx->sort_done, st));
+    ctx->sort_done = nullptr;
+  }
+  for (int gi = 0; gi < 3; gi++)  // the prover's order of the accumulation grids (common.cuh: gate_wait / gate_done)
     if (ctx->gate_wait[gi]) {
       PCD_CUDA(ctx, cudaStreamWaitEvent(st, ctx->gate_wait[gi], 0));
       ctx->gate_wait[gi] = nullptr;
