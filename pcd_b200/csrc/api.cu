@@ -761,13 +761,15 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   // its start delays the proof.  Kept behind PCDGPU_ACC_ORDER for further experiments; off by default.
   static const bool want_gates = getenv("PCDGPU_ACC_ORDER") != nullptr;
   const bool gates = fork && !small && want_gates;
-  // What IS ordered by default (large proofs): b_g2's accumulation grid starts only when the a, b_g1 and l lanes have
+  // A lighter ordering, also measured: b_g2's accumulation grid starts only when the a, b_g1 and l lanes have
   // finished SORTING.  Its CTAs fill the register file (Fq2: 234 registers, Fq3 sliced: four CTAs per SM) and its first
   // work items are the largest buckets, so for the first millisecond nothing retires and the other lanes' sort kernels
   // (0.1 - 0.25 ms each alone) crawled for 0.9 - 1.4 ms, delaying the a / b_g1 accumulation and with it the
   // double-scalar multiplication.
-  static const bool no_sort_gate = getenv("PCDGPU_NO_SORT_GATE") != nullptr;  // development aid (A/B runs)
-  const bool sort_gate = fork && !small && !gates && !no_sort_gate;
+  // MEASURED: helper (MNT6, 2^16) 5.4 - 5.6 -> 5.3 - 5.4 ms, main (MNT4, 2^18) 8.0 - 8.2 -> 8.6 - 8.7 ms: off by default
+  // (PCDGPU_SORT_GATE enables it for experiments)
+  static const bool want_sort_gate = getenv("PCDGPU_SORT_GATE") != nullptr;
+  const bool sort_gate = fork && !small && !gates && want_sort_gate;
   const int order_gated[6] = {1, 2, 0, 3, 4, 5}, order_plain[6] = {0, 1, 2, 3, 4, 5}, order_sorted[6] = {1, 2, 3, 0, 4, 5};
   const int* order = gates ? order_gated : (sort_gate ? order_sorted : order_plain);
   for (int q = 0; q < nlanes - 1 && rc == 0; q++) {

@@ -55,12 +55,30 @@ __host__ __device__ __forceinline__ int msm_win_start(int j, int c, int nwin, in
 // Scalars i < n_main come from `scalars` (Montgomery form if mont), the n - n_main trailing ones from
 // `extra` (always plain integers): the per-proof pairs (delta, r), (a_query[0], 1), ... that the
 // Groth16 prover folds into its MSMs.
+// A base point at infinity (x = y = 0: the query point of a variable that never occurs in the matrix -- common in
+// b_query) gets all-zero digits: left in, its bucket entries cost a full mixed addition of WARP time each (the lane
+// that holds it sits out while its neighbours add), measured as 10 - 16 active lanes of 32 in the a / b_g1 MSMs of
+// the synthetic key.  bases / point_u4 / base_first: row 0 of the (table of) base points, 16-byte words per point,
+// index of scalar 0's point.
 template <class SP>
 __global__ void msm_digits_kernel(const u32* __restrict__ scalars, int mont, size_t n_main,
                                   const u32* __restrict__ extra, size_t n, int c, int nwin, int shared,
-                                  int* __restrict__ dig, u32* __restrict__ counts) {
+                                  int* __restrict__ dig, u32* __restrict__ counts, const uint4* __restrict__ bases,
+                                  int point_u4, size_t base_first) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
+  {
+    const uint4* bp = bases + (base_first + i) * (size_t)point_u4;
+    u32 any = 0;
+    for (int q = 0; q < point_u4; q++) {
+      uint4 v = __ldg(bp + q);
+      any |= v.x | v.y | v.z | v.w;
+    }
+    if (any == 0) {
+      for (int w = 0; w < nwin; w++) dig[(size_t)w * n + i] = 0;
+      return;
+    }
+  }
   Fp<SP> k;
   const bool is_extra = i >= n_main;
   const uint2* p = reinterpret_cast<const uint2*>(is_extra ? extra + (i - n_main) * 10 : scalars + i * 10);
@@ -135,6 +153,27 @@ static __global__ void msm_sizekey_kernel(const u32* __restrict__ counts, size_t
   id[g] = (u32)g;
 }
 
+// The heavy-bucket threshold the host passes is derived from n x windows entries; the REAL count (non-zero digits of
+// points that are not at infinity) is only known on the device and can be several times smaller for a witness (bits,
+// zero products, absent variables).  A bucket of a few hundred copies of one repeated value (-1, 2, ...: one such bucket
+// per window) then sits just under the threshold and ONE thread walks it while the rest of the grid has long finished:
+// measured on the helper proof's G2 MSM (Fq3, 0.36 M real entries of 1.3 M nominal): accumulate 9.2 ms with whole
+// buckets, 5.6 / 3.6 ms with 2 / 4 parts -- inversely proportional, i.e. the time of the longest item.  So the kernel
+// lowers the threshold to `split` x half the entries a resident work slot gets when the real work is spread evenly.
+// ... but never below twice the real average bucket (with few buckets for the resident threads the average bucket is
+// larger than a slot's share and `split` is what spreads it: without this floor every bucket of the dense h MSM at
+// 2^16 went to the heavy path, 18 ms).
+__device__ __forceinline__ u32 msm_dynamic_heavy_thr(u32 host_thr, u32 real_total, u32 resident_items, size_t nbuckets,
+                                                     u32 split) {
+  u32 share = real_total / (resident_items ? resident_items : 1u);
+  u32 item = share / 2 > 8u ? share / 2 : 8u;
+  u32 dyn = split * item;
+  u32 floor_thr = 2u * (u32)(real_total / nbuckets) + 8u;
+  if (dyn < floor_thr) dyn = floor_thr;
+  if (dyn < 24u) dyn = 24u;
+  return dyn < host_thr ? dyn : host_thr;
+}
+
 // Persistent warps pull 32 buckets at a time from a global queue (dynamic scheduling): with one thread per
 // bucket and a plain grid the kernel ran in a few "waves" of equally long threads, and its time was
 // the wave count rounded up (c = 18 at 2^20: 2.3 waves cost 3).
@@ -156,7 +195,8 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
                                                              const u32* __restrict__ perm, size_t nbuckets,
                                                              void* __restrict__ buckets, u32* __restrict__ heavy,
                                                              u32* __restrict__ queue, u32 heavy_thr, u32 split,
-                                                             u32* __restrict__ hflag, u32 quantum, u32 persistent_from) {
+                                                             u32* __restrict__ hflag, u32 quantum, u32 persistent_from,
+                                                             u32 resident_items) {
   typedef typename C::F F;
   typedef C CF;
   typedef typename CF::F FF;
@@ -166,6 +206,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
   // point where the block scheduler can start a higher-priority lane's kernel (witness map, sorts, the G2 chain); the
   // last CTAs of the grid stay until the queue is empty, so all the work is always done
   const bool may_retire = blockIdx.x < persistent_from;
+  heavy_thr = msm_dynamic_heavy_thr(heavy_thr, offsets[nbuckets], resident_items, nbuckets, split);
   u32 walked = 0;
   for (;;) {
     if (may_retire && __shfl_sync(0xffffffffu, walked, 0) >= quantum) break;
@@ -265,13 +306,15 @@ __global__ void __launch_bounds__(128, PCD_SLICED_MIN_CTAS) msm_accumulate_slice
                                                                     const u32* __restrict__ perm, size_t nbuckets,
                                                                     void* __restrict__ buckets, u32* __restrict__ heavy,
                                                                     u32* __restrict__ queue, u32 heavy_thr, u32 split,
-                                                                    u32* __restrict__ hflag, u32 quantum, u32 persistent_from) {
+                                                                    u32* __restrict__ hflag, u32 quantum, u32 persistent_from,
+                                                             u32 resident_items) {
   typedef typename CS::F FF;
   const unsigned lane = threadIdx.x & 31;
   const int l = (int)(lane % 3u);
   const unsigned grp = lane / 3u;  // 0..9 (10: the two idle lanes)
   const size_t nitems = nbuckets * split;
   const bool may_retire = blockIdx.x < persistent_from;  // see msm_accumulate_kernel
+  heavy_thr = msm_dynamic_heavy_thr(heavy_thr, offsets[nbuckets], resident_items, nbuckets, split);
   u32 walked = 0;
   for (;;) {
     if (may_retire && __shfl_sync(0xffffffffu, walked, 0) >= quantum) break;
@@ -636,7 +679,9 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                            // combination count themselves
   msm_digits_kernel<SP><<<(unsigned)((n + 127) / 128), 128, 0, st>>>((const u32*)d_scalars, scalars_mont, n_main,
                                                                     (const u32*)d_extra, n, c, nwin,
-                                                                    shared, (int*)dig, counts);
+                                                                    shared, (int*)dig, counts, (const uint4*)d_bases,
+                                                                    (int)(sizeof(AffinePoint<typename C::F>) / 16),
+                                                                    shared ? plan.offset : (size_t)0);
   PCD_CUDA(ctx, cudaGetLastError());
   size_t cub_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, counts, offsets, (int)(nbuckets + 1), st);
@@ -706,12 +751,15 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   }
   // bucket parts: at least ~6 waves of work items, at least 8 entries per part
   u32 split = 1;
-  while (split < (u32)MSM_MAX_SPLIT && nbuckets * split < 6 * acc_grid * ITEMS_PER_CTA && avg_entries / (2 * split) >= 8) split *= 2;
+  static const int split_env = getenv("PCDGPU_ACC_SPLIT") ? atoi(getenv("PCDGPU_ACC_SPLIT")) : 0;  // development aid
+  const u32 max_split = split_env > 0 ? (u32)split_env : (u32)MSM_MAX_SPLIT;
+  while (split < max_split && nbuckets * split < 6 * acc_grid * ITEMS_PER_CTA && avg_entries / (2 * split) >= 8) split *= 2;
   if (acc_grid > (nbuckets * split + ITEMS_PER_CTA - 1) / ITEMS_PER_CTA) acc_grid = (nbuckets * split + ITEMS_PER_CTA - 1) / ITEMS_PER_CTA;
   // inside a proof the CTAs retire after ~a quarter of a millisecond of work (quantum entries per lane) so that the
   // other lanes' kernels are not starved by a persistent grid; a lone MSM keeps the persistent form
   static const int quantum_env = getenv("PCDGPU_ACC_QUANTUM") ? atoi(getenv("PCDGPU_ACC_QUANTUM")) : -1;  // development aid
   u32 quantum = 0, persistent_from = 0;
+  const u32 resident_items = (u32)(acc_grid * ITEMS_PER_CTA);
   {
     const int prods = SLICED ? 20 : (sizeof(typename C::F) / 40 == 1 ? 10 : 28);
     int q = quantum_env >= 0 ? quantum_env : (ctx->concurrent && ctx->in_proof ? 320 / prods : 0);
@@ -730,17 +778,17 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   if constexpr (SLICED) {
     if (shared)
       msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, true><<<(unsigned)acc_grid, 128, 0, st>>>(
-          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from);
+          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items);
     else
       msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, false><<<(unsigned)acc_grid, 128, 0, st>>>(
-          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from);
+          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items);
   } else {
     if (shared)
       msm_accumulate_kernel<C, true><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                       acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from);
+                                                                       acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items);
     else
       msm_accumulate_kernel<C, false><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                        acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from);
+                                                                        acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items);
   }
   PCD_CUDA(ctx, cudaGetLastError());
   if (ctx->gate_done) {
