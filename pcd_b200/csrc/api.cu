@@ -756,10 +756,11 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   // kernels are ordered (events recorded right after / waited right before their launch): sorting, bucket reduction
   // and the tails of every lane still overlap freely.  Enqueue order = dependency order (an event must have been
   // recorded before it is waited for).
-  // MEASURED (2^18 main proof, B200): ordering the grids this way is SLOWER than letting the lanes contend (9.05 vs
-  // 8.15 ms): b_g2's accumulate takes ~5.9 ms whenever it shares the SMs, whatever it shares them with, so delaying
-  // its start delays the proof.  Kept behind PCDGPU_ACC_ORDER for further experiments; off by default.
-  static const bool want_gates = getenv("PCDGPU_ACC_ORDER") != nullptr;
+  // MEASURED (B200, tools/probe_pcd.py).  While b_g2's accumulation was the longest chain this order was slower (main
+  // 2^18: 9.05 vs 8.15 ms); since base points at infinity are skipped and the heavy-bucket threshold follows the real
+  // entry count, the a / b_g1 -> double-scalar chain is the critical one and the order wins: main 6.16 -> 6.10 ms,
+  // helper (MNT6, 2^16) 4.28 -> 3.88 ms.  PCDGPU_NO_ACC_ORDER turns it off (A/B runs).
+  static const bool want_gates = getenv("PCDGPU_NO_ACC_ORDER") == nullptr;
   const bool gates = fork && !small && want_gates;
   // A lighter ordering, also measured: b_g2's accumulation grid starts only when the a, b_g1 and l lanes have
   // finished SORTING.  Its CTAs fill the register file (Fq2: 234 registers, Fq3 sliced: four CTAs per SM) and its first

@@ -448,38 +448,73 @@ __global__ void __launch_bounds__(32) wec_sum_affine_kernel(const void* __restri
 }
 
 // out[iout] = sum_{j < npairs} [k_j] pts[i_j], npairs <= 2, k_j 320-bit plain integers (ten words at k + 10 j): one
-// double-and-add chain with 2-bit windows per pair.  The chains are independent, so they run as two groups of the
-// same warp at the cost of one (G1 curves: G = 4); a final addition joins them.  This is s g_a + r g1_b of a Groth16
-// proof and [r] C2' of a GM17 proof.
+// double-and-add chain per pair with SIGNED 4-bit windows (digits -7 .. 8, table P .. 8 P: 4 doublings + 3 additions to
+// build, then <= 300 doublings and ~76 additions; the 2-bit unsigned form before it took 320 + 120).  The chains are
+// independent, so they run as two groups of the same warp at the cost of one (G1 curves: G = 4); a final addition
+// joins them.  This is s g_a + r g1_b of a Groth16 proof -- the longest serial tail of a proof -- and [r] C2' of a
+// GM17 proof.
 template <class C>
 __global__ void __launch_bounds__(32) wec_multi_mul_kernel(const void* __restrict__ pts, size_t i0, size_t i1,
                                                             const u32* __restrict__ k, int npairs, void* __restrict__ out,
                                                             size_t iout) {
   typedef Wec<C> WG;
+  typedef typename WG::B B;
   static_assert(WG::G <= 16, "two groups in one warp");
-  constexpr int AREA = 4 * WG::PW + WG::NTW;  // acc | table 1 P, 2 P, 3 P
+  constexpr int NDIG = 81;                             // 320 bits / 4 + the last carry
+  constexpr int DIGW = 24;                             // words holding the digits (one byte each)
+  constexpr int AREA = 10 * WG::PW + WG::NTW + DIGW;  // acc | table 1 P .. 8 P | q | temporaries | digits
   __shared__ uint4 sm4[2 * AREA / 4];
+  static_assert(AREA % 4 == 0, "16-byte aligned areas");
   const int g = threadIdx.x / WG::G;
   if (g >= 2) return;
   u32* acc = reinterpret_cast<u32*>(sm4) + (size_t)g * AREA;
-  u32* t1 = acc + WG::PW;
-  u32* t2 = t1 + WG::PW;
-  u32* t3 = t2 + WG::PW;
-  WG wg(t3 + WG::PW);
+  u32* tab = acc + WG::PW;  // tab + (m - 1) PW = m P
+  u32* q = tab + 8 * WG::PW;
+  WG wg(q + WG::PW);
+  signed char* dig = reinterpret_cast<signed char*>(q + WG::PW + WG::NTW);
   const unsigned both = (1u << (2 * WG::G)) - 1u;
   wg.set_inf(acc);
   if (g < npairs) {
     const u32* kk = k + 10 * g;
-    wg.load(t1, pts, g == 0 ? i0 : i1);
-    wg.copy(t2, t1);
-    wg.dbl(t2);
-    wg.copy(t3, t2);
-    wg.add(t3, t1);
-    for (int pos = 318; pos >= 0; pos -= 2) {  // 160 two-bit windows, top first
+    if (wg.gl == 0) {  // signed recoding from the low end: d in -7 .. 8
+      u32 carry = 0;
+      for (int j = 0; j < NDIG; j++) {
+        u32 d = (j < 80 ? (kk[j >> 3] >> ((j & 7) * 4)) & 15u : 0u) + carry;
+        carry = d > 8u ? 1u : 0u;
+        dig[j] = (signed char)(carry ? (int)d - 16 : (int)d);
+      }
+    }
+    wg.load(tab, pts, g == 0 ? i0 : i1);
+    for (int m = 2; m <= 8; m++) {  // m P = 2 (m / 2) P for even m, (m - 1) P + P for odd m
+      u32* t = tab + (m - 1) * WG::PW;
+      if ((m & 1) == 0) {
+        wg.copy(t, tab + (m / 2 - 1) * WG::PW);
+        wg.dbl(t);
+      } else {
+        wg.copy(t, tab + (m - 2) * WG::PW);
+        wg.add(t, tab);
+      }
+    }
+    for (int j = NDIG - 1; j >= 0; j--) {
       wg.dbl(acc);
       wg.dbl(acc);
-      const u32 d = (kk[pos >> 5] >> (pos & 31)) & 3u;
-      if (d) wg.add(acc, d == 1 ? t1 : (d == 2 ? t2 : t3));
+      wg.dbl(acc);
+      wg.dbl(acc);
+      // ONE addition site for both signs and both groups of the warp: with `add` called from a positive and a negative
+      // branch the two chains (different digits) serialised the two calls -- 1.5 additions of warp time per window
+      const int d = dig[j];
+      const int m = d < 0 ? -d : d;
+      if (m) {
+        wg.copy(q, tab + (m - 1) * WG::PW);
+        if (d < 0 && wg.gl < WG::K) {  // y <- -y, coefficient by coefficient (stored points are canonical)
+          u32* yc = q + WG::EW + wg.gl * 10;
+          wec_st<B>(yc, wec_ld<B>(yc).neg());
+        }
+        wg.sync();
+      } else {
+        wg.set_inf(q);
+      }
+      wg.add(acc, q);
     }
   }
   __syncwarp(both);
