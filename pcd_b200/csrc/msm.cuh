@@ -174,6 +174,58 @@ __device__ __forceinline__ u32 msm_dynamic_heavy_thr(u32 host_thr, u32 real_tota
   return dyn < host_thr ? dyn : host_thr;
 }
 
+// Small bucket sets (<= 1024 buckets: the default-circuit proofs' MSMs, ~10^3 points at c = 7) get their offsets, cursors
+// and visiting order from ONE single-CTA kernel instead of cub's scan + radix sort (seven launches): these MSMs are
+// bound by the host's enqueue rate (seven MSMs per proof, ~75 us of launches each before this).  The order is the same
+// rule -- decreasing clamped size, ties by bucket index -- computed as a rank by comparison (n^2 / 1024 per thread).
+static __global__ void __launch_bounds__(1024) msm_plan_small_kernel(const u32* __restrict__ counts, u32 nbuckets,
+                                                                      u32* __restrict__ offsets, u32* __restrict__ cursor,
+                                                                      u32* __restrict__ perm, u32* __restrict__ heavy,
+                                                                      u32* __restrict__ queue) {
+  __shared__ u32 key[1024];
+  __shared__ u32 warp_sum[32];
+  const u32 t = threadIdx.x;
+  const u32 c = t < nbuckets ? counts[t] : 0u;
+  key[t] = c < 2047u ? c : 2047u;
+  // exclusive scan of the counts (nbuckets + 1 outputs)
+  u32 v = c;
+  for (int d = 1; d < 32; d <<= 1) {
+    u32 o = __shfl_up_sync(0xffffffffu, v, d);
+    if ((t & 31u) >= (u32)d) v += o;
+  }
+  if ((t & 31u) == 31u) warp_sum[t >> 5] = v;
+  __syncthreads();
+  if (t < 32) {
+    u32 w = warp_sum[t];
+    for (int d = 1; d < 32; d <<= 1) {
+      u32 o = __shfl_up_sync(0xffffffffu, w, d);
+      if (t >= (u32)d) w += o;
+    }
+    warp_sum[t] = w;
+  }
+  __syncthreads();
+  const u32 incl = v + ((t >> 5) ? warp_sum[(t >> 5) - 1] : 0u);
+  if (t < nbuckets) {
+    offsets[t] = incl - c;
+    cursor[t] = incl - c;
+    if (t == nbuckets - 1) {
+      offsets[nbuckets] = incl;
+      cursor[nbuckets] = incl;
+    }
+    u32 rank = 0;
+    const u32 mine = key[t];
+    for (u32 j = 0; j < nbuckets; j++) {
+      const u32 kj = key[j];
+      rank += (kj > mine || (kj == mine && j < t)) ? 1u : 0u;
+    }
+    perm[rank] = t;
+  }
+  if (t == 0) {
+    heavy[0] = 0;
+    queue[0] = 0;
+  }
+}
+
 // Persistent warps pull 32 buckets at a time from a global queue (dynamic scheduling): with one thread per
 // bucket and a plain grid the kernel ran in a few "waves" of equally long threads, and its time was
 // the wave count rounded up (c = 18 at 2^20: 2.3 waves cost 3).
@@ -667,10 +719,13 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   u32* id_in = key_out + cstride;
   u32* perm = id_in + cstride;
   u32* heavy = perm + cstride;
+  const bool small_plan = nbuckets <= 1024;  // msm_plan_small_kernel: it also clears the heavy list and the queue
   PCD_CUDA(ctx, cudaMemsetAsync(counts, 0, cstride * 4, st));
-  PCD_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
   u32* queue = heavy + MSM_MAX_HEAVY + 2;
-  PCD_CUDA(ctx, cudaMemsetAsync(queue, 0, 4, st));
+  if (!small_plan) {
+    PCD_CUDA(ctx, cudaMemsetAsync(heavy, 0, 4, st));
+    PCD_CUDA(ctx, cudaMemsetAsync(queue, 0, 4, st));
+  }
   const int acc_slot = n < ((size_t)1 << 14) ? PROF_MSM_ACC_SMALL
                        : (sizeof(typename C::F) > 80 ? PROF_MSM_ACC_G2Q3
                                                      : (sizeof(typename C::F) > 40 ? PROF_MSM_ACC_G2 : PROF_MSM_ACC_G1));
@@ -683,6 +738,10 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                                                                     (int)(sizeof(AffinePoint<typename C::F>) / 16),
                                                                     shared ? plan.offset : (size_t)0);
   PCD_CUDA(ctx, cudaGetLastError());
+  if (small_plan) {
+    msm_plan_small_kernel<<<1, 1024, 0, st>>>(counts, (u32)nbuckets, offsets, cursor, perm, heavy, queue);
+    PCD_CUDA(ctx, cudaGetLastError());
+  } else {
   size_t cub_bytes = 0;
   cub::DeviceScan::ExclusiveSum(nullptr, cub_bytes, counts, offsets, (int)(nbuckets + 1), st);
   PCD_TRY(ctx->scratch(SLOT_CUB, cub_bytes + 16, &cub_tmp));
@@ -698,6 +757,7 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   PCD_CUDA(ctx, cub::DeviceRadixSort::SortPairsDescending(sort_tmp, sort_bytes, key_in, key_out, id_in, perm,
                                                           (int)nbuckets, 0, 11, st));
   ctx->launches += 4;  // size keys + cub's radix sort passes
+  }
   size_t total = (size_t)nwin * n;
   msm_scatter_kernel<<<(unsigned)((total + 255) / 256), 256, 0, st>>>((const int*)dig, n, c, nwin, shared,
                                                                       plan.stride, plan.offset, cursor, (u32*)ent);
@@ -719,7 +779,13 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   }
   constexpr bool SLICED = MsmSliced<C>::value;      // three lanes per work item (Fq3)
   constexpr size_t ITEMS_PER_CTA = SLICED ? 40 : 128;  // work items a CTA of 128 threads holds at a time
-  int acc_ctas = 0;
+  // occupancy and function attributes are per device and never change: asked once (every query / set is a few
+  // microseconds of host time, and the default-circuit proofs are bound by the host's enqueue rate)
+  static int occ_cache[2][16] = {{0}};
+  static bool attr_done[16] = {false};
+  const int dev_slot = ctx->device & 15;
+  int acc_ctas = occ_cache[shared ? 1 : 0][dev_slot];
+  if (acc_ctas == 0) {
   if constexpr (SLICED) {
     if (shared) PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, true>, 128, 0));
     else PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, false>, 128, 0));
@@ -728,6 +794,8 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     else PCD_CUDA(ctx, cudaOccupancyMaxActiveBlocksPerMultiprocessor(&acc_ctas, msm_accumulate_kernel<C, false>, 128, 0));
   }
   if (acc_ctas < 1) acc_ctas = 1;
+  occ_cache[shared ? 1 : 0][dev_slot] = acc_ctas;
+  }
   // CTAs per SM (measured, bench.py): side by side with the other lanes of a proof two CTAs (8 warps) are best -- the
   // registers left free let the latency-bound kernels (reduction, sorting, tails) run beside this one; a lone MSM
   // gains 4 % from a third CTA (5.99 -> 5.77 ms at 2^20); a fourth, forced to 128 registers, is slower.
@@ -825,12 +893,14 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     PCD_CUDA(ctx, cudaGetLastError());
     msm_heavy_finish_sliced_kernel<CS><<<64, 128, sl_smem, st>>>(heavy, hp_count, hp_id, hp_sum, bkt);
   } else {
-    PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)heavy_smem));
-    PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)heavy_smem));
-    PCD_CUDA(ctx, cudaFuncSetAttribute(msm_heavy_finish_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                       (int)heavy_smem));
+    if (!attr_done[dev_slot]) {
+      PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, true>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)heavy_smem));
+      PCD_CUDA(ctx, cudaFuncSetAttribute(msm_accumulate_heavy_kernel<C, false>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)heavy_smem));
+      PCD_CUDA(ctx, cudaFuncSetAttribute(msm_heavy_finish_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize,
+                                         (int)heavy_smem));
+    }
     if (shared)
       msm_accumulate_heavy_kernel<C, true><<<ctx->sm_count * 4, MSM_HEAVY_THREADS, heavy_smem, st>>>(
           d_bases, offsets, (const u32*)ent, heavy, hp_count, hp_id, hp_sum);
@@ -860,8 +930,11 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   void* wsum = (char*)lvl[1] + (size_t)rwin * pitch * PB;
   void* fin = rwin == 1 ? d_out : wsum;  // one window (precomputed tables): its sum IS the result
   const size_t red_smem = wec_smem_bytes<C>(WEC_THREADS, 4), sum_smem = wec_smem_bytes<C>(WEC_THREADS, 2);
-  PCD_CUDA(ctx, cudaFuncSetAttribute(wec_reduce_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
-  PCD_CUDA(ctx, cudaFuncSetAttribute(wec_sum_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
+  if (!attr_done[dev_slot]) {
+    PCD_CUDA(ctx, cudaFuncSetAttribute(wec_reduce_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)red_smem));
+    PCD_CUDA(ctx, cudaFuncSetAttribute(wec_sum_kernel<C>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sum_smem));
+    attr_done[dev_slot] = true;
+  }
   wec_reduce_kernel<C><<<dim3((unsigned)ctas, (unsigned)rwin), WEC_THREADS, red_smem, st>>>(bkt, B, logL,
                                                                                          ctas == 1 ? fin : seg);
   PCD_CUDA(ctx, cudaGetLastError());
