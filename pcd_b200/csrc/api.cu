@@ -688,8 +688,15 @@ extern "C" {
 // b_g1 queries) instead of a double-scalar multiplication of the finished g_a and g1_b: the two MSMs start with the
 // others, so nothing waits for a 298-doubling chain -- the tiny default-circuit proofs of a PCD step
 // (/root/reference/src/ec_cycle_pcd/data_structures.rs:139-143,343-350) are pure latency.  Above it the extra
-// accumulation work would cost more than the chain, which there hides under the h MSM.
-static const size_t GROTH16_SMALL_NV = (size_t)1 << 13;
+// accumulation work (two MSMs with DENSE scalars) costs more than the chain, which there hides under the h MSM.
+// MEASURED inside the PCD step (B200, tools/probe_step.py): the helper proof (MNT6, 2^16 variables) 4.87 ms with the
+// chain, 4.23 ms with the two MSMs; the main proof (MNT4, 2^18) 6.7 ms with the chain, 9.2 ms with the MSMs -- hence
+// 2^17.  PCDGPU_SMALL_NV_LOG overrides it (development aid for A/B runs).
+static size_t groth16_small_nv() {
+  static const int lg = getenv("PCDGPU_SMALL_NV_LOG") ? atoi(getenv("PCDGPU_SMALL_NV_LOG")) : 17;
+  return (size_t)1 << (lg < 0 ? 0 : (lg > 40 ? 40 : lg));
+}
+#define GROTH16_SMALL_NV groth16_small_nv()
 
 int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
                              const void* r, const void* s, void* out_proof) {
@@ -760,6 +767,10 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   // 2^18: 9.05 vs 8.15 ms); since base points at infinity are skipped and the heavy-bucket threshold follows the real
   // entry count, the a / b_g1 -> double-scalar chain is the critical one and the order wins: main 6.16 -> 6.10 ms,
   // helper (MNT6, 2^16) 4.28 -> 3.88 ms.  PCDGPU_NO_ACC_ORDER turns it off (A/B runs).
+  // Also measured and NOT kept: every lane's accumulation grid waiting for the witness map (whose transforms take ~0.7 ms
+  // alone and ~3.1 ms beside four accumulating lanes, and the h MSM cannot start before them): the map then ends at
+  // 1.1 ms, but the h MSM's sorting kernels crawl behind the four grids that start together (0.2 -> 2.2 ms) and the
+  // double-scalar chain starts a millisecond later: main 6.77 -> 7.2 - 7.3 ms.  h's grid not waiting for b_g2's: 6.8 - 6.9.
   static const bool want_gates = getenv("PCDGPU_NO_ACC_ORDER") == nullptr;
   const bool gates = fork && !small && want_gates;
   // A lighter ordering, also measured: b_g2's accumulation grid starts only when the a, b_g1 and l lanes have

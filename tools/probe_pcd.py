@@ -43,7 +43,8 @@ def timeline(g, idx, z, r, s, label):
 
 
 def one(pairing, log_n, precompute, label, reps=5):
-    inst = synthetic.make_groth16_instance(ctx, pairing, log_n, seed=77 + pairing)
+    inst = synthetic.make_groth16_instance(ctx, pairing, log_n,
+                                            seed=77 + pairing + (10 * log_n if os.environ.get("PROBE_BENCH_SEED") else 0))
     g = pcd_b200.Groth16(ctx, pairing)
     pk = pcd_b200.ProvingKey(pairing=pairing, **inst["pk"])
     cm = pcd_b200.ConstraintMatrices(pairing, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"], inst["C"])
