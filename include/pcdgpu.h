@@ -75,6 +75,17 @@ int pcdgpu_set_stream(pcdgpu_ctx* ctx, void* stream);
 int pcdgpu_set_concurrency(pcdgpu_ctx* ctx, int on);
 /* MSM window override (0 = automatic); exposed for benchmarking */
 int pcdgpu_set_msm_window(pcdgpu_ctx* ctx, int c);
+/* Proof graphs (default OFF): when on, pcdgpu_groth16_prove[_dev] captures the launch sequence of a proof into a CUDA
+ * graph the second time it sees the same (key, constraint system, device assignment address) and replays it afterwards
+ * -- one launch instead of 150 - 250 on up to seven streams.  Results are identical (tests/test_gpu_graphs.py).
+ * MEASURED on B200 inside the PCD step (tools/probe_step.py): replay is SLOWER than eager enqueueing -- main proof
+ * (2^18) 7.58 vs 6.75 ms, helper (2^16) 4.31 vs 4.24 ms, default-circuit proofs 1.27 - 1.34 vs 1.21 - 1.25 ms: the
+ * eager path's stream priorities and enqueue order (witness map first, accumulation grids gated) schedule the lanes
+ * better than the graph's dependency-only order, and a 250-node launch costs about what the staggered enqueue did.
+ * Kept as an option for hosts whose enqueue rate is the bound.
+ * stats: graphs captured / proofs replayed from a graph since the context exists. */
+int pcdgpu_set_proof_graphs(pcdgpu_ctx* ctx, int on);
+int pcdgpu_proof_graph_stats(pcdgpu_ctx* ctx, uint64_t* captured, uint64_t* replayed);
 
 /* ---- radix-2 (coset) NTT --------------------------------------------------------------------
  * Replaces ark-poly EvaluationDomain::{fft,ifft,coset_fft,coset_ifft}_in_place on

@@ -1,5 +1,6 @@
 // api.cu -- the extern "C" surface of libpcdgpu.so (include/pcdgpu.h).  Host-pointer entry points
 // stage through device scratch; _dev entry points are asynchronous on the context's stream.
+#include <atomic>
 #include <cstdlib>
 
 #include "groth16.cuh"
@@ -59,6 +60,12 @@ static MsmPlanC plan_plain(pcdgpu_ctx* ctx, size_t n) {
       return PCDGPU_E_ARG;                \
     }                                     \
   } while (0)
+
+// identities of uploaded keys and constraint systems (pcdgpu_ctx::ProofGraph: an address can be reused, a uid cannot)
+static unsigned long long next_uid() {
+  static std::atomic<unsigned long long> n{0};
+  return ++n;
+}
 
 extern "C" {
 
@@ -138,6 +145,8 @@ void pcdgpu_ctx_destroy(pcdgpu_ctx* ctx) {
     if (ctx->ev_join[l]) cudaEventDestroy(ctx->ev_join[l]);
   }
   if (ctx->ev_fork) cudaEventDestroy(ctx->ev_fork);
+  for (auto& g : ctx->graphs)
+    if (g.exec) cudaGraphExecDestroy(g.exec);
   for (int i = 0; i < 3; i++) {
     if (ctx->ev_acc[i]) cudaEventDestroy(ctx->ev_acc[i]);
     if (ctx->ev_sorted[i]) cudaEventDestroy(ctx->ev_sorted[i]);
@@ -168,6 +177,17 @@ int pcdgpu_set_concurrency(pcdgpu_ctx* ctx, int on) {
   if (!ctx) return PCDGPU_E_ARG;
   PCD_CUDA(ctx, cudaStreamSynchronize(ctx->stream));
   ctx->concurrent = on != 0;
+  return 0;
+}
+int pcdgpu_set_proof_graphs(pcdgpu_ctx* ctx, int on) {
+  if (!ctx) return PCDGPU_E_ARG;
+  ctx->use_graphs = on != 0;
+  return 0;
+}
+int pcdgpu_proof_graph_stats(pcdgpu_ctx* ctx, uint64_t* captured, uint64_t* replayed) {
+  if (!ctx) return PCDGPU_E_ARG;
+  if (captured) *captured = ctx->graphs_captured;
+  if (replayed) *replayed = ctx->graphs_replayed;
   return 0;
 }
 int pcdgpu_set_msm_window(pcdgpu_ctx* ctx, int c) {
@@ -472,6 +492,7 @@ int pcdgpu_r1cs_upload(pcdgpu_ctx* ctx, int pairing, size_t m, size_t num_inputs
     total += (nnz[i] * 40 + 15) & ~(size_t)15;
   }
   pcdgpu_r1cs* r = new pcdgpu_r1cs();
+  r->uid = next_uid();
   r->ctx = ctx;
   r->pairing = pairing;
   r->m = m;
@@ -575,6 +596,7 @@ static int pk_upload_impl(pcdgpu_ctx* ctx, int pairing, size_t num_vars, size_t 
   size_t s1 = msm_ops(g1)->affine_bytes, s2 = msm_ops(g2)->affine_bytes;
   pcdgpu_pk* pk = new pcdgpu_pk();
   memset(pk, 0, sizeof(*pk));
+  pk->uid = next_uid();
   pk->ctx = ctx;
   pk->pairing = pairing;
   pk->num_vars = num_vars;
@@ -698,19 +720,12 @@ static size_t groth16_small_nv() {
 }
 #define GROTH16_SMALL_NV groth16_small_nv()
 
-int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
-                             const void* r, const void* s, void* out_proof) {
-  if (!ctx) return PCDGPU_E_ARG;
-  CHECK_ARG(ctx, pk && r1cs && d_z && r && s && out_proof, "null pointer");
-  CHECK_ARG(ctx, pk->pairing == r1cs->pairing, "key and constraint system are over different pairings");
-  CHECK_ARG(ctx, pk->num_vars == r1cs->num_inputs + r1cs->num_witness && pk->num_inputs == r1cs->num_inputs,
-            "key and constraint system disagree on the variable counts");
-  CHECK_ARG(ctx, pk->shard_world == 1, "sharded key: use pcdgpu_groth16_prove_sharded");
-  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
-  InProofGuard in_proof(ctx);
+// Everything a proof enqueues, from the upload of (r, s) (staged in ctx->pinned) to the copy of the proof into
+// h_proof (pinned): no host synchronisation, no host read of device data -- the sequence depends only on the key, the
+// constraint system and the addresses, so it can be captured into a CUDA graph (pcdgpu_groth16_prove_dev).
+static int groth16_enqueue(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z, const G16Misc& m,
+                           void* h_proof) {
   int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
-  G16Misc m;
-  PCD_TRY(g16_misc(ctx, pk->pairing, &m));
   const size_t x1 = m.x1;
   u32* d_rs = m.d_rs;
   char* extras = m.extras;
@@ -719,8 +734,6 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   char* d_A = m.d_proof;
   char* d_B = m.d_proof + m.a1;
   char* d_C = m.d_proof + m.a1 + m.a2;
-  memcpy(ctx->pinned, r, 40);
-  memcpy((char*)ctx->pinned + 40, s, 40);
   PCD_CUDA(ctx, cudaMemcpyAsync(d_rs, ctx->pinned, 80, cudaMemcpyHostToDevice, ctx->stream));
   PCD_TRY(groth16_prepare(ctx, pk->pairing, d_rs, (u32*)extras));
   const char* z = (const char*)d_z;
@@ -821,8 +834,106 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
     for (int l = 1; l < nlanes && rc == 0; l++)
       if (cudaStreamWaitEvent(ctx->stream, ctx->ev_join[l], 0) != cudaSuccess) rc = PCDGPU_E_CUDA;
   if (rc == 0) rc = groth16_finish(ctx, pk->pairing, sums1, d_C, small ? 4 : 3);
-  if (rc == 0 && cudaMemcpyAsync(out_proof, m.d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
+  if (rc == 0 && cudaMemcpyAsync(h_proof, m.d_proof, proof_bytes, cudaMemcpyDeviceToHost, ctx->stream) != cudaSuccess)
     rc = PCDGPU_E_CUDA;
+  return rc;
+}
+
+static pcdgpu_ctx::ProofGraph* proof_graph_slot(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z) {
+  pcdgpu_ctx::ProofGraph* lru = &ctx->graphs[0];
+  for (auto& g : ctx->graphs) {
+    if (g.seen && g.pk_uid == pk->uid && g.r1cs_uid == r1cs->uid && g.d_z == d_z) {
+      g.last_use = ++ctx->graph_clock;
+      return &g;
+    }
+    if (g.last_use < lru->last_use) lru = &g;
+  }
+  if (lru->exec) cudaGraphExecDestroy(lru->exec);
+  *lru = pcdgpu_ctx::ProofGraph();
+  lru->pk_uid = pk->uid;
+  lru->r1cs_uid = r1cs->uid;
+  lru->d_z = d_z;
+  lru->last_use = ++ctx->graph_clock;
+  return lru;
+}
+
+int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1cs* r1cs, const void* d_z,
+                             const void* r, const void* s, void* out_proof) {
+  if (!ctx) return PCDGPU_E_ARG;
+  CHECK_ARG(ctx, pk && r1cs && d_z && r && s && out_proof, "null pointer");
+  CHECK_ARG(ctx, pk->pairing == r1cs->pairing, "key and constraint system are over different pairings");
+  CHECK_ARG(ctx, pk->num_vars == r1cs->num_inputs + r1cs->num_witness && pk->num_inputs == r1cs->num_inputs,
+            "key and constraint system disagree on the variable counts");
+  CHECK_ARG(ctx, pk->shard_world == 1, "sharded key: use pcdgpu_groth16_prove_sharded");
+  PCD_CUDA(ctx, cudaSetDevice(ctx->device));
+  InProofGuard in_proof(ctx);
+  G16Misc m;
+  PCD_TRY(g16_misc(ctx, pk->pairing, &m));
+  const size_t proof_bytes = 2 * m.a1 + m.a2;
+  char* h_proof = (char*)ctx->pinned + 128;
+  memcpy(ctx->pinned, r, 40);
+  memcpy((char*)ctx->pinned + 40, s, 40);
+  // Proof graphs (common.cuh: ProofGraph; off unless pcdgpu_set_proof_graphs).  First call with a (key, system,
+  // assignment address): eager.  Second call in
+  // the same scratch epoch: captured, instantiated and launched.  Later calls: one cudaGraphLaunch.
+  static const bool env_graphs = getenv("PCDGPU_GRAPHS") != nullptr;  // development aid (A/B runs): on without the call
+  pcdgpu_ctx::ProofGraph* ge =
+      ((ctx->use_graphs || env_graphs) && ctx->concurrent && !ctx->profiling) ? proof_graph_slot(ctx, pk, r1cs, d_z) : nullptr;
+  if (ge && ge->exec && ge->epoch != ctx->scratch_epoch) {  // scratch moved since the capture
+    cudaGraphExecDestroy(ge->exec);
+    ge->exec = nullptr;
+    ge->seen = 1;
+  }
+  int rc = 0;
+  bool launched = false;
+  if (ge && ge->exec) {
+    if (cudaGraphLaunch(ge->exec, ctx->stream) != cudaSuccess) {
+      ctx->set_error("cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
+      rc = PCDGPU_E_CUDA;
+    }
+    ctx->launches += ge->launches;
+    ctx->graphs_replayed++;
+    launched = true;
+  } else if (ge && ge->seen == 1 && ge->epoch == ctx->scratch_epoch) {
+    const unsigned long long l0 = ctx->launches;
+    cudaGraph_t graph = nullptr;
+    bool ok = cudaStreamBeginCapture(ctx->stream, cudaStreamCaptureModeRelaxed) == cudaSuccess;
+    if (ok) {
+      ctx->capturing = true;
+      int crc = groth16_enqueue(ctx, pk, r1cs, d_z, m, h_proof);
+      ctx->capturing = false;
+      ctx->lane = 0;
+      ok = cudaStreamEndCapture(ctx->stream, &graph) == cudaSuccess && graph != nullptr && crc == 0;
+      if (ok) ok = cudaGraphInstantiate(&ge->exec, graph, 0) == cudaSuccess;
+      if (graph) cudaGraphDestroy(graph);
+      if (ok) {
+        ge->launches = ctx->launches - l0;
+        ge->epoch = ctx->scratch_epoch;
+        ctx->launches = l0;
+        if (cudaGraphLaunch(ge->exec, ctx->stream) != cudaSuccess) {
+          ctx->set_error("cudaGraphLaunch: %s", cudaGetErrorString(cudaGetLastError()));
+          rc = PCDGPU_E_CUDA;
+        }
+        ctx->launches += ge->launches;
+        ctx->graphs_captured++;
+        ctx->graphs_replayed++;
+        launched = true;
+      } else {
+        ctx->launches = l0;
+        if (crc != 0 && crc != PCD_E_RETRY) rc = crc;  // a real error: nothing was executed, report it
+      }
+    }
+    if (!ok) {  // no graph for this entry, now or later; the call is redone eagerly below
+      cudaGetLastError();
+      ge->exec = nullptr;
+      ge->seen = 2;
+    }
+  }
+  if (!launched && rc == 0) {
+    rc = groth16_enqueue(ctx, pk, r1cs, d_z, m, h_proof);
+    if (ge && ge->seen == 0) ge->seen = 1;
+    if (ge) ge->epoch = ctx->scratch_epoch;  // compared at the next call: captured only if nothing grew in between
+  }
   // every exit, error or not, drains the lanes and the stream: the next call reuses the pinned staging buffer and
   // the scratch the lanes are working in
   if (rc) ctx->drain_lanes();
@@ -831,6 +942,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
     ctx->set_error("cudaStreamSynchronize: %s", cudaGetErrorString(e));
     rc = PCDGPU_E_CUDA;
   }
+  if (rc == 0) memcpy(out_proof, h_proof, proof_bytes);
   return rc;
 }
 

@@ -58,6 +58,8 @@ struct ProfSpan {
   int units_pinned;  // >= 0: index into ctx->prof_pinned holding the unit count read back from the device
 };
 
+static const int PCD_E_RETRY = -100;  // internal: abandon the graph capture and redo the call eagerly (never returned)
+
 struct pcdgpu_ctx {
   int device = 0;
   int sm_count = 148;
@@ -99,6 +101,22 @@ struct pcdgpu_ctx {
   size_t spans_used = 0;
   unsigned* prof_pinned = nullptr;  // 4096 u32, pinned
   unsigned long long launches = 0;  // kernels launched by this context since the last read
+  // CUDA graphs of whole proofs (pcdgpu_set_proof_graphs, off by default -- measured slower, see include/pcdgpu.h): a
+  // proof's ~150 - 250 launches on up to seven streams depend only on the key, the constraint system and the addresses
+  // involved, not on the assignment, so the second call with the same (key, system, assignment address) is captured
+  // and every later one is ONE cudaGraphLaunch.  A graph bakes scratch addresses in: scratch_epoch counts
+  // (re)allocations, an entry of another epoch is dropped; while capturing, scratch() refuses to grow (PCD_E_RETRY: the
+  // call is redone eagerly).
+  struct ProofGraph {
+    unsigned long long pk_uid = 0, r1cs_uid = 0, epoch = 0, last_use = 0, launches = 0;
+    const void* d_z = nullptr;
+    int seen = 0;
+    cudaGraphExec_t exec = nullptr;
+  };
+  static const int NGRAPH = 8;
+  ProofGraph graphs[NGRAPH];
+  unsigned long long scratch_epoch = 0, graph_clock = 0, graphs_captured = 0, graphs_replayed = 0;
+  bool capturing = false, use_graphs = false;  // pcdgpu_set_proof_graphs: measured slower than eager enqueueing
   // multi-GPU (comm.cu): NCCL communicator of the ranks that share one proof / MSM; world 1 = none
   void* nccl_comm = nullptr;
   int comm_rank = 0, comm_world = 1;
@@ -141,6 +159,11 @@ struct pcdgpu_ctx {
   int scratch(int id, size_t bytes, void** out) {
     id += lane * SLOTS_PER_LANE;
     if (bytes > slot_bytes[id]) {
+      if (capturing) {
+        set_error("scratch slot %d would grow during graph capture", id);
+        return PCD_E_RETRY;
+      }
+      scratch_epoch++;
       if (slot[id]) {
         cudaStreamSynchronize(cur());
         cudaFree(slot[id]);

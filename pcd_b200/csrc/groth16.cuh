@@ -17,6 +17,7 @@ struct pcdgpu_r1cs {
   int dom_a, dom_b;
   CsrDev A, B, C;
   void* storage;  // one allocation holding all nine arrays
+  unsigned long long uid;  // unique per upload (keys of the context's proof graphs; an address can be reused)
 };
 
 struct pcdgpu_bases {
@@ -40,6 +41,7 @@ struct pcdgpu_pk {
   size_t v_lo, v_hi;  // of the num_vars - 1 ordinary points of a / b_g1 / b_g2
   size_t h_lo, h_hi;  // of h_query
   size_t l_lo, l_hi;  // of l_query
+  unsigned long long uid;  // unique per upload (see pcdgpu_r1cs)
 };
 
 struct pcdgpu_gm17_pk {

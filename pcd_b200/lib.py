@@ -29,7 +29,7 @@ TWO_ADICITY = {FIELD_R4: 34, FIELD_Q4: 17}
 
 EXPORTS = [
     "pcdgpu_strerror", "pcdgpu_last_error", "pcdgpu_affine_bytes", "pcdgpu_ctx_create", "pcdgpu_ctx_destroy",
-    "pcdgpu_sync", "pcdgpu_set_stream", "pcdgpu_set_concurrency", "pcdgpu_set_msm_window", "pcdgpu_ntt", "pcdgpu_ntt_dev", "pcdgpu_domain_size", "pcdgpu_ntt_general", "pcdgpu_msm",
+    "pcdgpu_sync", "pcdgpu_set_stream", "pcdgpu_set_concurrency", "pcdgpu_set_msm_window", "pcdgpu_set_proof_graphs", "pcdgpu_proof_graph_stats", "pcdgpu_ntt", "pcdgpu_ntt_dev", "pcdgpu_domain_size", "pcdgpu_ntt_general", "pcdgpu_msm",
     "pcdgpu_msm_dev", "pcdgpu_bases_upload", "pcdgpu_bases_free", "pcdgpu_msm_bases", "pcdgpu_msm_bases_dev",
     "pcdgpu_xyzz_sum", "pcdgpu_xyzz_download", "pcdgpu_fixed_base_mul", "pcdgpu_fixed_base_mul_dev",
     "pcdgpu_r1cs_upload", "pcdgpu_r1cs_free", "pcdgpu_r1cs_domain_size", "pcdgpu_witness_map", "pcdgpu_pk_upload",
@@ -83,6 +83,8 @@ def load():
     lib.pcdgpu_set_stream.argtypes = [vp, vp]
     lib.pcdgpu_set_msm_window.argtypes = [vp, ci]
     lib.pcdgpu_set_concurrency.argtypes = [vp, ci]
+    lib.pcdgpu_set_proof_graphs.argtypes = [vp, ci]
+    lib.pcdgpu_proof_graph_stats.argtypes = [vp, ctypes.POINTER(ctypes.c_uint64), ctypes.POINTER(ctypes.c_uint64)]
     lib.pcdgpu_ntt.argtypes = [vp, ci, vp, ctypes.c_uint32, ci, ci]
     lib.pcdgpu_ntt_dev.argtypes = [vp, ci, vp, ctypes.c_uint32, ci, ci]
     lib.pcdgpu_domain_size.restype = sz
@@ -223,6 +225,16 @@ class Context:
 
     def set_concurrency(self, on: bool):
         self._check(self.lib.pcdgpu_set_concurrency(self.h, int(on)))
+
+    def set_proof_graphs(self, on: bool):
+        """CUDA graphs of whole Groth16 proofs (include/pcdgpu.h: pcdgpu_set_proof_graphs); off by default (measured slower)"""
+        self._check(self.lib.pcdgpu_set_proof_graphs(self.h, int(on)))
+
+    def proof_graph_stats(self):
+        """(graphs captured, proofs replayed from a graph) since the context exists"""
+        a, b = ctypes.c_uint64(), ctypes.c_uint64()
+        self._check(self.lib.pcdgpu_proof_graph_stats(self.h, ctypes.byref(a), ctypes.byref(b)))
+        return int(a.value), int(b.value)
 
     def set_msm_window(self, c: int):
         self._check(self.lib.pcdgpu_set_msm_window(self.h, c))

@@ -41,6 +41,8 @@ extern "C" {
     pub fn pcdgpu_set_stream(ctx: *mut pcdgpu_ctx, stream: *mut c_void) -> c_int;
     pub fn pcdgpu_set_concurrency(ctx: *mut pcdgpu_ctx, on: c_int) -> c_int;
     pub fn pcdgpu_set_msm_window(ctx: *mut pcdgpu_ctx, c: c_int) -> c_int;
+    pub fn pcdgpu_set_proof_graphs(ctx: *mut pcdgpu_ctx, on: c_int) -> c_int;
+    pub fn pcdgpu_proof_graph_stats(ctx: *mut pcdgpu_ctx, captured: *mut u64, replayed: *mut u64) -> c_int;
     pub fn pcdgpu_ntt(ctx: *mut pcdgpu_ctx, field: c_int, data: *mut c_void, log_n: u32, inverse: c_int, coset: c_int) -> c_int;
     pub fn pcdgpu_ntt_dev(ctx: *mut pcdgpu_ctx, field: c_int, d_data: *mut c_void, log_n: u32, inverse: c_int, coset: c_int) -> c_int;
     pub fn pcdgpu_domain_size(field: c_int, min_size: usize, pow7: *mut c_int, pow2: *mut c_int) -> usize;
