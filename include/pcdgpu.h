@@ -13,7 +13,8 @@
  *     across the boundary; pcdgpu_strerror() names a code, pcdgpu_last_error() gives detail.
  *   - the caller owns every host buffer; device objects are opaque handles with explicit free.
  *   - one context = one GPU + one stream set; a context must not be used from two host threads at
- *     once.  There is NO CPU fallback: without a usable sm_100 device ctx_create fails.
+ *     once (the prover entry points refuse a second concurrent call with PCDGPU_E_ARG).  There is NO
+ *     CPU fallback: without a usable sm_100 device ctx_create fails.
  *   - encodings are arkworks' in-memory ones so the shim copies, never converts:
  *       field element  : 40 bytes, five little-endian u64 limbs of a*R mod p, R = 2^320
  *                        (ark-ff Fp320 / BigInteger320)
@@ -24,8 +25,9 @@
  *       xyzz point     : X || Y || ZZ || ZZZ (x = X/ZZ, y = Y/ZZZ; infinity: ZZ = 0) -- only used
  *                        for partial sums exchanged between GPUs
  *   - functions with the _dev suffix take DEVICE pointers on the context's GPU and are
- *     asynchronous on the context's stream (pcdgpu_sync() waits); the others take HOST pointers
- *     and return when the result is in the host buffer.
+ *     asynchronous on the context's stream (pcdgpu_sync() waits) -- except the provers
+ *     (*_prove_dev, *_prove_sharded_dev), whose proof lands in a HOST buffer: they return when it
+ *     is there; the others take HOST pointers and return when the result is in the host buffer.
  */
 #ifndef PCDGPU_H
 #define PCDGPU_H

@@ -867,6 +867,7 @@ int pcdgpu_groth16_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_
   CHECK_ARG(ctx, pk->shard_world == 1, "sharded key: use pcdgpu_groth16_prove_sharded");
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
   InProofGuard in_proof(ctx);
+  CHECK_ARG(ctx, in_proof.ok, "the context is running a prover call on another host thread (one context per thread)");
   G16Misc m;
   PCD_TRY(g16_misc(ctx, pk->pairing, &m));
   const size_t proof_bytes = 2 * m.a1 + m.a2;
@@ -963,6 +964,7 @@ int pcdgpu_groth16_prove_sharded_dev(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const
             "the key was sharded for another communicator");
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
   InProofGuard in_proof(ctx);
+  CHECK_ARG(ctx, in_proof.ok, "the context is running a prover call on another host thread (one context per thread)");
   const int world = ctx->comm_world;
   int g1 = g1_of(pk->pairing), g2 = g2_of(pk->pairing);
   G16Misc m;

@@ -2,6 +2,7 @@
 #pragma once
 #include <cuda_runtime.h>
 
+#include <atomic>
 #include <cstdarg>
 #include <cstdio>
 #include <cstring>
@@ -67,6 +68,7 @@ struct pcdgpu_ctx {
   cudaStream_t stream = nullptr;
   int msm_window = 0;
   bool in_proof = false;     // inside a prover entry point: its MSMs run side by side on the lanes
+  std::atomic<bool> busy{false};  // a prover call is running (InProofGuard): concurrent use from a second thread is refused
   bool key_upload = false;  // set while a proving key's queries are uploaded (window rule of concurrent MSMs)
   char err[512] = {0};
   // Lanes: the five MSMs of a proof are independent, so each runs on its own stream with its own
@@ -183,10 +185,21 @@ struct pcdgpu_ctx {
   }
 };
 
-struct InProofGuard {  // marks the context as "inside a prover call" for the MSM launch heuristics
+// Marks the context as "inside a prover call" (MSM launch heuristics) and enforces the header's rule that a context is
+// used by one host thread at a time: a second prover call that finds the context busy fails (`ok` false) instead of
+// sharing lanes, scratch and the pinned staging buffer with the first.
+struct InProofGuard {
   pcdgpu_ctx* c;
-  explicit InProofGuard(pcdgpu_ctx* ctx) : c(ctx) { c->in_proof = true; }
-  ~InProofGuard() { c->in_proof = false; }
+  bool ok;
+  explicit InProofGuard(pcdgpu_ctx* ctx) : c(ctx), ok(!ctx->busy.exchange(true)) {
+    if (ok) c->in_proof = true;
+  }
+  ~InProofGuard() {
+    if (ok) {
+      c->in_proof = false;
+      c->busy.store(false);
+    }
+  }
 };
 
 enum {

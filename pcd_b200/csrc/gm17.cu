@@ -320,6 +320,7 @@ int pcdgpu_gm17_prove_dev(pcdgpu_ctx* ctx, const pcdgpu_gm17_pk* pk, const pcdgp
                  "key and constraint system disagree on the variable counts");
   PCD_CUDA(ctx, cudaSetDevice(ctx->device));
   InProofGuard in_proof(ctx);
+  GM17_CHECK_ARG(ctx, in_proof.ok, "the context is running a prover call on another host thread (one context per thread)");
   int g1 = pcd_g1_of(pk->pairing), g2 = pcd_g2_of(pk->pairing);
   const MsmOps *o1 = msm_ops(g1), *o2 = msm_ops(g2);
   size_t x1 = o1->xyzz_bytes, x2 = o2->xyzz_bytes;

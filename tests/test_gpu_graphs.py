@@ -50,3 +50,46 @@ def test_replayed_proofs_match_discrete_logs(ctx, pairing, log_n):
     proof = g.create_proof_dev(idx, z.data_ptr(), codec.int_to_limbs(r), codec.int_to_limbs(s))
     assert np.array_equal(proof.affine_limbs(), synthetic.expected_proof(ctx, inst, r, s, mul=co.fixed_base_mul))
     idx.close()
+
+
+def test_context_refuses_a_second_concurrent_prover_call(ctx):
+    """include/pcdgpu.h: one context per host thread.  Two threads proving on ONE context: every call either returns the
+    right proof or is refused with PCDGPU_E_ARG -- never a proof computed in scratch another call was using"""
+    import threading
+
+    import torch
+
+    import pcd_b200
+    from pcd_b200 import synthetic
+    from pcd_b200.lib import PcdGpuError
+    pairing, log_n = 1, 14
+    inst = synthetic.make_groth16_instance(ctx, pairing, log_n, seed=4242)
+    g = pcd_b200.Groth16(ctx, pairing)
+    idx = g.index(pcd_b200.ProvingKey(pairing=pairing, **inst["pk"]),
+                  pcd_b200.ConstraintMatrices(pairing, inst["num_inputs"], inst["num_witness"], inst["A"], inst["B"],
+                                              inst["C"]), precompute=True)
+    z = torch.from_numpy(inst["z"].view(np.int64)).to("cuda:0")
+    p = inst["p"]
+    pairs = [(pow(3, 20 + k, p), pow(7, 30 + k, p)) for k in range(12)]
+    expect = [synthetic.expected_proof(ctx, inst, r, s, mul=co.fixed_base_mul) for r, s in pairs]
+    g.create_proof_dev(idx, z.data_ptr(), codec.int_to_limbs(pairs[0][0]), codec.int_to_limbs(pairs[0][1]))  # warm
+    good, refused, bad = [], [], []
+
+    def work(ks):
+        for k in ks:
+            r, s = pairs[k]
+            try:
+                proof = g.create_proof_dev(idx, z.data_ptr(), codec.int_to_limbs(r), codec.int_to_limbs(s))
+            except PcdGpuError as e:
+                (refused if e.code == -1 else bad).append((k, str(e)))
+                continue
+            (good if np.array_equal(proof.affine_limbs(), expect[k]) else bad).append((k, "wrong proof"))
+
+    ts = [threading.Thread(target=work, args=(range(i, 12, 2),)) for i in range(2)]
+    for t in ts:
+        t.start()
+    for t in ts:
+        t.join()
+    assert not bad, bad
+    assert len(good) + len(refused) == 12 and len(good) >= 1
+    idx.close()

@@ -1,13 +1,14 @@
 #!/bin/bash
-# ncu --set full capture of the PCD step's main (MNT4-298, 2^18) and helper (MNT6-298, 2^16) proofs, lanes serialised
-# (tools/ncu_step.py proves each twice; the raw csv keeps both proofs, tools/ncu_summary.py is given the second one).
-# Run under gpurun from the repo root; writes gpurun_out/r02_step_{main,help}_raw.csv
+# Evidence for profiles/ at the PCD step's main proof (MNT4-298, 2^18; tools/ncu_step.py proves it twice with the lanes
+# serialised): (1) the launch list of both proofs, (2) an `ncu --set full` capture of the second proof's accumulation,
+# bucket-reduction and double-scalar kernels (11 launches per proof).  Run under gpurun from the repo root.
 set -u
-K='regex:msm_accumulate|msm_fold_parts|msm_heavy_finish|wec_reduce|wec_multi_mul|ntt_pass'
-for which in main help; do
-  NCU_STEP=$which ncu --set full --clock-control none --import-source on -k "$K" -c 100 -f \
-    -o gpurun_out/r02_step_$which python tools/ncu_step.py > gpurun_out/ncu_step_$which.log 2>&1
-  ncu -i gpurun_out/r02_step_$which.ncu-rep --page raw --csv > gpurun_out/r02_step_${which}_raw.csv 2>> gpurun_out/ncu_step_$which.log
-  rm -f gpurun_out/r02_step_$which.ncu-rep
-  wc -l gpurun_out/r02_step_${which}_raw.csv
-done
+mkdir -p gpurun_out
+timeout 240 ncu --metrics gpu__time_duration.sum --clock-control none -c 600 --csv --log-file gpurun_out/r02_list_main.csv \
+  python tools/ncu_step.py > gpurun_out/ncu_list_main.log 2>&1
+K='regex:msm_accumulate_kernel|wec_reduce_kernel|wec_multi_mul_kernel'
+timeout 420 ncu --set full --clock-control none -k "$K" --launch-skip 11 -c 11 -f -o gpurun_out/r02_step_main \
+  python tools/ncu_step.py > gpurun_out/ncu_step_main.log 2>&1
+ncu -i gpurun_out/r02_step_main.ncu-rep --page raw --csv > gpurun_out/r02_step_main_raw.csv 2>> gpurun_out/ncu_step_main.log
+rm -f gpurun_out/r02_step_main.ncu-rep
+wc -l gpurun_out/r02_list_main.csv gpurun_out/r02_step_main_raw.csv
