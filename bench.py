@@ -40,7 +40,8 @@ MADD_MODMULS = {1: 10, 2: 28, 3: 58}  # XYZZ mixed add 8M + 2S in Fq / Fq2 (M=3,
 METRIC = "pcd_step_proofs_per_sec"
 UNIT = "PCD steps/s"
 PROF_NAMES = ["msm_digits_sort", "msm_accumulate_g1", "msm_accumulate_g2_fq2", "msm_reduce", "msm_horner", "ntt", "spmv_qap",
-              "assemble", "msm_accumulate_g2_fq3", "msm_accumulate_small"]
+              "assemble", "msm_accumulate_g2_fq3", "msm_accumulate_small", "msm_accumulate_tail"]
+PROF_TAIL = 10  # part fold + heavy-bucket kernels behind the accumulate kernel of a large MSM
 PROF_ACC = {1: 1, 2: 2, 8: 3}  # accumulation classes of the large MSMs -> extension degree of the coordinates
 
 
@@ -450,14 +451,21 @@ def run_gpu(args, rank, local_rank, world):
         "kernel": PROF_NAMES[dom], "proof": dom_part, "bound": "imad", "achieved": achieved, "peak": imad_peak / 1e12,
         "unit": "TIMAD/s",
         "frac": achieved / (imad_peak / 1e12), "traffic": traffic,
-        "traffic_note": "DRAM bytes of one launch from the committed ncu capture (profiles/r02_traffic.json); algorithmic: "
-                        "80 / 160 / 240 B per gathered point + 4 B per entry",
+        "traffic_note": "DRAM bytes per launch (read + write, averaged over the class's launches) from the committed ncu "
+                        "capture of the same proof (profiles/r02_traffic.json); algorithmic: 80 / 160 / 240 B per gathered "
+                        "point + 4 B per entry",
+        "algorithmic_bytes_per_launch": pp["units"][dom] / max(pp["spans"][dom], 1) * ({1: 80, 2: 160, 3: 240}[deg] + 4),
         "peak_source": "measured live: IMAD.WIDE.U32 issue rate of the fmaheavy pipe (32 lanes/clk/SM), max of the "
                        "independent accumulate form (%.2f T/s) and the carry-chain form (%.2f T/s)" % (imad_indep / 1e12, imad_chain / 1e12),
         "launch_ms_avg": pp["ms"][dom] / max(pp["spans"][dom], 1), "work": work,
-        "scope": "the accumulation phase (accumulate + part fold + heavy-bucket kernels) of the %s proof's MSMs of this "
-                 "class, lanes serialised; the same class over the whole step (2^18, 2^16 and 2^10-point MSMs mixed): "
-                 "frac %s" % (dom_part, "%.3f" % step_frac if step_frac is not None else "n/a"),
+        "scope": "msm_accumulate_kernel launches of the %s proof's MSMs of this class (CUDA events around each launch, "
+                 "lanes serialised; work = the entries the kernel itself walks, read back from the device); the same "
+                 "kernel over the whole step (2^18 and 2^16-point MSMs mixed): frac %s.  What follows each launch -- part "
+                 "fold + heavy-bucket kernels, latency-bound trees over the buckets of repeated witness values -- is "
+                 "the msm_accumulate_tail class: %.3f ms per %s proof for %.0f entries (%.1f %% of the proof's entries)"
+                 % (dom_part, "%.3f" % step_frac if step_frac is not None else "n/a",
+                    pp["ms"][PROF_TAIL] / args.steps, dom_part, pp["units"][PROF_TAIL] / args.steps,
+                    100.0 * pp["units"][PROF_TAIL] / max(1.0, pp["units"][PROF_TAIL] + sum(pp["units"][i] for i in PROF_ACC))),
         "accumulation_by_proof": by_proof,
         "other_accumulation_classes": others,
     }

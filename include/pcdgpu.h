@@ -325,13 +325,14 @@ int pcdgpu_serialize_proof(pcdgpu_ctx* ctx, int pairing, const void* proof_affin
 
 /* ---- profiling ----------------------------------------------------------------------------------
  * CUDA-event spans around the library's kernel groups, on the context's stream.  Classes (array
- * index): 0 MSM digit/sort, 1 MSM bucket accumulation G1, 2 same G2 over Fq2, 3 MSM bucket reduction,
+ * index): 0 MSM digit/sort, 1 the accumulate kernel of a large G1 MSM, 2 same G2 over Fq2, 3 MSM bucket reduction,
  * 4 MSM window Horner, 5 NTT (all passes of a transform), 6 CSR mat-vec + QAP combine, 7 proof
- * assembly, 8 MSM bucket accumulation G2 over Fq3, 9 bucket accumulation of MSMs below 2^14 points (any curve).
+ * assembly, 8 the accumulate kernel of a large G2 MSM over Fq3, 9 the whole accumulation phase of MSMs below 2^14
+ * points (any curve), 10 what follows the accumulate kernel of a large MSM: part fold + heavy-bucket kernels.
  * read() synchronises, returns per class the summed milliseconds, algorithmic units
  * (bucket entries, butterflies, matrix rows, ...) and span count since the last read / enable, the
  * number of kernels launched, and resets.  Arrays hold PCDGPU_PROF_CLASSES entries. */
-#define PCDGPU_PROF_CLASSES 10
+#define PCDGPU_PROF_CLASSES 11
 int pcdgpu_profile_enable(pcdgpu_ctx* ctx, int on);
 int pcdgpu_profile_read(pcdgpu_ctx* ctx, double* ms, double* units, uint64_t* spans, uint64_t* launches);
 /* start / end (ms after the first span's start) and class of every span recorded since the last read:

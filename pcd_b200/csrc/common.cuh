@@ -40,7 +40,7 @@ struct NttTables {
 // roofline figures from them.
 enum {
   PROF_MSM_SORT = 0,  // digits + histogram, scan, scatter
-  PROF_MSM_ACC_G1,    // bucket accumulation (msm_accumulate + heavy), G1 curves
+  PROF_MSM_ACC_G1,    // the accumulate kernel of a large MSM (units: the entries IT walks -- heavy buckets excluded), G1 curves
   PROF_MSM_ACC_G2,    // same, G2 over Fq2 (MNT4)
   PROF_MSM_REDUCE,    // bucket reduction, per-window tree sum
   PROF_MSM_TAIL,      // Horner over windows
@@ -49,6 +49,8 @@ enum {
   PROF_ASSEMBLE,      // proof assembly (scalar multiplications, normalisation)
   PROF_MSM_ACC_G2Q3,  // bucket accumulation over Fq3 (MNT6 G2), kept apart from Fq2 so that the work per entry is exact
   PROF_MSM_ACC_SMALL, // bucket accumulation of MSMs below 2^14 points (default-circuit proofs): latency-bound regime
+  PROF_MSM_ACC_TAIL,  // after the accumulate kernel of a large MSM: part fold and the heavy-bucket kernels (latency-bound
+                      // trees over the few buckets that hold repeated witness values); units = the entries they add
   PROF_NSLOT
 };
 

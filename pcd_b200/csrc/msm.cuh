@@ -64,7 +64,7 @@ template <class SP>
 __global__ void msm_digits_kernel(const u32* __restrict__ scalars, int mont, size_t n_main,
                                   const u32* __restrict__ extra, size_t n, int c, int nwin, int shared,
                                   int* __restrict__ dig, u32* __restrict__ counts, const uint4* __restrict__ bases,
-                                  int point_u4, size_t base_first) {
+                                  int point_u4, size_t base_first, u32 unit_k) {
   size_t i = (size_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= n) return;
   {
@@ -90,12 +90,30 @@ __global__ void msm_digits_kernel(const u32* __restrict__ scalars, int mont, siz
     k.l[2 * j + 1] = v.y;
   }
   if (mont) k = k.from_mont();
+  const u32 B = 1u << (c - 1);  // buckets per window (bucket-set pitch)
+  // Unit buckets (unit_k > 0, shared bucket set only).  A witness is full of bits: every scalar equal to 1 would land in
+  // bucket 0 of window 0 -- a fifth of all points of a real assignment in ONE bucket, which then has to go through the
+  // latency-bound heavy-bucket kernels (measured: 2.1 ms of serialised kernel time per main proof for 3 % of the entries).
+  // Instead scalar 1 of point i goes to one of unit_k extra buckets behind the B weighted ones (digit B + 1 + i mod
+  // unit_k), which the accumulate kernel walks like any other bucket and the reduction adds with weight 1.  ark-ec's
+  // Pippenger has the same special case ("we only process unit scalars once in the first window").
+  if (unit_k) {
+    u32 rest = 0;
+#pragma unroll
+    for (int j = 1; j < 10; j++) rest |= k.l[j];
+    if (rest == 0 && k.l[0] == 1u) {
+      const u32 b = B + (u32)(i & (size_t)(unit_k - 1));
+      dig[i] = (int)(b + 1);
+      for (int w = 1; w < nwin; w++) dig[(size_t)w * n + i] = 0;
+      atomicAdd(&counts[b], 1u);
+      return;
+    }
+  }
   u32 w32[12];
 #pragma unroll
   for (int j = 0; j < 10; j++) w32[j] = k.l[j];
   w32[10] = 0;
   w32[11] = 0;
-  const u32 B = 1u << (c - 1);  // buckets per window (bucket-set pitch)
   u32 carry = 0;
   for (int w = 0; w < nwin; w++) {
     int bit = msm_win_start(w, c, nwin, shared);
@@ -151,6 +169,19 @@ static __global__ void msm_sizekey_kernel(const u32* __restrict__ counts, size_t
   u32 c = counts[g];
   key[g] = c < 2047u ? c : 2047u;
   id[g] = (u32)g;
+}
+
+// profiling only: out[0] = entries the accumulate kernel walked, out[1] = entries left to the heavy-bucket kernels
+static __global__ void msm_prof_entries_kernel(const u32* __restrict__ heavy, const u32* __restrict__ offsets, size_t nbuckets,
+                                               u32* __restrict__ out) {
+  u32 nheavy = heavy[0] < (u32)MSM_MAX_HEAVY ? heavy[0] : (u32)MSM_MAX_HEAVY;
+  u32 h = 0;
+  for (u32 i = threadIdx.x; i < nheavy; i += 32) h += offsets[heavy[1 + i] + 1] - offsets[heavy[1 + i]];
+  for (int d = 16; d > 0; d >>= 1) h += __shfl_xor_sync(0xffffffffu, h, d);
+  if (threadIdx.x == 0) {
+    out[0] = offsets[nbuckets] - h;
+    out[1] = h;
+  }
 }
 
 // The heavy-bucket threshold the host passes is derived from n x windows entries; the REAL count (non-zero digits of
@@ -248,7 +279,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
                                                              void* __restrict__ buckets, u32* __restrict__ heavy,
                                                              u32* __restrict__ queue, u32 heavy_thr, u32 split,
                                                              u32* __restrict__ hflag, u32 quantum, u32 persistent_from,
-                                                             u32 resident_items) {
+                                                             u32 resident_items, u32 nweighted) {
   typedef typename C::F F;
   typedef C CF;
   typedef typename CF::F FF;
@@ -272,7 +303,7 @@ __global__ void __launch_bounds__(128) msm_accumulate_kernel(const void* __restr
     size_t g = perm[t / split];
     u32 lo = offsets[g], hi = offsets[g + 1];
     XYZZ<CF> acc = XYZZ<CF>::inf();
-    if (hi - lo > heavy_thr) {
+    if (hi - lo > heavy_thr && g < nweighted) {  // unit buckets (msm_digits_kernel) are sized by the host: never heavy
       if (part != 0) continue;  // part 0 speaks for the whole bucket
       u32 slot = atomicAdd(&heavy[0], 1u);
       if (slot < (u32)MSM_MAX_HEAVY) {
@@ -359,7 +390,7 @@ __global__ void __launch_bounds__(128, PCD_SLICED_MIN_CTAS) msm_accumulate_slice
                                                                     void* __restrict__ buckets, u32* __restrict__ heavy,
                                                                     u32* __restrict__ queue, u32 heavy_thr, u32 split,
                                                                     u32* __restrict__ hflag, u32 quantum, u32 persistent_from,
-                                                             u32 resident_items) {
+                                                             u32 resident_items, u32 nweighted) {
   typedef typename CS::F FF;
   const unsigned lane = threadIdx.x & 31;
   const int l = (int)(lane % 3u);
@@ -381,7 +412,7 @@ __global__ void __launch_bounds__(128, PCD_SLICED_MIN_CTAS) msm_accumulate_slice
     size_t g = perm[t / split];
     u32 lo = offsets[g], hi = offsets[g + 1];
     XYZZ<CS> acc = XYZZ<CS>::inf();
-    if (hi - lo > heavy_thr) {
+    if (hi - lo > heavy_thr && g < nweighted) {  // unit buckets (msm_digits_kernel) are sized by the host: never heavy
       if (part != 0) continue;  // part 0 speaks for the whole bucket
       u32 slot = 0;
       if (l == 0) slot = atomicAdd(&heavy[0], 1u);
@@ -703,8 +734,16 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     return PCDGPU_E_ARG;
   }
   const size_t B = (size_t)1 << (c - 1);
-  const size_t nbuckets = shared ? B : B * nwin;
   const int rwin = shared ? 1 : nwin;  // windows seen by the reduction
+  // unit buckets (msm_digits_kernel): ~256 unit scalars per bucket if every scalar were 1, a power of two, a multiple of
+  // the reduction's group size; only with a shared bucket set and from 2^14 points up (smaller MSMs are launch-bound)
+  static const bool no_units = getenv("PCDGPU_NO_UNIT_BUCKETS") != nullptr;  // development aid (A/B runs)
+  size_t unit_k = 0;
+  if (shared && n >= ((size_t)1 << 14) && !no_units) {
+    unit_k = 64;
+    while (unit_k < (n >> 8) && unit_k < 16384) unit_k <<= 1;
+  }
+  const size_t nbuckets = (shared ? B : B * nwin) + unit_k;
   void *dig, *ent, *cnt, *bkt, *seg, *cub_tmp;
   PCD_TRY(ctx->scratch(SLOT_MSM_DIG, (size_t)nwin * n * 4, &dig));
   PCD_TRY(ctx->scratch(SLOT_MSM_ENT, (size_t)nwin * n * 4, &ent));
@@ -736,7 +775,7 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
                                                                     (const u32*)d_extra, n, c, nwin,
                                                                     shared, (int*)dig, counts, (const uint4*)d_bases,
                                                                     (int)(sizeof(AffinePoint<typename C::F>) / 16),
-                                                                    shared ? plan.offset : (size_t)0);
+                                                                    shared ? plan.offset : (size_t)0, (u32)unit_k);
   PCD_CUDA(ctx, cudaGetLastError());
   if (small_plan) {
     msm_plan_small_kernel<<<1, 1024, 0, st>>>(counts, (u32)nbuckets, offsets, cursor, perm, heavy, queue);
@@ -773,10 +812,6 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
       ctx->gate_wait[gi] = nullptr;
     }
   ps = ctx->prof_begin(acc_slot, (double)n * nwin);
-  if (ps >= 0 && ctx->prof_pinned) {  // exact number of bucket entries (non-zero digits) for the roofline
-    ctx->spans[ps].units_pinned = ps;
-    cudaMemcpyAsync(ctx->prof_pinned + ps, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st);
-  }
   constexpr bool SLICED = MsmSliced<C>::value;      // three lanes per work item (Fq3)
   constexpr size_t ITEMS_PER_CTA = SLICED ? 40 : 128;  // work items a CTA of 128 threads holds at a time
   // occupancy and function attributes are per device and never change: asked once (every query / set is a few
@@ -846,22 +881,43 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   if constexpr (SLICED) {
     if (shared)
       msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, true><<<(unsigned)acc_grid, 128, 0, st>>>(
-          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items);
+          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items, (u32)(nbuckets - unit_k));
     else
       msm_accumulate_sliced_kernel<typename MsmSliced<C>::type, false><<<(unsigned)acc_grid, 128, 0, st>>>(
-          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items);
+          d_bases, offsets, (const u32*)ent, perm, nbuckets, acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items, (u32)(nbuckets - unit_k));
   } else {
     if (shared)
       msm_accumulate_kernel<C, true><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                       acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items);
+                                                                       acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items, (u32)(nbuckets - unit_k));
     else
       msm_accumulate_kernel<C, false><<<(unsigned)acc_grid, 128, 0, st>>>(d_bases, offsets, (const u32*)ent, perm, nbuckets,
-                                                                        acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items);
+                                                                        acc_out, heavy, queue, heavy_thr, split, cursor, quantum, persistent_from, resident_items, (u32)(nbuckets - unit_k));
   }
   PCD_CUDA(ctx, cudaGetLastError());
   if (ctx->gate_done) {
     PCD_CUDA(ctx, cudaEventRecord(ctx->gate_done, st));
     ctx->gate_done = nullptr;
+  }
+  // Large MSMs: the accumulate kernel is a span (and a roofline) of its own; the part fold and the heavy-bucket kernels
+  // that follow are the ACC_TAIL class.  The exact entry counts (non-zero digits of points that are not at infinity,
+  // minus the heavy buckets the accumulate kernel handed over) are read back from the device.  Small MSMs keep one span.
+  if (ps >= 0 && acc_slot != PROF_MSM_ACC_SMALL) {
+    ctx->prof_end(ps);
+    const int ps_acc = ps;
+    ps = ctx->prof_begin(PROF_MSM_ACC_TAIL, 0.0);
+    if (ctx->prof_pinned) {
+      u32* pe = queue + 2;  // two spare words behind the queue counter
+      msm_prof_entries_kernel<<<1, 32, 0, st>>>(heavy, offsets, nbuckets, pe);
+      ctx->spans[ps_acc].units_pinned = ps_acc;
+      cudaMemcpyAsync(ctx->prof_pinned + ps_acc, pe, 4, cudaMemcpyDeviceToHost, st);
+      if (ps >= 0) {
+        ctx->spans[ps].units_pinned = ps;
+        cudaMemcpyAsync(ctx->prof_pinned + ps, pe + 1, 4, cudaMemcpyDeviceToHost, st);
+      }
+    }
+  } else if (ps >= 0 && ctx->prof_pinned) {
+    ctx->spans[ps].units_pinned = ps;
+    cudaMemcpyAsync(ctx->prof_pinned + ps, offsets + nbuckets, 4, cudaMemcpyDeviceToHost, st);
   }
   if (split > 1) {
     if constexpr (SLICED)
@@ -918,7 +974,11 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   static const int logL_env = getenv("PCDGPU_REDUCE_LOGL") ? atoi(getenv("PCDGPU_REDUCE_LOGL")) : 0;  // development aid
   const int logL = logL_env > 0 ? logL_env : MSM_REDUCE_LOGL;
   const size_t L = (size_t)1 << logL;
-  const size_t T = (B + L - 1) >> logL;
+  if (unit_k % L != 0) {
+    ctx->set_error("unit buckets (%zu) are not a multiple of the reduction's group size (%zu)", unit_k, L);
+    return PCDGPU_E_ARG;
+  }
+  const size_t T = ((B + L - 1) >> logL) + (unit_k >> logL);  // groups: weighted buckets, then unit buckets
   const size_t GPC = WEC_THREADS / WG::G;
   const size_t ctas = (T + GPC - 1) / GPC;
   const size_t per_cta = GPC * MSM_SUM_PER_GROUP;
@@ -936,7 +996,7 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     attr_done[dev_slot] = true;
   }
   wec_reduce_kernel<C><<<dim3((unsigned)ctas, (unsigned)rwin), WEC_THREADS, red_smem, st>>>(bkt, B, logL,
-                                                                                         ctas == 1 ? fin : seg);
+                                                                                         ctas == 1 ? fin : seg, unit_k);
   PCD_CUDA(ctx, cudaGetLastError());
   ctx->launches += 1;
   const void* in = seg;

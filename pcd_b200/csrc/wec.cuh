@@ -325,9 +325,11 @@ static constexpr int WEC_THREADS = 128;
 // S_w = sum_b (b + 1) B_{w,b} per window.  Group t of a window takes the L = 2^logL buckets [t L, t L + L) from the top
 // down with the running-sum trick (2 L additions), adds [t L] * (their plain sum), and the groups of a CTA fold their
 // contributions in a tree: part[w * gridDim.x + blockIdx.x] = the CTA's share of S_w.
+// K > 0 (one window only): K unit buckets follow the B weighted ones (msm_digits_kernel: scalars equal to 1); groups
+// T .. T + K / L - 1 add L of them each with weight 1.
 template <class C>
 __global__ void __launch_bounds__(WEC_THREADS) wec_reduce_kernel(const void* __restrict__ buckets, size_t B, int logL,
-                                                                  void* __restrict__ part) {
+                                                                  void* __restrict__ part, size_t K) {
   typedef Wec<C> WG;
   constexpr int G = WG::G, GPC = WEC_THREADS / G, AREA = 4 * WG::PW + WG::NTW;
   extern __shared__ uint4 wec_sm4[];
@@ -355,6 +357,12 @@ __global__ void __launch_bounds__(WEC_THREADS) wec_reduce_kernel(const void* __r
     if (k != 0 && !wg.is_inf(run)) {
       wg.mul_u32(tmp, run, k);
       wg.add(acc, tmp);
+    }
+  } else if (t < T + (K >> logL)) {
+    const size_t base = B + (t - T) * L;
+    for (size_t j = 0; j < L; j++) {
+      wg.load(q, buckets, base + j);
+      wg.add(acc, q);
     }
   }
   for (int s = GPC / 2; s > 0; s >>= 1) {

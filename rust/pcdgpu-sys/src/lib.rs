@@ -28,7 +28,7 @@ pub const PCDGPU_MNT4_G2: c_int = 1;
 pub const PCDGPU_MNT6_G1: c_int = 2;
 pub const PCDGPU_MNT6_G2: c_int = 3;
 pub const PCDGPU_COMM_ID_BYTES: usize = 128;
-pub const PCDGPU_PROF_CLASSES: usize = 8;
+pub const PCDGPU_PROF_CLASSES: usize = 11;
 
 #[link(name = "pcdgpu")]
 extern "C" {

@@ -16,7 +16,7 @@ ctx = pcd_b200.Context(0)
 if os.environ.get("SIDE_BY_SIDE"):
     ctx.lib.pcdgpu_set_msm_side_by_side(ctx.h, 1)
 dev = torch.device("cuda:0")
-NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small"]
+NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small", "acc_tail"]
 
 
 def profile(fn, reps=3):

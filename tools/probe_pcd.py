@@ -16,7 +16,7 @@ sys.path.insert(0, ROOT)
 import pcd_b200  # noqa: E402
 from pcd_b200 import synthetic  # noqa: E402
 
-NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small"]
+NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small", "acc_tail"]
 ctx = pcd_b200.Context(0)
 dev = torch.device("cuda:0")
 stream = torch.cuda.Stream(device=dev, priority=-1 if not os.environ.get("PCDGPU_NO_PRIORITIES") else 0)

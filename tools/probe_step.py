@@ -14,7 +14,7 @@ sys.path.insert(0, ROOT)
 import bench  # noqa: E402
 import pcd_b200  # noqa: E402
 
-NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small"]
+NAMES = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small", "acc_tail"]
 args = argparse.Namespace(pcd_main_log_n=18, pcd_help_log_n=16, pcd_tiny_log_n=10)
 ctx = pcd_b200.Context(0)
 dev = torch.device("cuda:0")

@@ -33,7 +33,7 @@ t1 = (ctypes.c_double * cap)()
 cls = (ctypes.c_int * cap)()
 n = ctypes.c_size_t()
 ctx._check(ctx.lib.pcdgpu_profile_timeline(ctx.h, t0, t1, cls, cap, ctypes.byref(n)))
-names = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small"]
+names = ["sort", "acc_g1", "acc_g2", "reduce", "horner", "ntt", "spmv", "assemble", "acc_g2q3", "acc_small", "acc_tail"]
 rows = sorted((t0[i], t1[i], names[cls[i]]) for i in range(n.value))
 for a, b, nm in rows:
     print("%8.3f -> %8.3f  (%6.3f ms)  %s" % (a, b, b - a, nm))
