@@ -163,9 +163,39 @@ class Groth16 {
   }
 
   static Result<bool> index(const ProvingKeyT& pk, const ConstraintMatrices& m, Index* out, bool precompute = true) {
+    return upload(pk, m, out, precompute, false, 0, nullptr, 0, 1);
+  }
+
+  // ONE proof over the GPUs of a box (include/pcdgpu.h, multi-GPU section; PCD chains, whose proofs depend on each
+  // other and cannot be spread over GPUs as independent jobs).  Called by `world` host threads (or processes), thread
+  // `rank` on CUDA device `device`; comm_id = the PCDGPU_COMM_ID_BYTES bytes rank 0 got from pcdgpu_comm_unique_id
+  // (ignored for world 1).  Collective: every rank calls index_sharded, then create_proof_sharded with the SAME
+  // circuit, r and s, and every rank receives the proof -- bit-identical to create_proof_with_reduction's.
+  static Result<bool> index_sharded(const ProvingKeyT& pk, const ConstraintMatrices& m, Index* out, int device,
+                                    const void* comm_id, int rank, int world, bool precompute = true) {
+    return upload(pk, m, out, precompute, true, device, comm_id, rank, world);
+  }
+  static Result<ProofT> create_proof_sharded(const Index& idx, const SynthesizedCircuit& circuit, const Fr& r, const Fr& s,
+                                             int device) {
+    return prove_impl(idx, circuit, r, s, device, true);
+  }
+
+ private:
+  static Result<bool> upload(const ProvingKeyT& pk, const ConstraintMatrices& m, Index* out, bool precompute, bool sharded,
+                             int device, const void* comm_id, int rank, int world) {
     Result<bool> res;
-    auto ctx = Backend::get();
+    auto ctx = Backend::get(device);
     if (!ctx) { res.error = ctx.error; return res; }
+    if (sharded) {
+      int have_rank = 0, have_world = 0;
+      int rc = pcdgpu_comm_info(ctx.value, &have_rank, &have_world);
+      if (rc == PCDGPU_OK && !(have_world == world && have_rank == rank))
+        rc = pcdgpu_comm_init(ctx.value, comm_id, rank, world);
+      if (rc != PCDGPU_OK) {
+        res.error = {ErrorKind::Backend, rc, pcdgpu_last_error(ctx.value)};
+        return res;
+      }
+    }
     const size_t nv = m.num_instance_variables + m.num_witness_variables;
     if (pk.a_query.size() != nv || pk.b_g1_query.size() != nv || pk.b_g2_query.size() != nv ||
         pk.l_query.size() != m.num_witness_variables) {
@@ -190,10 +220,10 @@ class Groth16 {
                                 m.num_witness_variables, ptr[0].data(), col[0].data(), val[0].data(), ptr[1].data(),
                                 col[1].data(), val[1].data(), ptr[2].data(), col[2].data(), val[2].data(), &out->r1cs);
     if (rc == PCDGPU_OK)
-      rc = pcdgpu_pk_upload(ctx.value, E::PAIRING, nv, m.num_instance_variables, pk.h_query.size(),
-                            pk.vk.alpha_g1.data(), pk.beta_g1.data(), pk.delta_g1.data(), pk.vk.beta_g2.data(),
-                            pk.vk.delta_g2.data(), pk.a_query.data(), pk.b_g1_query.data(), pk.b_g2_query.data(),
-                            pk.h_query.data(), pk.l_query.data(), precompute ? 1 : 0, &out->pk);
+      rc = (sharded ? pcdgpu_pk_upload_sharded : pcdgpu_pk_upload)(
+          ctx.value, E::PAIRING, nv, m.num_instance_variables, pk.h_query.size(), pk.vk.alpha_g1.data(),
+          pk.beta_g1.data(), pk.delta_g1.data(), pk.vk.beta_g2.data(), pk.vk.delta_g2.data(), pk.a_query.data(),
+          pk.b_g1_query.data(), pk.b_g2_query.data(), pk.h_query.data(), pk.l_query.data(), precompute ? 1 : 0, &out->pk);
     if (rc != PCDGPU_OK) {
       res.error = {ErrorKind::Backend, rc, pcdgpu_last_error(ctx.value)};
       return res;
@@ -203,11 +233,19 @@ class Groth16 {
     return res;
   }
 
+ public:
+
   // ark-groth16 create_proof_with_reduction(circuit, pk, r, s); r, s as plain integers (into_repr)
   static Result<ProofT> create_proof_with_reduction(const Index& idx, const SynthesizedCircuit& circuit, const Fr& r,
                                                     const Fr& s) {
+    return prove_impl(idx, circuit, r, s, 0, false);
+  }
+
+ private:
+  static Result<ProofT> prove_impl(const Index& idx, const SynthesizedCircuit& circuit, const Fr& r, const Fr& s, int device,
+                                   bool sharded) {
     Result<ProofT> res;
-    auto ctx = Backend::get();
+    auto ctx = Backend::get(device);
     if (!ctx) { res.error = ctx.error; return res; }
     std::vector<Fr> z(circuit.instance_assignment);
     z.insert(z.end(), circuit.witness_assignment.begin(), circuit.witness_assignment.end());
@@ -216,7 +254,8 @@ class Groth16 {
       return res;
     }
     std::vector<uint64_t> out(2 * E::G1_LIMBS + E::G2_LIMBS);
-    int rc = pcdgpu_groth16_prove(ctx.value, idx.pk, idx.r1cs, z.data(), r.data(), s.data(), out.data());
+    int rc = (sharded ? pcdgpu_groth16_prove_sharded : pcdgpu_groth16_prove)(ctx.value, idx.pk, idx.r1cs, z.data(), r.data(),
+                                                                             s.data(), out.data());
     if (rc != PCDGPU_OK) {
       res.error = {rc == PCDGPU_E_DOMAIN ? ErrorKind::DomainTooLarge : ErrorKind::Backend, rc, pcdgpu_last_error(ctx.value)};
       return res;
@@ -226,6 +265,8 @@ class Groth16 {
     std::memcpy(res.value.c.data(), out.data() + E::G1_LIMBS + E::G2_LIMBS, 8 * E::G1_LIMBS);
     return res;
   }
+
+ public:
 
   // SNARK::prove(pk, circuit, rng): r = Fr::rand(rng), then s = Fr::rand(rng) (create_random_proof's order).
   // Rng: any type with `Fr next_scalar(int pairing)` returning a uniform scalar as plain-integer limbs.

@@ -5,10 +5,13 @@
 // Exit codes: 0 ok, 2 backend unavailable (no GPU: there is no CPU fallback), 1 anything else.
 #include <cstdio>
 #include <cstdlib>
+#include <thread>
 
 #include "pcdgpu_snark.hpp"
 
 using namespace pcdgpu;
+
+extern "C" int cudaGetDeviceCount(int* count);  // libcudart (the test links it; no CUDA headers needed for this)
 
 static std::vector<uint64_t> g_data;
 static size_t g_pos = 0;
@@ -84,6 +87,39 @@ static int run(FILE* out) {
   fwrite(proof.value.b.data(), 8, E::G2_LIMBS, out);
   fwrite(proof.value.c.data(), 8, E::G1_LIMBS, out);
   fwrite(bytes.value.data(), 1, bytes.value.size(), out);
+  // ONE proof over the GPUs of the box through the sharded entry points (pcdgpu_comm_init, pcdgpu_pk_upload_sharded,
+  // pcdgpu_groth16_prove_sharded), one host thread per GPU as a Rust caller would run them: world = min(GPUs, 2); on a
+  // one-GPU box the same calls with world 1.  Every rank must return the single-GPU proof bit for bit.
+  {
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != 0 || ndev < 1) return 1;
+    const int world = ndev >= 2 ? 2 : 1;
+    unsigned char id[PCDGPU_COMM_ID_BYTES] = {0};
+    if (world > 1 && pcdgpu_comm_unique_id(id) != PCDGPU_OK) return 1;
+    std::vector<int> rcs(world, 1);
+    std::vector<std::thread> ts;
+    for (int rank = 0; rank < world; rank++)
+      ts.emplace_back([&, rank]() {
+        typename Groth16<E>::Index sidx;
+        auto up = Groth16<E>::index_sharded(pk, m, &sidx, rank, world > 1 ? id : nullptr, rank, world, true);
+        if (!up) {
+          fprintf(stderr, "index_sharded (rank %d of %d): %s\n", rank, world, up.error.message.c_str());
+          return;
+        }
+        auto sp = Groth16<E>::create_proof_sharded(sidx, circ, rng.draws[0], rng.draws[1], rank);
+        if (!sp) {
+          fprintf(stderr, "create_proof_sharded (rank %d of %d): %s\n", rank, world, sp.error.message.c_str());
+          return;
+        }
+        rcs[rank] = (sp.value.a == proof.value.a && sp.value.b == proof.value.b && sp.value.c == proof.value.c) ? 0 : 3;
+      });
+    for (auto& t : ts) t.join();
+    for (int rc : rcs)
+      if (rc != 0) {
+        fprintf(stderr, "sharded proof over %d GPU(s): rank returned %d\n", world, rc);
+        return 1;
+      }
+  }
   // a wrong-length assignment is an error, not a crash
   circ.witness_assignment.pop_back();
   auto bad = Groth16<E>::create_proof_with_reduction(idx, circ, rng.draws[0], rng.draws[1]);

@@ -23,7 +23,7 @@ def _build():
     hdr = os.path.join(ROOT, "include", "pcdgpu_snark.hpp")
     if not os.path.exists(EXE) or max(os.path.getmtime(src), os.path.getmtime(hdr)) > os.path.getmtime(EXE):
         os.makedirs(BUILD, exist_ok=True)
-        subprocess.check_call(["g++", "-O1", "-std=c++17", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
+        subprocess.check_call(["g++", "-O1", "-std=c++17", "-pthread", "-I", os.path.join(ROOT, "include"), src, "-o", EXE,
                                "-L", os.path.join(ROOT, "pcd_b200"), "-lpcdgpu",
                                "-Wl,-rpath," + os.path.join(ROOT, "pcd_b200"),
                                "-Wl,-rpath-link,/usr/local/cuda/lib64", "-L/usr/local/cuda/lib64", "-lcudart"])
