@@ -469,19 +469,29 @@ __global__ void __launch_bounds__(128) msm_fold_parts_kernel(const void* __restr
   st_vec(buckets, g, acc);
 }
 
-// CTA-wide tree sum of one xyzz point per thread (shared memory, MSM_HEAVY_THREADS entries)
+// CTA-wide tree sum of one xyzz point per thread (shared memory: MSM_HEAVY_THREADS points, then the temporaries of
+// the CTA's lane groups); the sum ends in sm[0].  The additions are lane-cooperative (wec.cuh: G lanes per addition,
+// its cost the multiplicative depth of the formula): with one thread per addition the seven levels of this tree were
+// seven full one-thread additions deep (G1 ~9 us, G2 over Fq2 ~27 us each) and made the heavy-bucket kernels -- a few
+// thousand entries -- as long as an accumulate launch over millions (profile class msm_accumulate_tail).
 template <class C>
 __device__ __forceinline__ void cta_tree_sum(XYZZ<C>* sm, const XYZZ<C>& mine) {
+  typedef Wec<C> WG;
+  constexpr int NG = MSM_HEAVY_THREADS / WG::G;
   sm[threadIdx.x] = mine;
-  __syncthreads();
+  u32* pts = reinterpret_cast<u32*>(sm);
+  WG wg(pts + (size_t)MSM_HEAVY_THREADS * WG::PW + (size_t)(threadIdx.x / WG::G) * WG::NTW);
+  const int g = (int)threadIdx.x / WG::G;
   for (int s = MSM_HEAVY_THREADS / 2; s > 0; s >>= 1) {
-    if ((int)threadIdx.x < s) {
-      XYZZ<C> a = sm[threadIdx.x];
-      a.add(sm[threadIdx.x + s]);
-      sm[threadIdx.x] = a;
-    }
     __syncthreads();
+    for (int i = g; i < s; i += NG) wg.add(pts + (size_t)i * WG::PW, pts + (size_t)(i + s) * WG::PW);
   }
+  __syncthreads();
+}
+// dynamic shared memory of a kernel that calls cta_tree_sum
+template <class C>
+constexpr size_t cta_tree_smem() {
+  return (size_t)MSM_HEAVY_THREADS * sizeof(XYZZ<C>) + (size_t)(MSM_HEAVY_THREADS / Wec<C>::G) * Wec<C>::NTW * 4;
 }
 
 // Heavy buckets (more than MSM_HEAVY entries: the "scalar == 1" bucket of a real witness holds a
@@ -928,7 +938,7 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
     PCD_CUDA(ctx, cudaGetLastError());
     ctx->launches += 1;
   }
-  size_t heavy_smem = MSM_HEAVY_THREADS * sizeof(XYZZ<C>);
+  size_t heavy_smem = cta_tree_smem<C>();
   // heavy-bucket partial list: at most one partial per MSM_HEAVY_CHUNK entries plus one per bucket
   size_t hp_cap = total / (SLICED ? MSM_HEAVY_CHUNK_SLICED : MSM_HEAVY_CHUNK) + MSM_MAX_HEAVY + 8;
   void* hp;
