@@ -784,6 +784,9 @@ static int groth16_enqueue(pcdgpu_ctx* ctx, const pcdgpu_pk* pk, const pcdgpu_r1
   // alone and ~3.1 ms beside four accumulating lanes, and the h MSM cannot start before them): the map then ends at
   // 1.1 ms, but the h MSM's sorting kernels crawl behind the four grids that start together (0.2 -> 2.2 ms) and the
   // double-scalar chain starts a millisecond later: main 6.77 -> 7.2 - 7.3 ms.  h's grid not waiting for b_g2's: 6.8 - 6.9.
+  // The h MSM enqueued right behind the witness map with every lane's grid waiting for h's SORTING (witness map + h's
+  // sort on a GPU that only sorts: 0.97 ms instead of 3.3): the grids then all start at ~1 ms but the a / b_g1 ->
+  // double-scalar chain starts 1.5 ms later than today: main 6.59 -> 7.41 ms.
   static const bool want_gates = getenv("PCDGPU_NO_ACC_ORDER") == nullptr;
   const bool gates = fork && !small && want_gates;
   // A lighter ordering, also measured: b_g2's accumulation grid starts only when the a, b_g1 and l lanes have

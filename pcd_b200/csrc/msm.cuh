@@ -982,7 +982,12 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   // seg layout, in points: CTA partial sums [rwin][ctas] | sum levels 2 x [rwin][pitch] | wsum [rwin]
   typedef Wec<C> WG;
   static const int logL_env = getenv("PCDGPU_REDUCE_LOGL") ? atoi(getenv("PCDGPU_REDUCE_LOGL")) : 0;  // development aid
-  const int logL = logL_env > 0 ? logL_env : MSM_REDUCE_LOGL;
+  // small bucket sets (the default-circuit proofs' MSMs: 64 buckets) are pure latency: fewer buckets per group, a shorter
+  // running-sum chain.  MEASURED inside the PCD step: default-circuit proofs 1.20 / 1.04 ms with 8 buckets per group,
+  // 1.12 / 0.94 ms with 4, 1.10 / 0.92 ms with 2; the large proofs lose with 4 (main 6.58 -> 6.80 ms: twice the groups,
+  // twice the instructions)
+  static const int logL_small_env = getenv("PCDGPU_REDUCE_LOGL_SMALL") ? atoi(getenv("PCDGPU_REDUCE_LOGL_SMALL")) : 0;  // development aid
+  const int logL = logL_env > 0 ? logL_env : (B <= 1024 ? (logL_small_env > 0 ? logL_small_env : 1) : MSM_REDUCE_LOGL);
   const size_t L = (size_t)1 << logL;
   if (unit_k % L != 0) {
     ctx->set_error("unit buckets (%zu) are not a multiple of the reduction's group size (%zu)", unit_k, L);
