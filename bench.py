@@ -225,9 +225,13 @@ class PcdStep:
             t0 = time.time()
             inst = synthetic.make_groth16_instance(ctx, pairing, lg, seed=seed_base + pairing + 10 * lg)
             g = pcd_b200.Groth16(ctx, pairing)
+            win = os.environ.get("PCD_WINDOW_" + label.upper())  # development aid: table window of one proof's key
+            if win:
+                ctx.set_msm_window(int(win))
             idx = g.index(pcd_b200.ProvingKey(pairing=pairing, **inst["pk"]),
                           pcd_b200.ConstraintMatrices(pairing, inst["num_inputs"], inst["num_witness"], inst["A"],
                                                       inst["B"], inst["C"]), precompute=True)
+            ctx.set_msm_window(0)
             z_host = torch.from_numpy(inst["z"].view(np.int64)).pin_memory()
             self.parts.append(dict(label=label, pairing=pairing, log_n=lg, inst=inst, g=g, idx=idx, z_host=z_host,
                                    z_dev=z_host.to(dev), nvars=inst["num_inputs"] + inst["num_witness"]))

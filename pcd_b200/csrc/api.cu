@@ -36,8 +36,10 @@ int msm_auto_window_c(size_t n, int shared) {
     c = lg <= 18 ? lg : lg - 1;
     // ~10^3 points (the default-circuit proofs of a PCD step): the walk of one thread per bucket has nothing to
     // parallelise over, so use FEW buckets and let every bucket go down the chunked (CTA tree sum) path: measured on
-    // the whole 2^10 proof c = 10: 1.78 / 2.10 ms (MNT4 / MNT6), 7: 1.37 / 1.70, 6: 1.32 / 1.79, 4: 1.31 / 2.11
-    if (lg <= 12) c = 7;
+    // the whole 2^10 proof c = 10: 1.78 / 2.10 ms (MNT4 / MNT6), 7: 1.37 / 1.70, 6: 1.32 / 1.79, 4: 1.31 / 2.11; measured
+    // again with lane-cooperative heavy-bucket trees and two buckets per reduction group (inside the PCD step): c = 9:
+    // 1.32 / 1.47, 8: 1.36 / 1.53, 7: 0.92 / 1.10, 6: 0.88 / 1.03, 5: 0.89 / 1.04
+    if (lg <= 12) c = 6;
     if (c < 6) c = 6;
     if (c > 21) c = 21;
   } else {
@@ -314,8 +316,12 @@ int pcdgpu_bases_upload(pcdgpu_ctx* ctx, int curve, const void* bases, size_t n,
     // reduction): 2^18 main proof c = 15: 8.41 ms, 16: 8.34, 17: 8.90, 18: 10.1; 2^16 helper proof (G2 over Fq3) c = 14:
     // 9.4 ms, 15: 6.27, 16: 7.50, 17: 8.4 (below c = 15 the accumulation runs out of buckets to spread over the SMs).
     b->c = ctx->msm_window > 0 ? ctx->msm_window : msm_auto_window_c(n, 1);
+    // Measured again at the end of round 2 inside the PCD step (unit buckets, lane-cooperative heavy-bucket trees;
+    // tools/probe_step.py with PCD_WINDOW_*): main 2^18 c = 13: 14.7 ms, 14: 9.9, 15: 6.25 - 6.45, 16: 6.57 - 6.68, 17: 6.99;
+    // helper 2^16 c = 13: 7.2, 14: 3.87, 15: 3.88 - 3.96, 16: 4.90.  Hence 15 for both (below it the cliff: too few buckets).
     if (ctx->msm_window <= 0 && ctx->key_upload) {
-      if (b->c >= 18) b->c -= 2;
+      if (b->c == 18 && n < ((size_t)3 << 17)) b->c = 15;  // ~2^18 points
+      else if (b->c >= 18) b->c -= 2;
       else if (b->c >= 16) b->c -= 1;
     }
     b->nwin = msm_num_windows_c(b->c);
