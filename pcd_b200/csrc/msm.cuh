@@ -867,6 +867,11 @@ static int msm_run(pcdgpu_ctx* ctx, const void* d_bases, const void* d_scalars, 
   static const int split_env = getenv("PCDGPU_ACC_SPLIT") ? atoi(getenv("PCDGPU_ACC_SPLIT")) : 0;  // development aid
   const u32 max_split = split_env > 0 ? (u32)split_env : (u32)MSM_MAX_SPLIT;
   while (split < max_split && nbuckets * split < 6 * acc_grid * ITEMS_PER_CTA && avg_entries / (2 * split) >= 8) split *= 2;
+  // ... and eight parts when four leave fewer than two work items per resident thread (2^18-point key tables with
+  // c = 15: 17 K buckets x 4 on 38 - 57 K threads ran as 1.2 - 1.8 "waves" of ~80-entry items, the last of them alone)
+  if (split_env <= 0 && split == (u32)MSM_MAX_SPLIT && nbuckets * split < 2 * acc_grid * ITEMS_PER_CTA &&
+      avg_entries / (4 * split) >= 8)
+    split *= 2;
   if (acc_grid > (nbuckets * split + ITEMS_PER_CTA - 1) / ITEMS_PER_CTA) acc_grid = (nbuckets * split + ITEMS_PER_CTA - 1) / ITEMS_PER_CTA;
   // inside a proof the CTAs retire after ~a quarter of a millisecond of work (quantum entries per lane) so that the
   // other lanes' kernels are not starved by a persistent grid; a lone MSM keeps the persistent form
